@@ -1,0 +1,862 @@
+// svb200.cu — C ABI (include/svb200.h) and substep driver of the B200 MPM back end.
+//
+// Mirrors the reference's back-end boundary: CpuState::from_io_state / produce_next_state /
+// to_io_state (/root/reference/rust/crates/cpu/src/cpu_state.rs:26-197) with the phase order of
+// cpu/src/phase/mod.rs:27-41.  There is NO CPU fallback: every per-particle / per-node phase is a
+// CUDA kernel from svb_kernels.cuh; the host only sequences launches, keeps the f64 clock and the
+// adaptive time-step history, and builds the (tiny) collider topology / BVH per keyframe.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/svb200.h"
+#include "svb_host.h"
+#include "svb_kernels.cuh"
+#include "svb_sort.cuh"
+
+using namespace svb;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t want, bool keep = false) {
+    if (want <= bytes) return cudaSuccess;
+    const size_t grow = want + want / 4 + 256;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, grow);
+    if (e != cudaSuccess) return e;
+    if (keep && p && bytes) cudaMemcpy(q, p, bytes, cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    p = q;
+    bytes = grow;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum Stage : int { ST_MESH = 0, ST_FORCE, ST_KEYS, ST_SORT, ST_PERMUTE, ST_ACTIVATE, ST_LIMIT, ST_P2G, ST_G2P, ST_ADVANCE, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"mesh_interpolate", "collide_force", "bin_keys", "radix_sort", "permute", "activate_blocks", "limit_time_step", "p2g", "g2p", "advance"};
+
+}  // namespace
+
+struct SvbHandle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  SvbConsts consts{};
+  SimConsts K{};
+  uint32_t n = 0;
+  size_t cap = 0;
+  DevBuf pbuf[2];
+  int cur = 0;
+  DevBuf energy;
+  std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
+  DevBuf keys[2], idx[2], sort_tmp;
+  DevBuf group_start, group_touch, nbr, cand[2], active_keys, grid, tile_count, node_mask, node_offset;
+  size_t group_cap = 0, active_cap = 0;
+  DevBuf scalars, layout, layer_slots, slot_rank, layer_bits;
+  StepScalars* h_scalars = nullptr;  // pinned
+  BinLayout* h_layout = nullptr;     // pinned
+  int sort_bits = 0;                 // end_bit used for the particle sort (lagged knowledge of the layout)
+  uint32_t n_groups = 0, n_live = 0, n_active = 0;
+  BinLayout last_layout{};
+  bool have_grid = false;
+  bool store_grid = false, masks_valid = false;
+
+  // collider input
+  svbh::HostTopology topo;
+  bool have_topology = false, have_keyframes = false;
+  uint64_t frame = 0;
+  float gravity_a[3] = {0, 0, 0}, gravity_b[3] = {0, 0, 0};
+  bool has_b = false, has_goals = false;
+  DevBuf d_tri, d_opp, d_tri_collider, d_fan_offsets, d_fan_tris;
+  DevBuf d_va, d_vb, d_vvel, d_fric_a, d_fric_b, d_damp_a, d_damp_b, d_vpos, d_vnormal, d_tnormal, d_tfric, d_tdamp;
+  DevBuf d_node_min, d_node_max, d_node_first, d_node_count, d_children, d_tri_indices;
+  DevBuf d_flags_a, d_flags_b, d_goal_a, d_goal_b;
+  svbh::FlatBvh bvh;
+  MeshDev M{};
+
+  double time = 0;
+  svbh::AdaptiveTimeStep adaptive;
+  uint64_t substeps = 0;
+  uint32_t status = 0;
+  uint64_t launches = 0;
+  std::string last_error;
+
+  // snapshot
+  DevBuf snap_p, snap_e;
+  double snap_time = 0;
+  svbh::AdaptiveTimeStep snap_adaptive;
+  uint64_t snap_substeps = 0;
+  bool have_snapshot = false;
+
+  // stage timing
+  bool timing = false;
+  cudaEvent_t ev[ST_COUNT + 1] = {};
+  float stage_ms[ST_COUNT] = {};
+  int last_stage = -1;
+
+  ParticleBuf P(int which) const { return ParticleBuf{pbuf[which].as<uint32_t>(), cap}; }
+  ParticleBuf Pc() const { return P(cur); }
+};
+
+namespace {
+
+int fail(SvbHandle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->last_error = buf;
+  return code;
+}
+#define CK(call)                                                                                           \
+  do {                                                                                                     \
+    cudaError_t e_ = (call);                                                                               \
+    if (e_ != cudaSuccess) return fail(h, SVB_CUDA_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCH_CHECK()                                                                                     \
+  do {                                                                                                     \
+    ++h->launches;                                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                                                   \
+    if (e_ != cudaSuccess) return fail(h, SVB_CUDA_ERROR, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+inline uint32_t blocks_for(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
+
+void stage_begin(SvbHandle* h, int st) {
+  if (!h->timing) return;
+  cudaEventRecord(h->ev[0], h->stream);
+  h->last_stage = st;
+}
+void stage_end(SvbHandle* h) {
+  if (!h->timing || h->last_stage < 0) return;
+  cudaEventRecord(h->ev[1], h->stream);
+  cudaEventSynchronize(h->ev[1]);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+  h->stage_ms[h->last_stage] += ms;
+  h->last_stage = -1;
+}
+
+int upload_array(SvbHandle* h, DevBuf& b, const void* src, size_t bytes) {
+  CK(b.ensure(bytes ? bytes : 4));
+  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int ensure_group_capacity(SvbHandle* h, size_t groups) {
+  if (groups <= h->group_cap) return 0;
+  const size_t c = groups + groups / 2 + 1024;
+  CK(h->group_start.ensure((c + 1) * 4));
+  CK(h->group_touch.ensure(c * 4));
+  CK(h->nbr.ensure(c * 8 * 4));
+  CK(h->cand[0].ensure(c * 8 * 8));
+  CK(h->cand[1].ensure(c * 8 * 8));
+  h->group_cap = c;
+  return 0;
+}
+int ensure_active_capacity(SvbHandle* h, size_t active) {
+  if (active <= h->active_cap) return 0;
+  const size_t c = active + active / 2 + 1024;
+  CK(h->active_keys.ensure(c * 8));
+  CK(h->grid.ensure(c * 64 * 16));
+  h->active_cap = c;
+  return 0;
+}
+
+int set_device(SvbHandle* h) {
+  CK(cudaSetDevice(h->device));
+  return 0;
+}
+
+// ---- one substep: the 12 phases of cpu/src/phase/mod.rs:27-41 in the reference's order
+int substep(SvbHandle* h, bool adaptive_steps) {
+  cudaStream_t s = h->stream;
+  const uint32_t n = h->n;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  BinLayout* L = h->layout.as<BinLayout>();
+  const float hh = h->K.h;
+
+  if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
+
+  // -- InterpolateInput (interpolate_input.rs:18-107; frame factor xpu/src/frame_input.rs:266-278)
+  const double frame_time = h->time * (double)h->consts.frames_per_second;
+  const uint64_t frame_low = (uint64_t)std::floor(frame_time);
+  if (frame_low != h->frame) return fail(h, SVB_FRAME_INPUT, "Wrong frame loaded: %llu (need %llu)", (unsigned long long)h->frame, (unsigned long long)frame_low);
+  const float factor_b = (float)std::fmod(frame_time, 1.0);
+  const float factor_a = 1.f - factor_b;
+  const float* gb = h->has_b ? h->gravity_b : h->gravity_a;
+  float g[3];
+  for (int k = 0; k < 3; ++k) g[k] = factor_a * h->gravity_a[k] + factor_b * gb[k];
+  const bool has_mesh = h->topo.n_triangles > 0;
+  if (has_mesh) {
+    stage_begin(h, ST_MESH);
+    const uint32_t m = std::max(h->topo.n_vertices * 3, h->topo.n_triangles);
+    k_mesh_lerp<<<blocks_for(m, 256), 256, 0, s>>>(h->M, factor_b);
+    LAUNCH_CHECK();
+    k_mesh_tri_normals<<<blocks_for(h->topo.n_triangles, 256), 256, 0, s>>>(h->M);
+    LAUNCH_CHECK();
+    k_mesh_vertex_normals<<<blocks_for(h->topo.n_vertices, 256), 256, 0, s>>>(h->M);
+    LAUNCH_CHECK();
+    stage_end(h);
+  }
+  if (n == 0) {
+    h->time += (double)h->adaptive.allowed();
+    ++h->substeps;
+    return 0;
+  }
+
+  // -- Collide + ExternalForce (collide.rs, external_force.rs) in the current order; per particle, so
+  //    running them before the re-bin is equivalent to the reference's Sort -> Collide -> Force.
+  stage_begin(h, ST_FORCE);
+  {
+    StepScalars init{};
+    init.n = n;
+    for (int k = 0; k < 3; ++k) { init.bbox_min[k] = INT32_MAX; init.bbox_max[k] = INT32_MIN; }
+    init.min_sound_key = INT32_MAX; init.min_isolated_key = INT32_MAX; init.max_velocity_key = INT32_MIN; init.min_deformation_key = INT32_MAX;
+    init.status = 0;
+    *h->h_scalars = init;
+    CK(cudaMemcpyAsync(S, h->h_scalars, sizeof(StepScalars), cudaMemcpyHostToDevice, s));
+    if (has_mesh) CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
+  }
+  const float dt_force = h->adaptive.allowed();
+  GoalDev G{nullptr, nullptr, nullptr, nullptr};
+  if (h->has_goals) {
+    G.flags_a = h->d_flags_a.as<uint32_t>();
+    G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : G.flags_a;
+    G.goal_a = h->d_goal_a.as<float>();
+    G.goal_b = h->has_b ? h->d_goal_b.as<float>() : G.goal_a;
+  }
+  if (has_mesh) k_force<true><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, h->layer_slots.as<unsigned long long>(), n, dt_force, g[0], g[1], g[2], factor_b);
+  else k_force<false><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, h->layer_slots.as<unsigned long long>(), n, dt_force, g[0], g[1], g[2], factor_b);
+  LAUNCH_CHECK();
+  stage_end(h);
+
+  // -- Sort (sort.rs) : bin keys -> radix sort -> gather
+  stage_begin(h, ST_KEYS);
+  k_layout<<<1, 1024, 0, s>>>(S, L, h->layer_slots.as<unsigned long long>(), h->slot_rank.as<uint32_t>(), h->layer_bits.as<uint32_t>());
+  LAUNCH_CHECK();
+  stage_end(h);
+  if (h->sort_bits == 0) {  // first substep: learn the key width
+    CK(cudaMemcpyAsync(h->h_layout, L, sizeof(BinLayout), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->sort_bits = std::min(64, h->h_layout->total_bits + 1 + 3);
+  }
+  const uint32_t n_tiles = blocks_for(n, SCAN_TILE);
+  CK(h->tile_count.ensure((size_t)std::max<uint32_t>(n_tiles, 1024) * 4));
+  for (int attempt = 0;; ++attempt) {
+    stage_begin(h, ST_KEYS);
+    k_keys<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), L, h->layer_slots.as<unsigned long long>(), h->slot_rank.as<uint32_t>(), hh, n, h->keys[0].as<unsigned long long>(),
+                                             h->idx[0].as<uint32_t>());
+    LAUNCH_CHECK();
+    stage_end(h);
+    stage_begin(h, ST_SORT);
+    {
+      int rc = sort_pairs_u64(h->sort_tmp.p, h->sort_tmp.bytes, h->keys[0].as<unsigned long long>(), h->keys[1].as<unsigned long long>(), h->idx[0].as<uint32_t>(),
+                              h->idx[1].as<uint32_t>(), n, h->sort_bits, s, &h->launches);
+      if (rc != 0) return fail(h, SVB_CUDA_ERROR, "radix sort failed: %s", cudaGetErrorString((cudaError_t)rc));
+    }
+    stage_end(h);
+    stage_begin(h, ST_PERMUTE);
+    k_permute<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->idx[1].as<uint32_t>(), n);
+    LAUNCH_CHECK();
+    h->cur ^= 1;
+    stage_end(h);
+    // -- UpdateGridNodes (update_grid_nodes.rs) : runs of equal (block, layer)
+    stage_begin(h, ST_ACTIVATE);
+    k_flag_count<0><<<n_tiles, SCAN_THREADS, 0, s>>>(h->keys[1].as<unsigned long long>(), nullptr, n, L, h->tile_count.as<uint32_t>(), S);
+    LAUNCH_CHECK();
+    k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_count.as<uint32_t>(), n_tiles, &S->n_groups);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->h_layout, L, sizeof(BinLayout), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stage_end(h);
+    if (h->h_scalars->status & 0x80000000u) return fail(h, SVB_KEY_RANGE, "live particles span too many grid blocks for a 63-bit bin key");
+    if (h->h_layout->total_bits + 1 <= h->sort_bits) break;
+    if (attempt > 2) return fail(h, SVB_KEY_RANGE, "bin key width did not settle");
+    h->sort_bits = std::min(64, h->h_layout->total_bits + 1 + 3);  // the bounding box outgrew the lagged key width: redo the re-bin
+  }
+  h->sort_bits = std::min(64, h->h_layout->total_bits + 1 + 3);
+  h->last_layout = *h->h_layout;
+  h->n_groups = h->h_scalars->n_groups;
+  h->n_live = h->h_scalars->n_live;
+  h->status |= h->h_scalars->status & 0xffffu;
+  if (int rc = ensure_group_capacity(h, h->n_groups)) return rc;
+
+  stage_begin(h, ST_ACTIVATE);
+  const unsigned long long* skeys = h->keys[1].as<unsigned long long>();
+  uint32_t* group_start = h->group_start.as<uint32_t>();
+  if (h->n_groups) {
+    k_flag_write<0><<<n_tiles, SCAN_THREADS, 0, s>>>(skeys, nullptr, n, L, h->tile_count.as<uint32_t>(), group_start, nullptr, (uint32_t)h->group_cap, S);
+    LAUNCH_CHECK();
+    k_group_touch<<<std::min<uint32_t>(blocks_for((uint64_t)h->n_groups * 32, 256), 148 * 8), 256, 0, s>>>(skeys, group_start, L, S, h->cand[0].as<unsigned long long>(),
+                                                                                                          h->group_touch.as<uint32_t>());
+    LAUNCH_CHECK();
+    const uint32_t n_cand = h->n_groups * 8;
+    {
+      int rc = sort_keys_u64(h->sort_tmp.p, h->sort_tmp.bytes, h->cand[0].as<unsigned long long>(), h->cand[1].as<unsigned long long>(), n_cand, 64, s, &h->launches);
+      if (rc != 0) return fail(h, SVB_CUDA_ERROR, "candidate sort failed: %s", cudaGetErrorString((cudaError_t)rc));
+    }
+    const uint32_t c_tiles = blocks_for(n_cand, SCAN_TILE);
+    CK(h->tile_count.ensure((size_t)std::max<uint32_t>(c_tiles, 1024) * 4));
+    k_flag_count<1><<<c_tiles, SCAN_THREADS, 0, s>>>(h->cand[1].as<unsigned long long>(), nullptr, n_cand, L, h->tile_count.as<uint32_t>(), S);
+    LAUNCH_CHECK();
+    k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_count.as<uint32_t>(), c_tiles, &S->n_active);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&h->h_scalars->n_active, &S->n_active, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    h->n_active = h->h_scalars->n_active;
+    if (int rc = ensure_active_capacity(h, h->n_active)) return rc;
+    k_flag_write<1><<<c_tiles, SCAN_THREADS, 0, s>>>(h->cand[1].as<unsigned long long>(), nullptr, n_cand, L, h->tile_count.as<uint32_t>(), nullptr,
+                                                      h->active_keys.as<unsigned long long>(), (uint32_t)h->active_cap, S);
+    LAUNCH_CHECK();
+    k_neighbors<<<std::min<uint32_t>(blocks_for((uint64_t)n_cand, 256), 148 * 16), 256, 0, s>>>(skeys, group_start, h->group_touch.as<uint32_t>(), L, S,
+                                                                                                h->active_keys.as<unsigned long long>(), h->nbr.as<int>());
+    LAUNCH_CHECK();
+    CK(cudaMemsetAsync(h->grid.p, 0, (size_t)h->n_active * 64 * 16, s));
+    h->masks_valid = false;
+    if (h->store_grid) {
+      CK(h->node_mask.ensure((size_t)h->n_active * 8));
+      CK(cudaMemsetAsync(h->node_mask.p, 0, (size_t)h->n_active * 8, s));
+      k_touch_nodes<<<std::min<uint32_t>(blocks_for((uint64_t)h->n_groups * 32, 256), 148 * 8), 256, 0, s>>>(h->Pc(), group_start, h->nbr.as<int>(), S, hh,
+                                                                                                            h->node_mask.as<unsigned long long>());
+      LAUNCH_CHECK();
+      h->masks_valid = true;
+    }
+  } else {
+    h->n_active = 0;
+  }
+  h->have_grid = true;
+  stage_end(h);
+
+  // -- LimitTimeStepBeforeForce (limit_time_step.rs:25-33)
+  if (adaptive_steps) {
+    stage_begin(h, ST_LIMIT);
+    k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, hh, n);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stage_end(h);
+    const bool any = h->h_scalars->live_count > 0;
+    h->adaptive.has_sound = h->adaptive.has_isolated = any;
+    if (any) {
+      h->adaptive.by_sound = total_unkey(h->h_scalars->min_sound_key);
+      h->adaptive.by_isolated = total_unkey(h->h_scalars->min_isolated_key);
+    }
+    h->adaptive.push_current_limit();
+    if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
+  }
+
+  // -- ScatterMomentum (scatter_momentum.rs)
+  const float dt_scatter = h->adaptive.allowed();
+  const uint32_t persistent = std::max<uint32_t>(1, std::min<uint32_t>(h->n_groups, 148 * 6));
+  stage_begin(h, ST_P2G);
+  if (h->n_groups) {
+    k_p2g<<<persistent, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), group_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt_scatter);
+    LAUNCH_CHECK();
+  }
+  stage_end(h);
+
+  // -- MeldGrid + CollectVelocity (+ AdvanceParticles + CullParticles when dt is already known)
+  const uint32_t g2p_grid = std::max<uint32_t>(1, std::min<uint32_t>(h->n_groups, 148 * 12));
+  if (!adaptive_steps) {
+    stage_begin(h, ST_G2P);
+    if (h->n_groups) {
+      k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), group_start, h->nbr.as<int>(), S, h->grid.as<float4>(), h->active_keys.as<unsigned long long>(),
+                                                         h->layer_bits.as<uint32_t>(), L, h->K, dt_scatter);
+      LAUNCH_CHECK();
+    }
+    stage_end(h);
+  } else {
+    stage_begin(h, ST_G2P);
+    if (h->n_groups) {
+      k_g2p<false, true><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), group_start, h->nbr.as<int>(), S, h->grid.as<float4>(), h->active_keys.as<unsigned long long>(),
+                                                         h->layer_bits.as<uint32_t>(), L, h->K, dt_scatter);
+      LAUNCH_CHECK();
+    }
+    // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
+    CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stage_end(h);
+    const bool any = h->n_live > 0;
+    const float max_vel = any ? total_unkey(h->h_scalars->max_velocity_key) : 0.f;
+    h->adaptive.has_velocity = any && max_vel != 0.f;
+    if (h->adaptive.has_velocity) h->adaptive.by_velocity = 0.5f * hh / max_vel;
+    h->adaptive.has_deformation = any;
+    if (any) h->adaptive.by_deformation = total_unkey(h->h_scalars->min_deformation_key);
+    h->adaptive.push_current_limit();
+    if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
+    stage_begin(h, ST_ADVANCE);
+    k_advance<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, h->K, n, h->adaptive.allowed());
+    LAUNCH_CHECK();
+    stage_end(h);
+  }
+  h->time += (double)h->adaptive.allowed();
+  ++h->substeps;
+  return 0;
+}
+
+int read_status(SvbHandle* h) {
+  StepScalars* S = h->scalars.as<StepScalars>();
+  CK(cudaMemcpyAsync(&h->h_scalars->status, &S->status, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->status |= h->h_scalars->status & 0xffffu;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t svb_available_devices(char* out, size_t cap) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) return SVB_CUDA_ERROR;
+  std::string s;
+  for (int d = 0; d < count; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) != cudaSuccess) return SVB_CUDA_ERROR;
+    s += std::to_string(d) + ": " + p.name + "\n";
+  }
+  if (out && cap) {
+    const size_t m = std::min(cap - 1, s.size());
+    std::memcpy(out, s.data(), m);
+    out[m] = 0;
+  }
+  return count;
+}
+
+int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, int32_t device, SvbHandle** out) {
+  if (!consts || !p || !out) return SVB_BAD_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return SVB_CUDA_ERROR;  // no CPU fallback
+  if (device < 0 || device >= count) return SVB_BAD_ARGUMENT;
+  if (p->n > 0xfffffff0ull) return SVB_BAD_ARGUMENT;
+  SvbHandle* h = new SvbHandle();
+  *out = h;  // returned even on failure so the caller can read svb_last_error, then svb_destroy
+  h->device = device;
+  h->consts = *consts;
+  h->K.h = consts->grid_node_size / consts->simulation_scale;                 // header.rs:36-38
+  h->K.leaf_size = consts->leaf_size;                                         // unscaled
+  h->K.accept_distance = h->K.h * 2.f;                                        // header.rs:60-62
+  h->K.forget_distance = h->K.h * 2.2f;                                       // header.rs:64-66
+  for (int k = 0; k < 3; ++k) {
+    h->K.domain_min[k] = consts->domain_min[k] / consts->simulation_scale;    // header.rs:40-58
+    h->K.domain_max[k] = consts->domain_max[k] / consts->simulation_scale;
+  }
+  h->time = time;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  CK(cudaMallocHost(&h->h_scalars, sizeof(StepScalars)));
+  CK(cudaMallocHost(&h->h_layout, sizeof(BinLayout)));
+  CK(cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+  const uint32_t n = (uint32_t)p->n;
+  h->n = n;
+  h->cap = ((size_t)std::max<uint32_t>(n, 1) + 63) & ~(size_t)63;
+  for (int b = 0; b < 2; ++b) {
+    CK(h->pbuf[b].ensure(h->cap * NFIELDS * 4));
+    CK(h->keys[b].ensure(h->cap * 8));
+    CK(h->idx[b].ensure(h->cap * 4));
+  }
+  CK(h->energy.ensure(h->cap * 4));
+  CK(h->scalars.ensure(sizeof(StepScalars)));
+  CK(h->layout.ensure(sizeof(BinLayout)));
+  CK(h->layer_slots.ensure(LAYER_SLOTS * 8));
+  CK(h->slot_rank.ensure(LAYER_SLOTS * 4));
+  CK(h->layer_bits.ensure(LAYER_CAP * 4));
+  CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, h->stream));
+  CK(cudaMemsetAsync(h->pbuf[0].p, 0, h->cap * NFIELDS * 4, h->stream));
+  CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
+  CK(h->sort_tmp.ensure(sort_temp_bytes(h->cap)));
+  if (int rc = ensure_group_capacity(h, (size_t)n / 64 + 1024)) return rc;
+  if (int rc = ensure_active_capacity(h, (size_t)n / 32 + 1024)) return rc;
+
+  if (n) {
+    if (!p->flags || !p->mass || !p->initial_volume || !p->mu_or_bulk_modulus || !p->lambda_or_exponent || !p->positions || !p->position_gradients || !p->velocities ||
+        !p->velocity_gradients)
+      return fail(h, SVB_BAD_ARGUMENT, "svb_create: a required particle array is NULL");
+    // stage each wire array through the spare particle buffer and transpose it into the SoA
+    ParticleBuf P = h->Pc();
+    float* stagef = h->pbuf[1].as<float>();
+    const uint32_t blocks = blocks_for(n, 256);
+    auto scalar = [&](const void* src, int field) -> int {
+      if (!src) return 0;
+      CK(cudaMemcpyAsync(P.u(field), src, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+      return 0;
+    };
+    auto vec = [&](const float* src, int field, int k) -> int {
+      if (!src) return 0;
+      CK(cudaMemcpyAsync(stagef, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
+      if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(stagef, P.f(field), h->cap, n);
+      else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(stagef, P.f(field), h->cap, n);
+      LAUNCH_CHECK();
+      CK(cudaStreamSynchronize(h->stream));
+      return 0;
+    };
+    int rc = 0;
+    if ((rc = scalar(p->flags, PFLAGS)) || (rc = scalar(p->mass, PMASS)) || (rc = scalar(p->initial_volume, PVOL)) || (rc = scalar(p->mu_or_bulk_modulus, PP0)) ||
+        (rc = scalar(p->lambda_or_exponent, PP1)) || (rc = scalar(p->sand_alpha, PALPHA)) || (rc = scalar(p->viscosity_dynamic, PVD)) || (rc = scalar(p->viscosity_bulk, PVB)) ||
+        (rc = scalar(p->collider_bits, PBITS)) || (rc = vec(p->positions, PX, 3)) || (rc = vec(p->velocities, PV, 3)) || (rc = vec(p->velocity_gradients, PC, 9)) ||
+        (rc = vec(p->position_gradients, PF, 9)))
+      return rc;
+    if (p->elastic_energies) CK(cudaMemcpyAsync(h->energy.p, p->elastic_energies, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_iota<<<blocks, 256, 0, h->stream>>>(P.u(PORIG), n, 0);
+    LAUNCH_CHECK();
+    h->initial_positions.assign((size_t)n * 3, 0.f);
+    if (p->initial_positions) std::memcpy(h->initial_positions.data(), p->initial_positions, (size_t)n * 12);
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  // an empty collider set is a valid input (the reference builds an empty Topology)
+  h->topo = svbh::HostTopology();
+  h->have_topology = true;
+  return 0;
+}
+
+void svb_destroy(SvbHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->keys[0], &h->keys[1], &h->idx[0], &h->idx[1], &h->sort_tmp, &h->group_start, &h->group_touch, &h->nbr, &h->cand[0],
+                   &h->cand[1], &h->active_keys, &h->grid, &h->tile_count, &h->node_mask, &h->node_offset, &h->scalars, &h->layout, &h->layer_slots, &h->slot_rank, &h->layer_bits,
+                   &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
+                   &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
+                   &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e};
+  for (DevBuf* b : all) b->release();
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_layout) cudaFreeHost(h->h_layout);
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t svb_set_topology(SvbHandle* h, uint32_t n_colliders, const uint32_t* num_vertices, const uint32_t* num_triangles, const uint32_t* triangles) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (n_colliders > 16) return fail(h, SVB_TOO_MANY_COLLIDERS, "too many colliders: %u (at most 16)", n_colliders);
+  if (int rc = set_device(h)) return rc;
+  const std::string err = h->topo.build(n_colliders, num_vertices, num_triangles, triangles);
+  if (!err.empty()) {
+    h->topo = svbh::HostTopology();
+    return fail(h, SVB_BAD_MESH, "Something is wrong with the mesh inputs: %s", err.c_str());
+  }
+  const auto& T = h->topo;
+  int rc = 0;
+  if ((rc = upload_array(h, h->d_tri, T.tri.data(), T.tri.size() * 4)) || (rc = upload_array(h, h->d_opp, T.opp.data(), T.opp.size() * 4)) ||
+      (rc = upload_array(h, h->d_tri_collider, T.tri_collider.data(), T.tri_collider.size() * 4)) ||
+      (rc = upload_array(h, h->d_fan_offsets, T.fan_offsets.data(), T.fan_offsets.size() * 4)) || (rc = upload_array(h, h->d_fan_tris, T.fan_tris.data(), T.fan_tris.size() * 4)))
+    return rc;
+  CK(h->d_vpos.ensure((size_t)T.n_vertices * 12 + 4));
+  CK(h->d_vnormal.ensure((size_t)T.n_vertices * 12 + 4));
+  CK(h->d_tnormal.ensure((size_t)T.n_triangles * 12 + 4));
+  CK(h->d_tfric.ensure((size_t)T.n_triangles * 4 + 4));
+  CK(h->d_tdamp.ensure((size_t)T.n_triangles * 4 + 4));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_topology = true;
+  h->have_keyframes = false;
+  return 0;
+}
+
+int32_t svb_set_keyframes(SvbHandle* h, uint64_t frame, const SvbKeyframe* a, const SvbKeyframe* b) {
+  if (!h || !a) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  const auto& T = h->topo;
+  const uint32_t nv = T.n_vertices, nt = T.n_triangles, n = h->n;
+  if (nv && (!a->vertex_positions || (b && !b->vertex_positions))) return fail(h, SVB_BAD_ARGUMENT, "keyframe lacks vertex_positions");
+  h->frame = frame;
+  h->has_b = b != nullptr;
+  for (int k = 0; k < 3; ++k) {
+    h->gravity_a[k] = a->gravity[k];
+    h->gravity_b[k] = b ? b->gravity[k] : a->gravity[k];
+  }
+  int rc = 0;
+  // goals (external_force.rs:38-41): only uploaded when some particle has HAS_GOAL in keyframe a
+  h->has_goals = false;
+  if (a->particle_flags && a->particle_goal_positions && n) {
+    bool any = false;
+    for (uint32_t i = 0; i < n && !any; ++i) any = (a->particle_flags[i] & F_HAS_GOAL) != 0;
+    if (any) {
+      if ((rc = upload_array(h, h->d_flags_a, a->particle_flags, (size_t)n * 4)) || (rc = upload_array(h, h->d_goal_a, a->particle_goal_positions, (size_t)n * 12))) return rc;
+      if (b) {
+        if (!b->particle_flags || !b->particle_goal_positions) return fail(h, SVB_BAD_ARGUMENT, "keyframe b lacks goal arrays");
+        if ((rc = upload_array(h, h->d_flags_b, b->particle_flags, (size_t)n * 4)) || (rc = upload_array(h, h->d_goal_b, b->particle_goal_positions, (size_t)n * 12))) return rc;
+      }
+      h->has_goals = true;
+    }
+  }
+  MeshDev M{};
+  M.n_vertices = nv; M.n_triangles = nt; M.n_colliders = T.n_colliders;
+  if (nt) {
+    std::vector<float> zeros(nt, 0.f);
+    const float* fa = a->triangle_frictions ? a->triangle_frictions : zeros.data();
+    const float* da = a->triangle_dampings ? a->triangle_dampings : zeros.data();
+    const float* fb = b ? (b->triangle_frictions ? b->triangle_frictions : zeros.data()) : fa;
+    const float* db = b ? (b->triangle_dampings ? b->triangle_dampings : zeros.data()) : da;
+    const float* va = a->vertex_positions;
+    const float* vb = b ? b->vertex_positions : a->vertex_positions;
+    // linear_vertex_velocities (xpu/src/frame_input.rs:334-348)
+    std::vector<float> vvel((size_t)nv * 3, 0.f);
+    if (b)
+      for (size_t i = 0; i < (size_t)nv * 3; ++i) vvel[i] = (vb[i] - va[i]) * (float)h->consts.frames_per_second;
+    if ((rc = upload_array(h, h->d_va, va, (size_t)nv * 12)) || (rc = upload_array(h, h->d_vb, vb, (size_t)nv * 12)) || (rc = upload_array(h, h->d_vvel, vvel.data(), (size_t)nv * 12)) ||
+        (rc = upload_array(h, h->d_fric_a, fa, (size_t)nt * 4)) || (rc = upload_array(h, h->d_fric_b, fb, (size_t)nt * 4)) || (rc = upload_array(h, h->d_damp_a, da, (size_t)nt * 4)) ||
+        (rc = upload_array(h, h->d_damp_b, db, (size_t)nt * 4)))
+      return rc;
+    // update_bvh (xpu/src/frame_input.rs:350-390)
+    h->bvh = svbh::BvhBuilder::build(T, va, b ? vb : nullptr, h->K.forget_distance, h->consts.leaf_size, h->consts.leaf_threshold);
+    const auto& B = h->bvh;
+    if ((rc = upload_array(h, h->d_node_min, B.node_min.data(), B.node_min.size() * 4)) || (rc = upload_array(h, h->d_node_max, B.node_max.data(), B.node_max.size() * 4)) ||
+        (rc = upload_array(h, h->d_node_first, B.node_first.data(), B.node_first.size() * 4)) || (rc = upload_array(h, h->d_node_count, B.node_count.data(), B.node_count.size() * 4)) ||
+        (rc = upload_array(h, h->d_children, B.children.data(), B.children.size() * 4)) || (rc = upload_array(h, h->d_tri_indices, B.tri_indices.data(), B.tri_indices.size() * 4)))
+      return rc;
+    CK(cudaStreamSynchronize(h->stream));  // the host vectors above go out of scope
+    M.tri = h->d_tri.as<uint32_t>(); M.opp = h->d_opp.as<uint32_t>(); M.tri_collider = h->d_tri_collider.as<uint32_t>();
+    M.fan_offsets = h->d_fan_offsets.as<uint32_t>(); M.fan_tris = h->d_fan_tris.as<uint32_t>();
+    M.va = h->d_va.as<float>(); M.vb = h->d_vb.as<float>(); M.vvel = h->d_vvel.as<float>();
+    M.fric_a = h->d_fric_a.as<float>(); M.fric_b = h->d_fric_b.as<float>(); M.damp_a = h->d_damp_a.as<float>(); M.damp_b = h->d_damp_b.as<float>();
+    M.vpos = h->d_vpos.as<float>(); M.vnormal = h->d_vnormal.as<float>(); M.tnormal = h->d_tnormal.as<float>(); M.tfric = h->d_tfric.as<float>(); M.tdamp = h->d_tdamp.as<float>();
+    M.bvh_level = B.level; M.bvh_nodes = (int32_t)B.node_count.size();
+    M.node_min = h->d_node_min.as<int32_t>(); M.node_max = h->d_node_max.as<int32_t>(); M.node_first = h->d_node_first.as<int32_t>(); M.node_count = h->d_node_count.as<int32_t>();
+    M.children = h->d_children.as<int32_t>(); M.tri_indices = h->d_tri_indices.as<uint32_t>();
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->M = M;
+  h->have_keyframes = true;
+  return 0;
+}
+
+int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32_t adaptive_time_steps, const volatile int32_t* cancel, void (*progress)(void*, size_t), void* user) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (!h->have_keyframes) return fail(h, SVB_INPUT_MISSING, "At this point, interpolated input should be ready (svb_set_keyframes not called)");
+  if (int rc = set_device(h)) return rc;
+  h->adaptive.max_time_step = max_time_step;
+  h->status = 0;
+  if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
+  const double spf = 1.0 / (double)h->consts.frames_per_second;
+  while (h->time < target_time) {
+    if (cancel && *cancel) return fail(h, SVB_CANCELED, "The computation was canceled");
+    if (int rc = substep(h, adaptive_time_steps != 0)) return rc;
+    if (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED) break;
+    if (progress) progress(user, (size_t)(std::fmod(h->time, spf) * 1000.0));
+  }
+  if (int rc = read_status(h)) return rc;
+  if (h->status) {
+    if (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED) fail(h, 0, "Failed to compute the elastic energy of a particle (EnergyError::PositionGradientNonPositive)");
+    else fail(h, 0, "device status word 0x%x", h->status);
+    return (int32_t)h->status;
+  }
+  return 0;
+}
+
+int32_t svb_download(SvbHandle* h, SvbParticles* out) {
+  if (!h || !out) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  const uint32_t n = h->n;
+  out->n = n;
+  if (!n) return 0;
+  ParticleBuf P = h->Pc();
+  const uint32_t* orig = P.u(PORIG);
+  float* stagef = h->pbuf[h->cur ^ 1].as<float>();  // the spare buffer is free between substeps
+  const uint32_t blocks = blocks_for(n, 256);
+  auto field = [&](void* dst, const float* src_field, int k) -> int {
+    if (!dst) return 0;
+    if (k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, stagef, n);
+    else if (k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, stagef, n);
+    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, stagef, n);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(dst, stagef, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+  };
+  int rc = 0;
+  if ((rc = field(out->flags, P.f(PFLAGS), 1)) || (rc = field(out->mass, P.f(PMASS), 1)) || (rc = field(out->initial_volume, P.f(PVOL), 1)) ||
+      (rc = field(out->mu_or_bulk_modulus, P.f(PP0), 1)) || (rc = field(out->lambda_or_exponent, P.f(PP1), 1)) || (rc = field(out->sand_alpha, P.f(PALPHA), 1)) ||
+      (rc = field(out->viscosity_dynamic, P.f(PVD), 1)) || (rc = field(out->viscosity_bulk, P.f(PVB), 1)) || (rc = field(out->collider_bits, P.f(PBITS), 1)) ||
+      (rc = field(out->positions, P.f(PX), 3)) || (rc = field(out->velocities, P.f(PV), 3)) || (rc = field(out->velocity_gradients, P.f(PC), 9)) ||
+      (rc = field(out->position_gradients, P.f(PF), 9)) || (rc = field(out->elastic_energies, h->energy.as<float>(), 1)))
+    return rc;
+  if (out->initial_positions) std::memcpy(out->initial_positions, h->initial_positions.data(), (size_t)n * 12);
+  return 0;
+}
+
+static int build_node_masks(SvbHandle* h, uint32_t* total) {
+  *total = 0;
+  if (!h->have_grid || h->n_active == 0) return 0;
+  const uint32_t na = h->n_active;
+  CK(h->node_offset.ensure((size_t)(na + 1) * 4));
+  if (!h->masks_valid) {
+    // store_grid was off during the last substep: fall back to "node holds mass or momentum"
+    CK(h->node_mask.ensure((size_t)na * 8));
+    k_mask_from_values<<<na, 64, 0, h->stream>>>(h->grid.as<float4>(), h->node_mask.as<unsigned long long>());
+    LAUNCH_CHECK();
+  }
+  k_popc_masks<<<blocks_for(na, 256), 256, 0, h->stream>>>(h->node_mask.as<unsigned long long>(), h->node_offset.as<uint32_t>(), na);
+  LAUNCH_CHECK();
+  CK(h->tile_count.ensure(4096));
+  k_scan_tiles<<<1, 1024, 0, h->stream>>>(h->node_offset.as<uint32_t>(), na, h->tile_count.as<uint32_t>());
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(total, h->tile_count.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// The grid is the one of the last substep's P2G (positions before the last advance), like the
+// reference's `grid_nodes` after produce_next_state.  Emitted nodes = nodes with >= 1 contributor
+// (exact when the "store_grid" option was on during the substep; the reference additionally keeps
+// zero-mass nodes touched one substep earlier, SURVEY.md §8g.9 — those are not emitted).
+int64_t svb_grid_count(SvbHandle* h) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  uint32_t total = 0;
+  if (int rc = build_node_masks(h, &total)) return rc;
+  return (int64_t)total;
+}
+
+int32_t svb_download_grid(SvbHandle* h, SvbGrid* out) {
+  if (!h || !out) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  uint32_t total = 0;
+  if (int rc = build_node_masks(h, &total)) return rc;
+  if (out->n < total) return fail(h, SVB_BAD_ARGUMENT, "svb_download_grid: capacity %llu < %u nodes", (unsigned long long)out->n, total);
+  out->n = total;
+  if (!total) return 0;
+  DevBuf ids, bits, masses, vels;
+  CK(ids.ensure((size_t)total * 12));
+  CK(bits.ensure((size_t)total * 4));
+  CK(masses.ensure((size_t)total * 4));
+  CK(vels.ensure((size_t)total * 12));
+  k_emit_grid<<<h->n_active, 64, 0, h->stream>>>(h->grid.as<float4>(), h->active_keys.as<unsigned long long>(), h->layer_bits.as<uint32_t>(), h->layout.as<BinLayout>(),
+                                               h->node_mask.as<unsigned long long>(), h->node_offset.as<uint32_t>(), h->n_active, ids.as<int32_t>(), bits.as<uint32_t>(),
+                                               masses.as<float>(), vels.as<float>());
+  LAUNCH_CHECK();
+  if (out->node_ids) CK(cudaMemcpyAsync(out->node_ids, ids.p, (size_t)total * 12, cudaMemcpyDeviceToHost, h->stream));
+  if (out->collider_bits) CK(cudaMemcpyAsync(out->collider_bits, bits.p, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->masses) CK(cudaMemcpyAsync(out->masses, masses.p, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->velocities) CK(cudaMemcpyAsync(out->velocities, vels.p, (size_t)total * 12, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (out->contributor_counts)
+    for (uint32_t i = 0; i < total; ++i) out->contributor_counts[i] = 1;
+  ids.release(); bits.release(); masses.release(); vels.release();
+  return 0;
+}
+
+double svb_time(const SvbHandle* h) { return h ? h->time : 0.0; }
+uint64_t svb_substeps(const SvbHandle* h) { return h ? h->substeps : 0; }
+float svb_allowed_time_step(const SvbHandle* h) { return h ? h->adaptive.allowed() : 0.f; }
+uint32_t svb_status(const SvbHandle* h) { return h ? h->status : 0; }
+const char* svb_last_error(const SvbHandle* h) { return h ? h->last_error.c_str() : "null handle"; }
+uint64_t svb_kernel_launches(const SvbHandle* h) { return h ? h->launches : 0; }
+uint64_t svb_particle_count(const SvbHandle* h) { return h ? h->n : 0; }
+
+int32_t svb_binning(SvbHandle* h, uint32_t* sort_map, int32_t* cells) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  const uint32_t n = h->n;
+  if (!n) return 0;
+  ParticleBuf P = h->Pc();
+  if (sort_map) CK(cudaMemcpyAsync(sort_map, P.u(PORIG), (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (cells) {
+    int32_t* d = h->pbuf[h->cur ^ 1].as<int32_t>();
+    k_cells<<<blocks_for(n, 256), 256, 0, h->stream>>>(P, h->K.h, n, d);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(cells, d, (size_t)n * 12, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t svb_active_block_count(SvbHandle* h) { return h ? (h->have_grid ? (int64_t)h->n_active : 0) : SVB_BAD_ARGUMENT; }
+
+int32_t svb_active_blocks(SvbHandle* h, int32_t* block_ids, uint32_t* collider_bits) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  const uint32_t na = h->have_grid ? h->n_active : 0;
+  if (!na) return 0;
+  DevBuf ids, bits;
+  CK(ids.ensure((size_t)na * 12));
+  CK(bits.ensure((size_t)na * 4));
+  k_decode_active<<<blocks_for(na, 256), 256, 0, h->stream>>>(h->active_keys.as<unsigned long long>(), h->layer_bits.as<uint32_t>(), h->layout.as<BinLayout>(), na, ids.as<int32_t>(),
+                                                             bits.as<uint32_t>());
+  LAUNCH_CHECK();
+  if (block_ids) CK(cudaMemcpyAsync(block_ids, ids.p, (size_t)na * 12, cudaMemcpyDeviceToHost, h->stream));
+  if (collider_bits) CK(cudaMemcpyAsync(collider_bits, bits.p, (size_t)na * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  ids.release(); bits.release();
+  return 0;
+}
+
+int32_t svb_stage_times(SvbHandle* h, const char** names, float* ms, int32_t cap) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  for (int i = 0; i < ST_COUNT && i < cap; ++i) {
+    if (names) names[i] = kStageNames[i];
+    if (ms) ms[i] = h->stage_ms[i];
+  }
+  return ST_COUNT;
+}
+void svb_enable_stage_timing(SvbHandle* h, int32_t on) {
+  if (h) h->timing = on != 0;
+}
+void svb_set_option(SvbHandle* h, const char* name, double value) {
+  if (!h || !name) return;
+  if (!std::strcmp(name, "store_grid")) h->store_grid = value != 0.0;  // CpuRunParameters::store_grid
+}
+
+int32_t svb_snapshot(SvbHandle* h) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  CK(h->snap_p.ensure(h->cap * NFIELDS * 4));
+  CK(h->snap_e.ensure(h->cap * 4));
+  CK(cudaMemcpyAsync(h->snap_p.p, h->pbuf[h->cur].p, h->cap * NFIELDS * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->snap_e.p, h->energy.p, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->snap_time = h->time;
+  h->snap_adaptive = h->adaptive;
+  h->snap_substeps = h->substeps;
+  h->have_snapshot = true;
+  return 0;
+}
+int32_t svb_restore(SvbHandle* h) {
+  if (!h) return SVB_BAD_ARGUMENT;
+  if (!h->have_snapshot) return fail(h, SVB_BAD_ARGUMENT, "svb_restore without svb_snapshot");
+  if (int rc = set_device(h)) return rc;
+  CK(cudaMemcpyAsync(h->pbuf[h->cur].p, h->snap_p.p, h->cap * NFIELDS * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->energy.p, h->snap_e.p, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->time = h->snap_time;
+  h->adaptive = h->snap_adaptive;
+  h->substeps = h->snap_substeps;
+  h->have_grid = false;
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- multi-GPU slab decomposition: see svb_comm.cuh (round 1: not wired yet) ----
+extern "C" {
+int32_t svb_comm_unique_id(uint8_t out[128]) {
+  (void)out;
+  return SVB_COMM_ERROR;
+}
+int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, int32_t n_ranks, int32_t slab_lo_block_x, int32_t slab_hi_block_x, uint64_t original_offset) {
+  (void)unique_id; (void)rank; (void)n_ranks; (void)slab_lo_block_x; (void)slab_hi_block_x; (void)original_offset;
+  return fail(h, SVB_COMM_ERROR, "multi-GPU slab exchange is not available in this build");
+}
+int32_t svb_download_resident(SvbHandle* h, SvbParticles* out, uint64_t* original_index) {
+  (void)out; (void)original_index;
+  return fail(h, SVB_COMM_ERROR, "multi-GPU slab exchange is not available in this build");
+}
+}
