@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — particle-substeps/s of the MPM substep (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scene jelly_collision]
+
+One "step" = one MPM substep (bin -> P2G -> grid -> G2P/advance) over the whole synthetic scene.
+At N=1 the workload is BASELINE.json configs[1]: the 1.02 M-particle two-block Neo-Hookean jelly
+collision (squishy_volumes_b200/scenes.py:jelly_collision, side=80).  For N>1 every rank runs its
+own replica-sized slab of the scene (weak scaling, no data-path collective yet).
+
+Printed JSON keys follow the driver contract; in particular
+  value     device-timed throughput, state already resident in HBM (CUDA events on the library's
+            own stream around the substep loop, `svb_last_advance_ms`), max over ranks;
+  e2e       same metric through the public API with HOST buffers: from_io_state (H2D) +
+            produce_next_state (K substeps + D2H of the IoState) inside the timed region;
+  roofline  dominant kernel: algorithmic bytes per launch / its mean launch time (CUDA events per
+            stage, a separate instrumented pass) against MEASURED_PEAKS.json's HBM copy bandwidth;
+  cpu_baseline   the oracle (C++ restatement of the reference's CPU path, OpenMP) on a bounded
+            sample of the same scene on this box's host cores.
+
+`--impl reference` times that CPU restatement on the same scene with all host threads (the
+reference's Rust crate cannot be built here: no cargo/rustc, un-vendored deps).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from squishy_volumes_b200 import scenes  # noqa: E402
+from squishy_volumes_b200.types import RunParameters  # noqa: E402
+
+METRIC = "particle-substeps/sec"
+UNIT = "particle-substeps/s"
+# algorithmic (compulsory) bytes per particle-substep
+A_P2G = 120.0
+A_G2P = 56.0 + 96.0
+A_GRID = 8.0
+A_NOSORT = 280.0
+A_SORT_EXTRA = 272.0
+
+
+def make_scene(name: str, scale: float):
+    if name == "jelly_collision":
+        side = max(4, int(round(80 * scale ** (1.0 / 3.0))))
+        return scenes.jelly_collision(side=side)
+    if name == "elastic_cube":
+        return scenes.elastic_cube(side=max(4, int(round(46 * scale ** (1.0 / 3.0)))))
+    if name == "sand_torus":
+        return scenes.sand_torus(side=max(8, int(round(200 * scale ** (1.0 / 3.0)))))
+    if name == "dam_break":
+        s = scale ** (1.0 / 3.0)
+        return scenes.dam_break(nx=max(8, int(400 * s)), ny=max(4, int(200 * s)), nz=max(4, int(200 * s)))
+    if name == "mixed":
+        return scenes.mixed(side=max(16, int(round(400 * scale ** (1.0 / 3.0)))))
+    raise SystemExit(f"unknown scene {name}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_leg(scene, steps: int, warmup: int, budget_s: float):
+    """Oracle (reference-algorithm CPU restatement) on this box's host cores; bounded sample."""
+    import oracle.oracle as orc
+    orc.build()
+    L = orc.lib()
+    cores = int(L.svo_max_threads())
+    o = orc.OracleState.from_io_state(scene.io_state, scene.frame_input)
+    o._sync_keyframes(scene.frame_input)
+    dt = scene.time_step
+    k = 0
+    for _ in range(warmup):
+        k += 1
+        L.svo_advance(o._h, (k - 0.5) * dt, dt, 0, None)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        k += 1
+        L.svo_advance(o._h, (k - 0.5) * dt, dt, 0, None)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    return {"value": scene.n * done / el, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": 1e3 * el / done,
+            "sample": f"{done} substeps of the same {scene.n}-particle scene after {warmup} warm-up substeps (C++/OpenMP restatement of the reference CPU path; Rust crate not buildable here)"}
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def all_max(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def all_sum(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    import torch
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+    torch.cuda.synchronize(local)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=42)     # one output frame at 24 fps, dt = 1e-3
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default="jelly_collision")
+    ap.add_argument("--scale", type=float, default=1.0, help="particle-count multiplier of the named scene")
+    ap.add_argument("--adaptive", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+
+    scene = make_scene(args.scene, args.scale)
+    scene.frame_input.consts.frames_per_second = 1  # one long frame: the bench never crosses a keyframe boundary
+    dt = scene.time_step
+    config = {"workload": f"{args.scene}: {scene.description}", "particles_per_gpu": scene.n, "time_step": dt, "adaptive_time_steps": bool(args.adaptive),
+              "rebin": "every substep (key + radix sort + physical permutation)", "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return 0
+        leg = cpu_leg(scene, steps, min(warmup, 2), budget_s=150.0)
+        line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from squishy_volumes_b200.state import B200State
+    rank, world, local, dist = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
+
+    # ---------------- device-resident throughput
+    state = B200State.from_io_state(scene.io_state, scene.frame_input, device=local)
+    fi = scene.frame_input
+    t0 = scene.io_state.time
+    params = lambda k: RunParameters(target_time=t0 + (k - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive)
+    state.snapshot()
+    if warmup:
+        state.advance(None, fi, params(warmup))
+    state.restore()
+    if warmup:
+        state.advance(None, fi, params(warmup))   # state now `warmup` substeps in: contact has begun
+    k0 = state.substeps
+    launches0 = state.kernel_launches
+    barrier(dist, local)
+    with ClockSampler(local) as clocks:
+        state.advance(None, fi, RunParameters(target_time=state.time + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+        ms = state.last_advance_ms
+        barrier(dist, local)
+        # keep sampling clocks over a few more identical passes so short runs still get samples
+        extra = 0
+        while len(clocks.samples) < 3 and extra < 20:
+            state.advance(None, fi, RunParameters(target_time=state.time + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+            extra += 1
+    done = steps
+    gpu_launches = (state.kernel_launches - launches0) // (1 + extra)
+    ms_max = all_max(dist, local, ms)
+    total_particles = all_sum(dist, local, float(scene.n))
+    value = total_particles * done / (ms_max * 1e-3)
+
+    # ---------------- per-stage pass (instrumented: one event pair + sync per stage) -> roofline
+    state.restore()
+    if warmup:
+        state.advance(None, fi, params(warmup))
+    state.enable_stage_timing(True)
+    state.advance(None, fi, RunParameters(target_time=state.time + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+    stages = {k: v / steps for k, v in state.stage_times().items()}
+    state.enable_stage_timing(False)
+    peak, peak_kind = measured_peak()
+    dom = max(("p2g", "g2p"), key=lambda s: stages.get(s, 0.0))
+    alg_bytes = scene.n * ((A_P2G if dom == "p2g" else A_G2P) + A_GRID / 2)
+    dom_ms = max(stages.get(dom, 0.0), 1e-9)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
+                "whole_substep": {"algorithmic_bytes": scene.n * (A_NOSORT + A_SORT_EXTRA), "achieved": scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9,
+                                  "frac": scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9 / peak},
+                "stage_ms_per_substep": stages}
+
+    # ---------------- end to end through the public API with host buffers
+    state.close()
+    host_state = scene.io_state
+    h2d = sum(getattr(host_state.particles, f).nbytes for f in ("flags", "mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha", "viscosity_dynamic",
+                                                                 "viscosity_bulk", "positions", "position_gradients", "velocities", "velocity_gradients", "elastic_energies", "collider_bits"))
+    d2h = h2d
+    barrier(dist, local)
+    te = time.perf_counter()
+    st2 = B200State.from_io_state(host_state, fi, device=local)
+    out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+    barrier(dist, local)
+    e2e_s = all_max(dist, local, time.perf_counter() - te)
+    e2e_done = st2.substeps
+    st2.close()
+    e2e = {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": d2h / e2e_done,
+           "what": f"from_io_state (H2D of the whole state) + produce_next_state ({e2e_done} substeps + D2H of the IoState), wall clock, max over ranks"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": warmup, "ms_per_step": ms_max / done, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "roofline": roofline, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "clocks": clocks.summary()}
+    if rank == 0 and not args.no_cpu:
+        leg = cpu_leg(scene, 1000, 2, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -136,6 +136,9 @@ float svb_allowed_time_step(const SvbHandle* h);      /* AdaptiveTimeStepState::
 uint32_t svb_status(const SvbHandle* h);              /* accumulated simulation-level status bits */
 const char* svb_last_error(const SvbHandle* h);
 uint64_t svb_kernel_launches(const SvbHandle* h);     /* kernels launched by this handle so far */
+/* Device time of the last svb_advance call: CUDA events recorded on the handle's own stream around
+ * the substep loop (gpu/src/gpu_state.rs `run_step` profiler scope analogue). */
+float svb_last_advance_ms(const SvbHandle* h);
 
 /* ---- introspection used by the parity tests (integer stages must be bit-exact) ---- */
 /* Current (binned) order: sort_map[current] = original index (cpu/src/particles.rs:13-17),

@@ -132,6 +132,7 @@ class OracleState:
         consts = cs.consts_struct(frame_input.consts)
         h = L.svo_create(C.byref(consts), C.byref(ps), C.c_double(io_state.time))
         self = cls(h, p.n, frame_input)
+        self._h_size = frame_input.consts.scaled_grid_node_size()
         self._params = p  # material parameters never change on the path; echoed back by to_io_state
         nv, nt, flat = cs.topology_arrays(frame_input)
         rc = L.svo_set_topology(h, len(frame_input.colliders), cs.uptr(nv), cs.uptr(nt), cs.uptr(flat))
@@ -186,6 +187,14 @@ class OracleState:
         g, s = cs.alloc_grid(n, with_counts=True)
         lib().svo_download_grid(self._h, C.byref(s))
         return g
+
+    def binning(self):
+        """(sort_map, cells) like B200State.binning: current order -> original index, base node per row
+        (cells recomputed from the CURRENT positions with the restatement of kernels.rs:46-49)."""
+        sm = self.sort_map()
+        pos = self.to_io_state().particles.positions  # original order
+        cells_orig = shift_quadratic(pos, float(self._h_size))
+        return sm, cells_orig[sm]
 
     def sort_map(self) -> np.ndarray:
         out = np.zeros(self.n, dtype=np.uint32)

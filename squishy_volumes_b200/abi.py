@@ -86,6 +86,8 @@ def load():
     L.svb_last_error.argtypes = [vp]
     L.svb_kernel_launches.restype = C.c_uint64
     L.svb_kernel_launches.argtypes = [vp]
+    L.svb_last_advance_ms.restype = C.c_float
+    L.svb_last_advance_ms.argtypes = [vp]
     L.svb_binning.restype = C.c_int32
     L.svb_binning.argtypes = [vp, cs.c_u32p, cs.c_i32p]
     L.svb_active_block_count.restype = C.c_int64

@@ -105,6 +105,8 @@ struct SvbHandle {
   bool timing = false;
   cudaEvent_t ev[ST_COUNT + 1] = {};
   float stage_ms[ST_COUNT] = {};
+  cudaEvent_t ev_adv[2] = {};
+  float last_advance_ms = 0;
   int last_stage = -1;
 
   ParticleBuf P(int which) const { return ParticleBuf{pbuf[which].as<uint32_t>(), cap}; }
@@ -462,6 +464,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  for (auto& e : h->ev_adv) CK(cudaEventCreate(&e));
   CK(cudaMallocHost(&h->h_scalars, sizeof(StepScalars)));
   CK(cudaMallocHost(&h->h_layout, sizeof(BinLayout)));
   CK(cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
@@ -540,6 +543,8 @@ void svb_destroy(SvbHandle* h) {
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_layout) cudaFreeHost(h->h_layout);
   for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_adv)
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -647,13 +652,16 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   h->status = 0;
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
+  CK(cudaEventRecord(h->ev_adv[0], h->stream));
   while (h->time < target_time) {
     if (cancel && *cancel) return fail(h, SVB_CANCELED, "The computation was canceled");
     if (int rc = substep(h, adaptive_time_steps != 0)) return rc;
     if (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED) break;
     if (progress) progress(user, (size_t)(std::fmod(h->time, spf) * 1000.0));
   }
+  CK(cudaEventRecord(h->ev_adv[1], h->stream));
   if (int rc = read_status(h)) return rc;
+  CK(cudaEventElapsedTime(&h->last_advance_ms, h->ev_adv[0], h->ev_adv[1]));
   if (h->status) {
     if (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED) fail(h, 0, "Failed to compute the elastic energy of a particle (EnergyError::PositionGradientNonPositive)");
     else fail(h, 0, "device status word 0x%x", h->status);
@@ -760,6 +768,7 @@ float svb_allowed_time_step(const SvbHandle* h) { return h ? h->adaptive.allowed
 uint32_t svb_status(const SvbHandle* h) { return h ? h->status : 0; }
 const char* svb_last_error(const SvbHandle* h) { return h ? h->last_error.c_str() : "null handle"; }
 uint64_t svb_kernel_launches(const SvbHandle* h) { return h ? h->launches : 0; }
+float svb_last_advance_ms(const SvbHandle* h) { return h ? h->last_advance_ms : 0.f; }
 uint64_t svb_particle_count(const SvbHandle* h) { return h ? h->n : 0; }
 
 int32_t svb_binning(SvbHandle* h, uint32_t* sort_map, int32_t* cells) {

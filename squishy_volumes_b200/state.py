@@ -191,5 +191,9 @@ class B200State:
         return float(abi.load().svb_allowed_time_step(self._h))
 
     @property
+    def last_advance_ms(self) -> float:
+        return float(abi.load().svb_last_advance_ms(self._h))
+
+    @property
     def kernel_launches(self) -> int:
         return int(abi.load().svb_kernel_launches(self._h))

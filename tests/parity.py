@@ -32,18 +32,27 @@ def field_error(a: np.ndarray, b: np.ndarray, mask=None):
     return float(np.max(np.abs(a - b))), scale
 
 
-def compare_states(got, ref, rtol, atol=ATOL, check_energy=True):
+def compare_states(got, ref, rtol, atol=ATOL, check_energy=True, h=None):
     """got / ref: IoState.  Returns dict of (err, scale); raises AssertionError on violation."""
     gp, rp = got.particles, ref.particles
     report = {}
     assert np.array_equal(gp.flags, rp.flags), f"flags differ at {np.nonzero(gp.flags != rp.flags)[0][:10]}"
     live = (rp.flags & ParticleFlags.TOMBSTONED) == 0
     assert np.array_equal(gp.collider_bits[live], rp.collider_bits[live]), "collider bits differ"
-    names = FIELDS + (("elastic_energies",) if check_energy else ())
-    for name in names:
+    vmax = max(float(np.max(np.abs(rp.velocities[live]))) if live.any() else 0.0, 1e-12)
+    for name in FIELDS:
         err, scale = field_error(getattr(gp, name), getattr(rp, name), live)
+        if name == "velocity_gradients" and h is not None:
+            scale = max(scale, vmax / h)  # C = 4/h^2 sum w v (x_n - x)^T: cancellation noise scales with |v|/h
         report[name] = (err, scale)
         assert err <= atol + rtol * scale, f"{name}: max abs err {err:.3e} vs scale {scale:.3e} (rtol {rtol})"
+    if check_energy:
+        # energies are differences of O(modulus) terms: absolute floor = f32 eps * modulus
+        modulus = float(np.max(np.abs(rp.mu_or_bulk_modulus) + np.where((rp.flags & ParticleFlags.IS_FLUID) != 0, 0.0, np.abs(rp.lambda_or_exponent))))
+        ok = live & ((rp.flags & ParticleFlags.FAILED) == 0)
+        err, scale = field_error(gp.elastic_energies, rp.elastic_energies, ok)
+        report["elastic_energies"] = (err, scale)
+        assert err <= 4e-6 * modulus + rtol * scale, f"elastic_energies: max abs err {err:.3e} vs scale {scale:.3e}, modulus {modulus:.3e}"
     return report
 
 
