@@ -310,7 +310,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     LAUNCH_CHECK();
     const uint32_t n_cand = h->n_groups * 8;
     {
-      int rc = sort_keys_u64(h->sort_tmp.p, h->sort_tmp.bytes, h->cand[0].as<unsigned long long>(), h->cand[1].as<unsigned long long>(), n_cand, 64, s, &h->launches);
+      int rc = sort_keys_u64(h->sort_tmp.p, h->sort_tmp.bytes, h->cand[0].as<unsigned long long>(), h->cand[1].as<unsigned long long>(), n_cand, h->h_layout->total_bits - 6 + 1, s, &h->launches);
       if (rc != 0) return fail(h, SVB_CUDA_ERROR, "candidate sort failed: %s", cudaGetErrorString((cudaError_t)rc));
     }
     const uint32_t c_tiles = blocks_for(n_cand, SCAN_TILE);

@@ -291,6 +291,9 @@ __global__ void __launch_bounds__(256) k_force(ParticleBuf P, StepScalars* S, Si
       mn[2] = mx[2] = base_node(x.z, K.h);
     }
   }
+  // block-level min/max, then at most 6 atomics per CTA — and only when they would change the box
+  // (same-address atomics from every warp serialise in L2: 32 k warps cost ~100 us at 1 M particles)
+  __shared__ int s_lo[3][8], s_hi[3][8];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     int lo = mn[a], hi = mx[a];
@@ -299,9 +302,17 @@ __global__ void __launch_bounds__(256) k_force(ParticleBuf P, StepScalars* S, Si
       lo = min(lo, __shfl_xor_sync(SVB_FULL, lo, o));
       hi = max(hi, __shfl_xor_sync(SVB_FULL, hi, o));
     }
-    if ((threadIdx.x & 31) == 0 && lo <= hi) {
-      atomicMin(&S->bbox_min[a], lo);
-      atomicMax(&S->bbox_max[a], hi);
+    if ((threadIdx.x & 31) == 0) { s_lo[a][threadIdx.x >> 5] = lo; s_hi[a][threadIdx.x >> 5] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    int lo = s_lo[a][0], hi = s_hi[a][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { lo = min(lo, s_lo[a][w]); hi = max(hi, s_hi[a][w]); }
+    if (lo <= hi) {
+      if (lo < *(volatile int*)&S->bbox_min[a]) atomicMin(&S->bbox_min[a], lo);
+      if (hi > *(volatile int*)&S->bbox_max[a]) atomicMax(&S->bbox_max[a], hi);
     }
   }
 }
@@ -410,7 +421,7 @@ __device__ __forceinline__ bool head_flag(const unsigned long long* __restrict__
     if (k >> total_bits) return false;
     return i == 0 || (keys[i - 1] >> 6) != (k >> 6);
   } else {
-    if (k == ~0ull) return false;
+    if (k >> (total_bits - 6)) return false;  // empty candidate slot (bit just above the tile-key range)
     return i == 0 || keys[i - 1] != k;
   }
 }
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(256) k_group_touch(const unsigned long long* _
     for (int o = 16; o > 0; o >>= 1) t |= __shfl_xor_sync(SVB_FULL, t, o);
     if (lane < 8) {
       const unsigned long long gk = keys[start] >> 6;
-      cand[(size_t)g * 8 + lane] = ((t >> lane) & 1u) ? gk + group_delta(L, (int)lane) : ~0ull;
+      cand[(size_t)g * 8 + lane] = ((t >> lane) & 1u) ? gk + group_delta(L, (int)lane) : (1ull << (L.total_bits - 6));
     }
     if (lane == 0) group_touch[g] = t;
   }
@@ -594,8 +605,8 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(ParticleBuf P, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S, float4* __restrict__ grid,
-                                                        float h, float dt) {
+__global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S, float4* __restrict__ grid,
+                                                           float h, float dt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   float* stage_all = reinterpret_cast<float*>(smem_raw + P2G_WARPS * TILE_NODES * 16);
@@ -605,9 +616,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(ParticleBuf P, const uin
   float* stage = stage_all + warp * 32 * STAGE_STRIDE;
   const uint32_t n_groups = S->n_groups, n_live = S->n_live;
   const float scaling = dt * 4.f / (h * h);
-  // node handled by this lane in the 3x3x3 stencil (k fastest), lanes 27..31 idle in the walk
-  const int li = lane / 9, lj = (lane / 3) % 3, lk = lane % 3;
+  // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
+  const int li = node_lane ? lane / 9 : 0, lj = node_lane ? (lane / 3) % 3 : 0, lk = node_lane ? lane % 3 : 0;
+  // staged row (floats): [0..17] (w,d) pairs x0 x1 x2 y0 y1 y2 z0 z1 z2 | 18 cell | 19 mass | 20..22 m*v | 23 A8 | 24..31 A0..A7
+  const float* lane_x = stage + 2 * li;
+  const float* lane_y = stage + 6 + 2 * lj;
+  const float* lane_z = stage + 12 + 2 * lk;
+  const int lane_tile_off = (li * 6 + lj) * 6 + lk;
 
   for (;;) {
     __syncthreads();
@@ -655,60 +671,63 @@ __global__ void __launch_bounds__(P2G_WARPS * 32) k_p2g(ParticleBuf P, const uin
           for (int q = 0; q < 9; ++q) A.m[q] -= sj * cauchy.m[q];
         }
         const float mv0 = mass * P.f(PV)[i], mv1 = mass * P.f(PV + 1)[i], mv2 = mass * P.f(PV + 2)[i];
-        st[0] = make_float4(w[0], w[1], w[2], w[3]);
-        st[1] = make_float4(w[4], w[5], w[6], w[7]);
-        st[2] = make_float4(w[8], d[0], d[1], d[2]);
-        st[3] = make_float4(d[3], d[4], d[5], d[6]);
-        st[4] = make_float4(d[7], d[8], __int_as_float(cell), mass);
+        st[0] = make_float4(w[0], d[0], w[1], d[1]);
+        st[1] = make_float4(w[2], d[2], w[3], d[3]);
+        st[2] = make_float4(w[4], d[4], w[5], d[5]);
+        st[3] = make_float4(w[6], d[6], w[7], d[7]);
+        st[4] = make_float4(w[8], d[8], __int_as_float(cell), mass);
         st[5] = make_float4(mv0, mv1, mv2, A.m[8]);
         st[6] = make_float4(A.m[0], A.m[1], A.m[2], A.m[3]);
         st[7] = make_float4(A.m[4], A.m[5], A.m[6], A.m[7]);
       } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q) st[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        st[4].z = __int_as_float(-1);
       }
+      // runs of equal cells inside this chunk (the run is sorted by cell): heads as a warp-uniform mask
+      const int prev_cell = __shfl_up_sync(SVB_FULL, cell, 1);
+      uint32_t heads = __ballot_sync(SVB_FULL, cell >= 0 && (lane == 0 || prev_cell != cell));
+      const uint32_t valid = __ballot_sync(SVB_FULL, cell >= 0);
       __syncwarp();
       float4* row = reinterpret_cast<float4*>(stage + lane * STAGE_STRIDE);
 #pragma unroll
       for (int q = 0; q < 8; ++q) row[q] = st[q];
       __syncwarp();
 
-      // ---- cooperative walk: lane = stencil node
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      int cur_cell = -1;
-      const int count = min(32u, end - chunk);
-      for (int p = 0; p < count; ++p) {
-        const float* sp = stage + p * STAGE_STRIDE;
-        const float4 q4 = *reinterpret_cast<const float4*>(sp + 16);  // d7 d8 cell m
-        const int pc = __float_as_int(q4.z);
-        if (pc != cur_cell) {
-          if (cur_cell >= 0 && node_lane) {
-            const int t = (((cur_cell >> 4) + li) * 6 + (((cur_cell >> 2) & 3) + lj)) * 6 + ((cur_cell & 3) + lk);
-            float4 o = my_tile[t];
-            o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-            my_tile[t] = o;
-          }
-          acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          cur_cell = pc;
-        }
-        if (node_lane) {
-          const float wgt = sp[li] * sp[3 + lj] * sp[6 + lk];
-          const float dx = sp[9 + li], dy = sp[12 + lj], dz = sp[15 + lk];
+      // ---- cooperative walk: lane = stencil node, one register accumulator per run of equal cells
+      const int count = __popc(valid);
+      while (heads) {
+        const int first = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int last = heads ? __ffs(heads) - 1 : count;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int off = first * STAGE_STRIDE;
+        const float* px = lane_x + off;
+        const float* py = lane_y + off;
+        const float* pz = lane_z + off;
+        const float* sp = stage + off;
+#pragma unroll 4
+        for (int p = first; p < last; ++p) {
+          const float2 wx = *reinterpret_cast<const float2*>(px);
+          const float2 wy = *reinterpret_cast<const float2*>(py);
+          const float2 wz = *reinterpret_cast<const float2*>(pz);
+          const float mass = sp[19];
           const float4 mvA = *reinterpret_cast<const float4*>(sp + 20);  // mv0 mv1 mv2 A8
           const float4 A0 = *reinterpret_cast<const float4*>(sp + 24);   // A0..A3
           const float4 A1 = *reinterpret_cast<const float4*>(sp + 28);   // A4..A7
-          const float m0 = mvA.x + (A0.x * dx + A0.w * dy + A1.z * dz);
-          const float m1 = mvA.y + (A0.y * dx + A1.x * dy + A1.w * dz);
-          const float m2 = mvA.z + (A0.z * dx + A1.y * dy + mvA.w * dz);
-          acc.x += wgt * m0; acc.y += wgt * m1; acc.z += wgt * m2; acc.w += wgt * q4.w;
+          const float wgt = wx.x * wy.x * wz.x;
+          const float m0 = mvA.x + (A0.x * wx.y + A0.w * wy.y + A1.z * wz.y);
+          const float m1 = mvA.y + (A0.y * wx.y + A1.x * wy.y + A1.w * wz.y);
+          const float m2 = mvA.z + (A0.z * wx.y + A1.y * wy.y + mvA.w * wz.y);
+          acc.x += wgt * m0; acc.y += wgt * m1; acc.z += wgt * m2; acc.w += wgt * mass;
+          px += STAGE_STRIDE; py += STAGE_STRIDE; pz += STAGE_STRIDE; sp += STAGE_STRIDE;
         }
-      }
-      if (cur_cell >= 0 && node_lane) {
-        const int t = (((cur_cell >> 4) + li) * 6 + (((cur_cell >> 2) & 3) + lj)) * 6 + ((cur_cell & 3) + lk);
-        float4 o = my_tile[t];
-        o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-        my_tile[t] = o;
+        if (node_lane) {
+          const int c = __float_as_int(stage[first * STAGE_STRIDE + 18]);
+          const int t = ((c >> 4) * 6 + ((c >> 2) & 3)) * 6 + (c & 3) + lane_tile_off;
+          float4 o = my_tile[t];
+          o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+          my_tile[t] = o;
+        }
       }
       __syncwarp();
     }
