@@ -16,7 +16,6 @@
 #include "../../include/svb200.h"
 #include "svb_host.h"
 #include "svb_kernels.cuh"
-#include "svb_sort.cuh"
 
 using namespace svb;
 
@@ -46,8 +45,8 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Stage : int { ST_MESH = 0, ST_FORCE, ST_KEYS, ST_SORT, ST_PERMUTE, ST_ACTIVATE, ST_LIMIT, ST_P2G, ST_G2P, ST_ADVANCE, ST_COUNT };
-const char* const kStageNames[ST_COUNT] = {"mesh_interpolate", "collide_force", "bin_keys", "radix_sort", "permute", "activate_blocks", "limit_time_step", "p2g", "g2p", "advance"};
+enum Stage : int { ST_MESH = 0, ST_BIN, ST_OFFSETS, ST_PERMUTE, ST_LIMIT, ST_P2G, ST_G2P, ST_ADVANCE, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"mesh_interpolate", "collide_force_bin", "offsets_halo", "permute", "limit_time_step", "p2g", "g2p", "advance"};
 
 }  // namespace
 
@@ -62,15 +61,14 @@ struct SvbHandle {
   int cur = 0;
   DevBuf energy;
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
-  DevBuf keys[2], idx[2], sort_tmp;
-  DevBuf group_start, group_touch, nbr, cand[2], active_keys, grid, tile_count, node_mask, node_offset;
-  size_t group_cap = 0, active_cap = 0;
-  DevBuf scalars, layout, layer_slots, slot_rank, layer_bits;
+  // binning scratch + tile table (rebuilt every substep)
+  DevBuf pcell, prank, table_keys, table_vals, tile_key, tile_touch, cell_count, tile_start, nbr, grid, node_mask, node_offset, scratch;
+  size_t tile_cap = 0;      // tiles the per-tile arrays can hold
+  uint32_t table_mask = 0;  // open-addressing slots - 1
+  DevBuf scalars, layer_slots, layer_list;
   StepScalars* h_scalars = nullptr;  // pinned
-  BinLayout* h_layout = nullptr;     // pinned
-  int sort_bits = 0;                 // end_bit used for the particle sort (lagged knowledge of the layout)
-  uint32_t n_groups = 0, n_live = 0, n_active = 0;
-  BinLayout last_layout{};
+  cudaEvent_t ev_front = nullptr;
+  uint32_t n_ptiles = 0, n_live = 0, n_tiles = 0;
   bool have_grid = false;
   bool store_grid = false, masks_valid = false;
 
@@ -159,23 +157,24 @@ int upload_array(SvbHandle* h, DevBuf& b, const void* src, size_t bytes) {
   return 0;
 }
 
-int ensure_group_capacity(SvbHandle* h, size_t groups) {
-  if (groups <= h->group_cap) return 0;
-  const size_t c = groups + groups / 2 + 1024;
-  CK(h->group_start.ensure((c + 1) * 4));
-  CK(h->group_touch.ensure(c * 4));
+// tile capacity: per-tile arrays + an open-addressing table at <= 25 % load
+int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
+  if (tiles <= h->tile_cap) return 0;
+  const size_t c = tiles + tiles / 2 + 1024;
+  size_t slots = 1024;
+  while (slots < 4 * c) slots <<= 1;
+  CK(h->table_keys.ensure(slots * 8));
+  CK(h->table_vals.ensure(slots * 4));
+  CK(h->tile_key.ensure(c * 8));
+  CK(h->tile_touch.ensure(c * 4));
+  CK(h->cell_count.ensure(c * 64 * 4));
+  CK(h->tile_start.ensure((c + 1) * 4));
   CK(h->nbr.ensure(c * 8 * 4));
-  CK(h->cand[0].ensure(c * 8 * 8));
-  CK(h->cand[1].ensure(c * 8 * 8));
-  h->group_cap = c;
-  return 0;
-}
-int ensure_active_capacity(SvbHandle* h, size_t active) {
-  if (active <= h->active_cap) return 0;
-  const size_t c = active + active / 2 + 1024;
-  CK(h->active_keys.ensure(c * 8));
   CK(h->grid.ensure(c * 64 * 16));
-  h->active_cap = c;
+  CK(h->node_mask.ensure(c * 8));
+  CK(h->node_offset.ensure((c + 1) * 4));
+  h->tile_cap = c;
+  h->table_mask = (uint32_t)(slots - 1);
   return 0;
 }
 
@@ -184,12 +183,116 @@ int set_device(SvbHandle* h) {
   return 0;
 }
 
+TileTable tile_table(SvbHandle* h) {
+  return TileTable{h->table_keys.as<unsigned long long>(), h->table_vals.as<uint32_t>(), h->table_mask, h->tile_key.as<unsigned long long>(), (uint32_t)h->tile_cap};
+}
+MeldInfo meld_info(SvbHandle* h) { return MeldInfo{h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>()}; }
+
+struct StepInputs {
+  float factor_b, g[3];
+  bool has_mesh;
+};
+
+// front half of a substep: (collide + force +) binning, cell/tile offsets, halo tiles.  Ends with an
+// async copy of the scalars to pinned memory and an event, so the host can look at the tile count
+// while the back half is already queued behind it.
+int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt_force) {
+  cudaStream_t s = h->stream;
+  const uint32_t n = h->n;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  stage_begin(h, ST_BIN);
+  k_reset_scalars<<<1, 32, 0, s>>>(S, n);
+  LAUNCH_CHECK();
+  CK(cudaMemsetAsync(h->table_keys.p, 0xff, ((size_t)h->table_mask + 1) * 8, s));
+  CK(cudaMemsetAsync(h->table_vals.p, 0xff, ((size_t)h->table_mask + 1) * 4, s));
+  CK(cudaMemsetAsync(h->cell_count.p, 0, h->tile_cap * 64 * 4, s));
+  CK(cudaMemsetAsync(h->tile_touch.p, 0, h->tile_cap * 4, s));
+  if (in.has_mesh) CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
+  GoalDev G{nullptr, nullptr, nullptr, nullptr};
+  if (h->has_goals) {
+    G.flags_a = h->d_flags_a.as<uint32_t>();
+    G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : G.flags_a;
+    G.goal_a = h->d_goal_a.as<float>();
+    G.goal_b = h->has_b ? h->d_goal_b.as<float>() : G.goal_a;
+  }
+  const TileTable T = tile_table(h);
+  const BinArrays B{h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(),
+                    h->layer_list.as<uint32_t>()};
+  const uint32_t blocks = blocks_for(n, 256);
+#define SVB_BIN(MESH, FORCE) k_bin<MESH, FORCE><<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, T, B, n, dt_force, in.g[0], in.g[1], in.g[2], in.factor_b)
+  if (in.has_mesh) { if (apply_force) SVB_BIN(true, true); else SVB_BIN(true, false); }
+  else { if (apply_force) SVB_BIN(false, true); else SVB_BIN(false, false); }
+#undef SVB_BIN
+  LAUNCH_CHECK();
+  stage_end(h);
+  stage_begin(h, ST_OFFSETS);
+  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
+  k_cell_scan<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), (uint32_t)h->tile_cap);
+  LAUNCH_CHECK();
+  k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_start.as<uint32_t>(), &S->n_ptiles, 0, &S->n_live);
+  LAUNCH_CHECK();
+  k_halo<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 8 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(h->ev_front, s));
+  stage_end(h);
+  return 0;
+}
+
+// re-bin + grid preparation that follows the front half
+int enqueue_rebin(SvbHandle* h) {
+  cudaStream_t s = h->stream;
+  const uint32_t n = h->n;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  stage_begin(h, ST_PERMUTE);
+  k_permute<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), n);
+  LAUNCH_CHECK();
+  h->cur ^= 1;
+  k_zero_grid<<<148 * 8, 256, 0, s>>>(S, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
+  LAUNCH_CHECK();
+  h->masks_valid = false;
+  if (h->store_grid) {
+    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
+    LAUNCH_CHECK();
+    h->masks_valid = true;
+  }
+  stage_end(h);
+  return 0;
+}
+
+// wait for the front half's scalars; on tile overflow grow the capacity and redo the binning
+// (the particle order is untouched until k_permute runs, and k_permute / P2G / G2P no-op on overflow)
+int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
+  for (int attempt = 0;; ++attempt) {
+    CK(cudaEventSynchronize(h->ev_front));
+    const StepScalars& r = *h->h_scalars;
+    if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys");
+    if (r.sticky) {  // the previous substep failed: this one was a no-op on the device
+      h->status |= r.sticky & 0xffffu;
+      if (back_enqueued) { CK(cudaStreamSynchronize(h->stream)); h->cur ^= 1; }
+      return 2;
+    }
+    if (!(r.status & ST_TILE_OVERFLOW)) {
+      h->n_tiles = r.n_tiles;
+      h->n_ptiles = r.n_ptiles;
+      h->n_live = r.n_live;
+      h->status |= r.status & 0xffffu;
+      return back_enqueued ? 0 : 1;  // 1: caller still has to enqueue the back half
+    }
+    if (attempt > 8) return fail(h, SVB_CUDA_ERROR, "tile capacity did not settle");
+    CK(cudaStreamSynchronize(h->stream));
+    if (back_enqueued) h->cur ^= 1;  // the queued k_permute was a no-op: undo the buffer swap
+    back_enqueued = false;
+    if (int rc = ensure_tile_capacity(h, (size_t)r.n_tiles * 2 + 1024)) return rc;
+    if (int rc = enqueue_front(h, in, /*apply_force=*/false, 0.f)) return rc;
+  }
+}
+
 // ---- one substep: the 12 phases of cpu/src/phase/mod.rs:27-41 in the reference's order
 int substep(SvbHandle* h, bool adaptive_steps) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->n;
   StepScalars* S = h->scalars.as<StepScalars>();
-  BinLayout* L = h->layout.as<BinLayout>();
   const float hh = h->K.h;
 
   if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
@@ -198,16 +301,16 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   const double frame_time = h->time * (double)h->consts.frames_per_second;
   const uint64_t frame_low = (uint64_t)std::floor(frame_time);
   if (frame_low != h->frame) return fail(h, SVB_FRAME_INPUT, "Wrong frame loaded: %llu (need %llu)", (unsigned long long)h->frame, (unsigned long long)frame_low);
-  const float factor_b = (float)std::fmod(frame_time, 1.0);
-  const float factor_a = 1.f - factor_b;
+  StepInputs in;
+  in.factor_b = (float)std::fmod(frame_time, 1.0);
+  const float factor_a = 1.f - in.factor_b;
   const float* gb = h->has_b ? h->gravity_b : h->gravity_a;
-  float g[3];
-  for (int k = 0; k < 3; ++k) g[k] = factor_a * h->gravity_a[k] + factor_b * gb[k];
-  const bool has_mesh = h->topo.n_triangles > 0;
-  if (has_mesh) {
+  for (int k = 0; k < 3; ++k) in.g[k] = factor_a * h->gravity_a[k] + in.factor_b * gb[k];
+  in.has_mesh = h->topo.n_triangles > 0;
+  if (in.has_mesh) {
     stage_begin(h, ST_MESH);
     const uint32_t m = std::max(h->topo.n_vertices * 3, h->topo.n_triangles);
-    k_mesh_lerp<<<blocks_for(m, 256), 256, 0, s>>>(h->M, factor_b);
+    k_mesh_lerp<<<blocks_for(m, 256), 256, 0, s>>>(h->M, in.factor_b);
     LAUNCH_CHECK();
     k_mesh_tri_normals<<<blocks_for(h->topo.n_triangles, 256), 256, 0, s>>>(h->M);
     LAUNCH_CHECK();
@@ -221,138 +324,61 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     return 0;
   }
 
-  // -- Collide + ExternalForce (collide.rs, external_force.rs) in the current order; per particle, so
-  //    running them before the re-bin is equivalent to the reference's Sort -> Collide -> Force.
-  stage_begin(h, ST_FORCE);
-  {
-    StepScalars init{};
-    init.n = n;
-    for (int k = 0; k < 3; ++k) { init.bbox_min[k] = INT32_MAX; init.bbox_max[k] = INT32_MIN; }
-    init.min_sound_key = INT32_MAX; init.min_isolated_key = INT32_MAX; init.max_velocity_key = INT32_MIN; init.min_deformation_key = INT32_MAX;
-    init.status = 0;
-    *h->h_scalars = init;
-    CK(cudaMemcpyAsync(S, h->h_scalars, sizeof(StepScalars), cudaMemcpyHostToDevice, s));
-    if (has_mesh) CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
-  }
-  const float dt_force = h->adaptive.allowed();
-  GoalDev G{nullptr, nullptr, nullptr, nullptr};
-  if (h->has_goals) {
-    G.flags_a = h->d_flags_a.as<uint32_t>();
-    G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : G.flags_a;
-    G.goal_a = h->d_goal_a.as<float>();
-    G.goal_b = h->has_b ? h->d_goal_b.as<float>() : G.goal_a;
-  }
-  if (has_mesh) k_force<true><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, h->layer_slots.as<unsigned long long>(), n, dt_force, g[0], g[1], g[2], factor_b);
-  else k_force<false><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, h->layer_slots.as<unsigned long long>(), n, dt_force, g[0], g[1], g[2], factor_b);
-  LAUNCH_CHECK();
-  stage_end(h);
+  // -- Collide + ExternalForce + Sort + UpdateGridNodes.  Collide / force are per particle, so running
+  //    them in the pre-bin order is equivalent to the reference's Sort -> Collide -> Force.
+  if (int rc = enqueue_front(h, in, /*apply_force=*/true, h->adaptive.allowed())) return rc;
+  const TileTable T = tile_table(h);
+  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
+  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
 
-  // -- Sort (sort.rs) : bin keys -> radix sort -> gather
-  stage_begin(h, ST_KEYS);
-  k_layout<<<1, 1024, 0, s>>>(S, L, h->layer_slots.as<unsigned long long>(), h->slot_rank.as<uint32_t>(), h->layer_bits.as<uint32_t>());
-  LAUNCH_CHECK();
-  stage_end(h);
-  if (h->sort_bits == 0) {  // first substep: learn the key width
-    CK(cudaMemcpyAsync(h->h_layout, L, sizeof(BinLayout), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    h->sort_bits = std::min(64, h->h_layout->total_bits + 1 + 3);
-  }
-  const uint32_t n_tiles = blocks_for(n, SCAN_TILE);
-  CK(h->tile_count.ensure((size_t)std::max<uint32_t>(n_tiles, 1024) * 4));
-  for (int attempt = 0;; ++attempt) {
-    stage_begin(h, ST_KEYS);
-    k_keys<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), L, h->layer_slots.as<unsigned long long>(), h->slot_rank.as<uint32_t>(), hh, n, h->keys[0].as<unsigned long long>(),
-                                             h->idx[0].as<uint32_t>());
+  if (!adaptive_steps) {
+    // fixed dt: queue the whole back half behind the front half, then look at the front half's result
+    const float dt = h->adaptive.allowed();
+    if (int rc = enqueue_rebin(h)) return rc;
+    stage_begin(h, ST_P2G);
+    k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
     LAUNCH_CHECK();
     stage_end(h);
-    stage_begin(h, ST_SORT);
-    {
-      int rc = sort_pairs_u64(h->sort_tmp.p, h->sort_tmp.bytes, h->keys[0].as<unsigned long long>(), h->keys[1].as<unsigned long long>(), h->idx[0].as<uint32_t>(),
-                              h->idx[1].as<uint32_t>(), n, h->sort_bits, s, &h->launches);
-      if (rc != 0) return fail(h, SVB_CUDA_ERROR, "radix sort failed: %s", cudaGetErrorString((cudaError_t)rc));
-    }
+    stage_begin(h, ST_G2P);
+    k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T, meld_info(h), h->K, dt);
+    LAUNCH_CHECK();
     stage_end(h);
-    stage_begin(h, ST_PERMUTE);
-    k_permute<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->idx[1].as<uint32_t>(), n);
-    LAUNCH_CHECK();
-    h->cur ^= 1;
-    stage_end(h);
-    // -- UpdateGridNodes (update_grid_nodes.rs) : runs of equal (block, layer)
-    stage_begin(h, ST_ACTIVATE);
-    k_flag_count<0><<<n_tiles, SCAN_THREADS, 0, s>>>(h->keys[1].as<unsigned long long>(), nullptr, n, L, h->tile_count.as<uint32_t>(), S);
-    LAUNCH_CHECK();
-    k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_count.as<uint32_t>(), n_tiles, &S->n_groups);
-    LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->h_layout, L, sizeof(BinLayout), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    stage_end(h);
-    if (h->h_scalars->status & 0x80000000u) return fail(h, SVB_KEY_RANGE, "live particles span too many grid blocks for a 63-bit bin key");
-    if (h->h_layout->total_bits + 1 <= h->sort_bits) break;
-    if (attempt > 2) return fail(h, SVB_KEY_RANGE, "bin key width did not settle");
-    h->sort_bits = std::min(64, h->h_layout->total_bits + 1 + 3);  // the bounding box outgrew the lagged key width: redo the re-bin
-  }
-  h->sort_bits = std::min(64, h->h_layout->total_bits + 1 + 3);
-  h->last_layout = *h->h_layout;
-  h->n_groups = h->h_scalars->n_groups;
-  h->n_live = h->h_scalars->n_live;
-  h->status |= h->h_scalars->status & 0xffffu;
-  if (int rc = ensure_group_capacity(h, h->n_groups)) return rc;
-
-  stage_begin(h, ST_ACTIVATE);
-  const unsigned long long* skeys = h->keys[1].as<unsigned long long>();
-  uint32_t* group_start = h->group_start.as<uint32_t>();
-  if (h->n_groups) {
-    k_flag_write<0><<<n_tiles, SCAN_THREADS, 0, s>>>(skeys, nullptr, n, L, h->tile_count.as<uint32_t>(), group_start, nullptr, (uint32_t)h->group_cap, S);
-    LAUNCH_CHECK();
-    k_group_touch<<<std::min<uint32_t>(blocks_for((uint64_t)h->n_groups * 32, 256), 148 * 8), 256, 0, s>>>(skeys, group_start, L, S, h->cand[0].as<unsigned long long>(),
-                                                                                                          h->group_touch.as<uint32_t>());
-    LAUNCH_CHECK();
-    const uint32_t n_cand = h->n_groups * 8;
-    {
-      int rc = sort_keys_u64(h->sort_tmp.p, h->sort_tmp.bytes, h->cand[0].as<unsigned long long>(), h->cand[1].as<unsigned long long>(), n_cand, h->h_layout->total_bits - 6 + 1, s, &h->launches);
-      if (rc != 0) return fail(h, SVB_CUDA_ERROR, "candidate sort failed: %s", cudaGetErrorString((cudaError_t)rc));
-    }
-    const uint32_t c_tiles = blocks_for(n_cand, SCAN_TILE);
-    CK(h->tile_count.ensure((size_t)std::max<uint32_t>(c_tiles, 1024) * 4));
-    k_flag_count<1><<<c_tiles, SCAN_THREADS, 0, s>>>(h->cand[1].as<unsigned long long>(), nullptr, n_cand, L, h->tile_count.as<uint32_t>(), S);
-    LAUNCH_CHECK();
-    k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_count.as<uint32_t>(), c_tiles, &S->n_active);
-    LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(&h->h_scalars->n_active, &S->n_active, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    h->n_active = h->h_scalars->n_active;
-    if (int rc = ensure_active_capacity(h, h->n_active)) return rc;
-    k_flag_write<1><<<c_tiles, SCAN_THREADS, 0, s>>>(h->cand[1].as<unsigned long long>(), nullptr, n_cand, L, h->tile_count.as<uint32_t>(), nullptr,
-                                                      h->active_keys.as<unsigned long long>(), (uint32_t)h->active_cap, S);
-    LAUNCH_CHECK();
-    k_neighbors<<<std::min<uint32_t>(blocks_for((uint64_t)n_cand, 256), 148 * 16), 256, 0, s>>>(skeys, group_start, h->group_touch.as<uint32_t>(), L, S,
-                                                                                                h->active_keys.as<unsigned long long>(), h->nbr.as<int>());
-    LAUNCH_CHECK();
-    CK(cudaMemsetAsync(h->grid.p, 0, (size_t)h->n_active * 64 * 16, s));
-    h->masks_valid = false;
-    if (h->store_grid) {
-      CK(h->node_mask.ensure((size_t)h->n_active * 8));
-      CK(cudaMemsetAsync(h->node_mask.p, 0, (size_t)h->n_active * 8, s));
-      k_touch_nodes<<<std::min<uint32_t>(blocks_for((uint64_t)h->n_groups * 32, 256), 148 * 8), 256, 0, s>>>(h->Pc(), group_start, h->nbr.as<int>(), S, hh,
-                                                                                                            h->node_mask.as<unsigned long long>());
+    const int rc = settle_front(h, in, /*back_enqueued=*/true);
+    if (rc < 0) return rc;
+    if (rc == 2) return 0;  // stopped by an earlier simulation-level error; time does not advance
+    if (rc == 1) {  // the binning was redone with a larger tile capacity: queue the back half again
+      const TileTable T2 = tile_table(h);
+      if (int rc2 = enqueue_rebin(h)) return rc2;
+      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
       LAUNCH_CHECK();
-      h->masks_valid = true;
+      k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt);
+      LAUNCH_CHECK();
     }
-  } else {
-    h->n_active = 0;
+    h->have_grid = true;
+    h->time += (double)dt;
+    ++h->substeps;
+    return 0;
   }
-  h->have_grid = true;
-  stage_end(h);
 
+  // adaptive dt: the host owns the time-step state machine, so every reduction is read back
+  {
+    const int rc = settle_front(h, in, /*back_enqueued=*/false);
+    if (rc < 0) return rc;
+    if (rc == 2) return 0;
+  }
+  if (int rc = enqueue_rebin(h)) return rc;
+  const TileTable T2 = tile_table(h);
+  tile_start = h->tile_start.as<uint32_t>();
   // -- LimitTimeStepBeforeForce (limit_time_step.rs:25-33)
-  if (adaptive_steps) {
-    stage_begin(h, ST_LIMIT);
-    k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, hh, n);
-    LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    stage_end(h);
+  stage_begin(h, ST_LIMIT);
+  k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, hh, n);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  stage_end(h);
+  {
     const bool any = h->h_scalars->live_count > 0;
     h->adaptive.has_sound = h->adaptive.has_isolated = any;
     if (any) {
@@ -362,38 +388,20 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     h->adaptive.push_current_limit();
     if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
   }
-
-  // -- ScatterMomentum (scatter_momentum.rs)
+  // -- ScatterMomentum, MeldGrid + CollectVelocity
   const float dt_scatter = h->adaptive.allowed();
-  const uint32_t persistent = std::max<uint32_t>(1, std::min<uint32_t>(h->n_groups, 148 * 6));
   stage_begin(h, ST_P2G);
-  if (h->n_groups) {
-    k_p2g<<<persistent, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), group_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt_scatter);
-    LAUNCH_CHECK();
-  }
+  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt_scatter);
+  LAUNCH_CHECK();
   stage_end(h);
-
-  // -- MeldGrid + CollectVelocity (+ AdvanceParticles + CullParticles when dt is already known)
-  const uint32_t g2p_grid = std::max<uint32_t>(1, std::min<uint32_t>(h->n_groups, 148 * 12));
-  if (!adaptive_steps) {
-    stage_begin(h, ST_G2P);
-    if (h->n_groups) {
-      k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), group_start, h->nbr.as<int>(), S, h->grid.as<float4>(), h->active_keys.as<unsigned long long>(),
-                                                         h->layer_bits.as<uint32_t>(), L, h->K, dt_scatter);
-      LAUNCH_CHECK();
-    }
-    stage_end(h);
-  } else {
-    stage_begin(h, ST_G2P);
-    if (h->n_groups) {
-      k_g2p<false, true><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), group_start, h->nbr.as<int>(), S, h->grid.as<float4>(), h->active_keys.as<unsigned long long>(),
-                                                         h->layer_bits.as<uint32_t>(), L, h->K, dt_scatter);
-      LAUNCH_CHECK();
-    }
-    // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
-    CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    stage_end(h);
+  stage_begin(h, ST_G2P);
+  k_g2p<false, true><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt_scatter);
+  LAUNCH_CHECK();
+  // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
+  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  stage_end(h);
+  {
     const bool any = h->n_live > 0;
     const float max_vel = any ? total_unkey(h->h_scalars->max_velocity_key) : 0.f;
     h->adaptive.has_velocity = any && max_vel != 0.f;
@@ -402,11 +410,13 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     if (any) h->adaptive.by_deformation = total_unkey(h->h_scalars->min_deformation_key);
     h->adaptive.push_current_limit();
     if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
-    stage_begin(h, ST_ADVANCE);
-    k_advance<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, h->K, n, h->adaptive.allowed());
-    LAUNCH_CHECK();
-    stage_end(h);
   }
+  // -- AdvanceParticles + CullParticles
+  stage_begin(h, ST_ADVANCE);
+  k_advance<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, h->K, n, h->adaptive.allowed());
+  LAUNCH_CHECK();
+  stage_end(h);
+  h->have_grid = true;
   h->time += (double)h->adaptive.allowed();
   ++h->substeps;
   return 0;
@@ -414,9 +424,9 @@ int substep(SvbHandle* h, bool adaptive_steps) {
 
 int read_status(SvbHandle* h) {
   StepScalars* S = h->scalars.as<StepScalars>();
-  CK(cudaMemcpyAsync(&h->h_scalars->status, &S->status, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  h->status |= h->h_scalars->status & 0xffffu;
+  h->status |= (h->h_scalars->status | h->h_scalars->sticky) & 0xffffu;
   return 0;
 }
 
@@ -466,28 +476,25 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   for (auto& e : h->ev_adv) CK(cudaEventCreate(&e));
   CK(cudaMallocHost(&h->h_scalars, sizeof(StepScalars)));
-  CK(cudaMallocHost(&h->h_layout, sizeof(BinLayout)));
+  CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
   const uint32_t n = (uint32_t)p->n;
   h->n = n;
   h->cap = ((size_t)std::max<uint32_t>(n, 1) + 63) & ~(size_t)63;
   for (int b = 0; b < 2; ++b) {
     CK(h->pbuf[b].ensure(h->cap * NFIELDS * 4));
-    CK(h->keys[b].ensure(h->cap * 8));
-    CK(h->idx[b].ensure(h->cap * 4));
   }
   CK(h->energy.ensure(h->cap * 4));
   CK(h->scalars.ensure(sizeof(StepScalars)));
-  CK(h->layout.ensure(sizeof(BinLayout)));
+  CK(h->pcell.ensure(h->cap * 4));
+  CK(h->prank.ensure(h->cap * 4));
+  CK(h->scratch.ensure(4096));
   CK(h->layer_slots.ensure(LAYER_SLOTS * 8));
-  CK(h->slot_rank.ensure(LAYER_SLOTS * 4));
-  CK(h->layer_bits.ensure(LAYER_CAP * 4));
+  CK(h->layer_list.ensure(LAYER_SLOTS * 4));
   CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, h->stream));
   CK(cudaMemsetAsync(h->pbuf[0].p, 0, h->cap * NFIELDS * 4, h->stream));
   CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
-  CK(h->sort_tmp.ensure(sort_temp_bytes(h->cap)));
-  if (int rc = ensure_group_capacity(h, (size_t)n / 64 + 1024)) return rc;
-  if (int rc = ensure_active_capacity(h, (size_t)n / 32 + 1024)) return rc;
+  if (int rc = ensure_tile_capacity(h, (size_t)n / 96 + 2048)) return rc;
 
   if (n) {
     if (!p->flags || !p->mass || !p->initial_volume || !p->mu_or_bulk_modulus || !p->lambda_or_exponent || !p->positions || !p->position_gradients || !p->velocities ||
@@ -534,14 +541,14 @@ void svb_destroy(SvbHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->keys[0], &h->keys[1], &h->idx[0], &h->idx[1], &h->sort_tmp, &h->group_start, &h->group_touch, &h->nbr, &h->cand[0],
-                   &h->cand[1], &h->active_keys, &h->grid, &h->tile_count, &h->node_mask, &h->node_offset, &h->scalars, &h->layout, &h->layer_slots, &h->slot_rank, &h->layer_bits,
+  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->table_keys, &h->table_vals, &h->tile_key, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
+                   &h->grid, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
                    &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e};
   for (DevBuf* b : all) b->release();
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
-  if (h->h_layout) cudaFreeHost(h->h_layout);
+  if (h->ev_front) cudaEventDestroy(h->ev_front);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_adv)
@@ -650,6 +657,7 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (int rc = set_device(h)) return rc;
   h->adaptive.max_time_step = max_time_step;
   h->status = 0;
+  CK(cudaMemsetAsync(h->scalars.p, 0, sizeof(StepScalars), h->stream));
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
   CK(cudaEventRecord(h->ev_adv[0], h->stream));
@@ -703,21 +711,18 @@ int32_t svb_download(SvbHandle* h, SvbParticles* out) {
 
 static int build_node_masks(SvbHandle* h, uint32_t* total) {
   *total = 0;
-  if (!h->have_grid || h->n_active == 0) return 0;
-  const uint32_t na = h->n_active;
-  CK(h->node_offset.ensure((size_t)(na + 1) * 4));
+  if (!h->have_grid || h->n_tiles == 0) return 0;
+  const uint32_t na = h->n_tiles;
   if (!h->masks_valid) {
     // store_grid was off during the last substep: fall back to "node holds mass or momentum"
-    CK(h->node_mask.ensure((size_t)na * 8));
     k_mask_from_values<<<na, 64, 0, h->stream>>>(h->grid.as<float4>(), h->node_mask.as<unsigned long long>());
     LAUNCH_CHECK();
   }
   k_popc_masks<<<blocks_for(na, 256), 256, 0, h->stream>>>(h->node_mask.as<unsigned long long>(), h->node_offset.as<uint32_t>(), na);
   LAUNCH_CHECK();
-  CK(h->tile_count.ensure(4096));
-  k_scan_tiles<<<1, 1024, 0, h->stream>>>(h->node_offset.as<uint32_t>(), na, h->tile_count.as<uint32_t>());
+  k_scan_tiles<<<1, 1024, 0, h->stream>>>(h->node_offset.as<uint32_t>(), nullptr, na, h->scratch.as<uint32_t>());
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(total, h->tile_count.p, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(total, h->scratch.p, 4, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -747,9 +752,8 @@ int32_t svb_download_grid(SvbHandle* h, SvbGrid* out) {
   CK(bits.ensure((size_t)total * 4));
   CK(masses.ensure((size_t)total * 4));
   CK(vels.ensure((size_t)total * 12));
-  k_emit_grid<<<h->n_active, 64, 0, h->stream>>>(h->grid.as<float4>(), h->active_keys.as<unsigned long long>(), h->layer_bits.as<uint32_t>(), h->layout.as<BinLayout>(),
-                                               h->node_mask.as<unsigned long long>(), h->node_offset.as<uint32_t>(), h->n_active, ids.as<int32_t>(), bits.as<uint32_t>(),
-                                               masses.as<float>(), vels.as<float>());
+  k_emit_grid<<<h->n_tiles, 64, 0, h->stream>>>(h->grid.as<float4>(), tile_table(h), meld_info(h), h->scalars.as<StepScalars>(), h->node_mask.as<unsigned long long>(),
+                                              h->node_offset.as<uint32_t>(), ids.as<int32_t>(), bits.as<uint32_t>(), masses.as<float>(), vels.as<float>());
   LAUNCH_CHECK();
   if (out->node_ids) CK(cudaMemcpyAsync(out->node_ids, ids.p, (size_t)total * 12, cudaMemcpyDeviceToHost, h->stream));
   if (out->collider_bits) CK(cudaMemcpyAsync(out->collider_bits, bits.p, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -788,18 +792,17 @@ int32_t svb_binning(SvbHandle* h, uint32_t* sort_map, int32_t* cells) {
   return 0;
 }
 
-int64_t svb_active_block_count(SvbHandle* h) { return h ? (h->have_grid ? (int64_t)h->n_active : 0) : SVB_BAD_ARGUMENT; }
+int64_t svb_active_block_count(SvbHandle* h) { return h ? (h->have_grid ? (int64_t)h->n_tiles : 0) : SVB_BAD_ARGUMENT; }
 
 int32_t svb_active_blocks(SvbHandle* h, int32_t* block_ids, uint32_t* collider_bits) {
   if (!h) return SVB_BAD_ARGUMENT;
   if (int rc = set_device(h)) return rc;
-  const uint32_t na = h->have_grid ? h->n_active : 0;
+  const uint32_t na = h->have_grid ? h->n_tiles : 0;
   if (!na) return 0;
   DevBuf ids, bits;
   CK(ids.ensure((size_t)na * 12));
   CK(bits.ensure((size_t)na * 4));
-  k_decode_active<<<blocks_for(na, 256), 256, 0, h->stream>>>(h->active_keys.as<unsigned long long>(), h->layer_bits.as<uint32_t>(), h->layout.as<BinLayout>(), na, ids.as<int32_t>(),
-                                                             bits.as<uint32_t>());
+  k_decode_active<<<blocks_for(na, 256), 256, 0, h->stream>>>(tile_table(h), h->layer_slots.as<unsigned long long>(), na, ids.as<int32_t>(), bits.as<uint32_t>());
   LAUNCH_CHECK();
   if (block_ids) CK(cudaMemcpyAsync(block_ids, ids.p, (size_t)na * 12, cudaMemcpyDeviceToHost, h->stream));
   if (collider_bits) CK(cudaMemcpyAsync(collider_bits, bits.p, (size_t)na * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -39,42 +39,71 @@ struct ParticleBuf {
   __host__ __device__ uint32_t* u(int field) const { return base + (size_t)field * cap; }
 };
 
-// ---- bin key layout, recomputed every substep from the live bounding box (device resident)
-//   key = tomb | bx | by | bz | layer | cell(6)     (most significant first)
-// bx/by/bz: block coordinates (node >> 2) relative to `block_min`; layer: rank of the particle's
-// collider bits among the distinct values present this substep; cell: (cx<<4 | cy<<2 | cz) of the
-// base node inside its block.
-struct BinLayout {
-  int32_t block_min[3];
-  int32_t nb[3];        // bits per block axis
-  int32_t nl;           // bits for the layer rank
-  int32_t total_bits;   // nb[0]+nb[1]+nb[2]+nl+6 ; the tombstone bit is bit `total_bits`
-  int32_t n_layers;
-  int32_t cell_min[3], cell_max[3];  // live bounding box of base nodes (debug / multi-GPU)
+// ---- grid tiles.  A tile = one 4x4x4-node block of one collider-bits layer; its 64-bit key packs the
+// absolute block coordinates (node >> 2, biased by 2^16, 17 bits per axis) and the layer id (13 bits):
+//   key = bx | by | bz | layer      (most significant first)
+// Tiles live in an open-addressing table (key -> dense tile id) that is rebuilt every substep; ids
+// are handed out in insertion order, tiles that own particles first, halo-only tiles after.
+// The layer id of a collider-bits pattern is 0 for "no collider near" and slot+1 in the small
+// per-substep set of distinct patterns otherwise.
+constexpr int BLOCK_BITS = 17;
+constexpr int BLOCK_BIAS = 1 << 16;
+constexpr int LAYER_BITS = 13;
+constexpr int LAYER_SLOTS = 4096;     // distinct collider-bit patterns per substep (open addressing)
+constexpr int SIB_MAX = 12;           // compatible sibling layers of one block a G2P tile load can sum
+constexpr unsigned long long TILE_EMPTY = ~0ull;
+constexpr uint32_t TILE_PENDING = 0xffffffffu;
+
+__host__ __device__ inline unsigned long long tile_key_pack(int bx, int by, int bz, uint32_t layer) {
+  return ((((unsigned long long)(uint32_t)(bx + BLOCK_BIAS) << BLOCK_BITS | (unsigned long long)(uint32_t)(by + BLOCK_BIAS)) << BLOCK_BITS |
+           (unsigned long long)(uint32_t)(bz + BLOCK_BIAS))
+          << LAYER_BITS) |
+         layer;
+}
+__host__ __device__ inline void tile_key_unpack(unsigned long long k, int& bx, int& by, int& bz, uint32_t& layer) {
+  layer = (uint32_t)(k & ((1u << LAYER_BITS) - 1));
+  k >>= LAYER_BITS;
+  bz = (int)(k & ((1u << BLOCK_BITS) - 1)) - BLOCK_BIAS;
+  k >>= BLOCK_BITS;
+  by = (int)(k & ((1u << BLOCK_BITS) - 1)) - BLOCK_BIAS;
+  k >>= BLOCK_BITS;
+  bx = (int)k - BLOCK_BIAS;
+}
+// key of the neighbour tile at block offset d (bit0 = +x, bit1 = +y, bit2 = +z), same layer
+__host__ __device__ inline unsigned long long tile_key_offset(unsigned long long k, int d) {
+  if (d & 1) k += 1ull << (2 * BLOCK_BITS + LAYER_BITS);
+  if (d & 2) k += 1ull << (BLOCK_BITS + LAYER_BITS);
+  if (d & 4) k += 1ull << LAYER_BITS;
+  return k;
+}
+
+struct TileTable {
+  unsigned long long* keys;   // [mask + 1], TILE_EMPTY when free
+  uint32_t* vals;             // [mask + 1], tile id (TILE_PENDING until published)
+  uint32_t mask;
+  unsigned long long* tile_key;  // [tile_cap] key of tile id
+  uint32_t tile_cap;
 };
-constexpr int LAYER_CAP = 4096;       // distinct collider-bit patterns per substep
-constexpr int LAYER_SLOTS = 8192;     // open-addressing set backing the rank table
 
 // ---- per-substep scalars that kernels read from HBM (so launches do not depend on host values)
+constexpr uint32_t ST_KEY_RANGE = 0x80000000u;   // a live particle lies outside the +-2^18-cell key range
+constexpr uint32_t ST_TILE_OVERFLOW = 0x40000000u;  // tile capacity exceeded: the host grows it and redoes the binning
+constexpr uint32_t ST_ABORT_MASK = ST_KEY_RANGE | ST_TILE_OVERFLOW;
 struct StepScalars {
-  float dt_force;      // dt seen by collide / external force
-  float dt_scatter;    // dt seen by P2G
-  float dt_advance;    // dt seen by advance
-  float factor_b;      // keyframe interpolation factor
-  float gravity[3];    // interpolated
   uint32_t n;          // resident particles (incl. tombstoned)
   uint32_t n_live;     // particles with a bin (not tombstoned)
-  uint32_t n_groups;   // (block, layer) runs of particles
-  uint32_t n_cand;
-  uint32_t n_active;   // active (block, layer) grid tiles
-  uint32_t status;     // SVB_* simulation-level bits
+  uint32_t n_tomb;
+  uint32_t n_tiles;    // active (block, layer) grid tiles
+  uint32_t n_ptiles;   // tiles that own particles = ids [0, n_ptiles): the work list of P2G / G2P
+  uint32_t n_layers;   // distinct non-zero collider-bit patterns
+  uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];
-  int32_t bbox_min[3], bbox_max[3];  // atomics target for the next layout
   // adaptive time step reductions (f32::total_cmp keys)
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;
-  uint32_t layer_count;
+  uint32_t sticky;     // simulation-level error bits that stop the run (SVB_PARTICLE_CLOSE_TO_INVERTED); survives the per-substep reset
 };
+#define SVB_ABORTED(S) (((S)->status & ST_ABORT_MASK) || (S)->sticky)
 
 struct MeshDev {
   uint32_t n_vertices, n_triangles, n_colliders;

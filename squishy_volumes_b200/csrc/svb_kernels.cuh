@@ -2,11 +2,11 @@
 //
 // Phase map to the reference's CPU back end (/root/reference/rust/crates/cpu/src/phase/*.rs):
 //   k_mesh_*            interpolate_input.rs:18-107      collider mesh lerp, face / vertex normals
-//   k_force             collide.rs:21-206 + external_force.rs:17-50 (+ live bounding box, layer set)
-//   k_layout, k_keys    sort.rs:29-33                     bin keys from floor(x/h - 1/2)
-//   k_permute           sort.rs:91-101                    gather the SoA state into binned order
-//   k_flag_*            update_grid_nodes.rs:31-156       block / layer activation (sorted, no hash map)
-//   k_group_touch, k_neighbors                            which neighbour blocks a run of particles touches
+//   k_bin               collide.rs:21-206 + external_force.rs:17-50 + sort.rs:29-33 (cell of floor(x/h - 1/2))
+//                       + update_grid_nodes.rs:31-156 (tile activation): single-pass counting sort on (tile, cell)
+//   k_cell_scan, k_scan_tiles                             cell / tile offsets of the binned order
+//   k_halo              update_grid_nodes.rs:102-108      neighbour tiles reached by each tile's particles
+//   k_permute           sort.rs:91-101                    scatter the SoA state into binned order
 //   k_p2g               scatter_momentum.rs:22-93         particle -> grid, stress once per particle
 //   k_g2p               meld_grid.rs:16-69 + collect_velocity.rs:19-75 + advance_particles.rs:17-93
 //                       + cull_particles.rs:17-41 (+ limit_time_step.rs:187-223 reductions)
@@ -217,247 +217,225 @@ __device__ __noinline__ uint32_t collide_particle(const MeshDev& M, const SimCon
 }
 
 // ------------------------------------------------------------------------------------------------
-// layer set: distinct non-zero collider-bit patterns of the live particles of this substep
+// layer set: distinct non-zero collider-bit patterns of the live particles of this substep.
+// layer id = slot + 1 (0 = "no collider near"); slots hold (1<<32 | bits), 0 = free.
 __device__ __forceinline__ uint32_t layer_hash(uint32_t b) {
   b ^= b >> 16; b *= 0x7feb352du; b ^= b >> 15; b *= 0x846ca68bu; b ^= b >> 16;
   return b & (LAYER_SLOTS - 1);
 }
-__device__ __forceinline__ void layer_insert(unsigned long long* slots, uint32_t bits, StepScalars* S) {
-  const unsigned long long want = (1ull << 32) | bits;
-  uint32_t s = layer_hash(bits);
-  for (int tries = 0; tries < LAYER_SLOTS; ++tries) {
-    unsigned long long cur = slots[s];
-    if (cur == want) return;
-    if (cur == 0ull) {
-      cur = atomicCAS(&slots[s], 0ull, want);
-      if (cur == 0ull || cur == want) return;
-    }
-    s = (s + 1) & (LAYER_SLOTS - 1);
-  }
-  atomicOr(&S->status, 1u /*SVB_TABLE_TRIES_EXCEEDED*/);
-}
-__device__ __forceinline__ uint32_t layer_rank(const unsigned long long* __restrict__ slots, const uint32_t* __restrict__ slot_rank, uint32_t bits) {
+__device__ __forceinline__ uint32_t layer_find_or_insert(unsigned long long* slots, uint32_t* layer_list, uint32_t bits, StepScalars* S) {
   if (bits == 0u) return 0u;
   const unsigned long long want = (1ull << 32) | bits;
   uint32_t s = layer_hash(bits);
   for (int tries = 0; tries < LAYER_SLOTS; ++tries) {
-    const unsigned long long cur = slots[s];
-    if (cur == want) return slot_rank[s];
-    if (cur == 0ull) break;
+    unsigned long long cur = *(volatile unsigned long long*)&slots[s];
+    if (cur == 0ull) {
+      cur = atomicCAS(&slots[s], 0ull, want);
+      if (cur == 0ull) {
+        const uint32_t at = atomicAdd(&S->n_layers, 1u);
+        layer_list[at] = s + 1;
+        return s + 1;
+      }
+    }
+    if (cur == want) return s + 1;
     s = (s + 1) & (LAYER_SLOTS - 1);
   }
-  return 0u;  // unreachable when k_force registered the value
+  atomicOr(&S->status, 1u /*SVB_TABLE_TRIES_EXCEEDED*/);
+  return 0u;
+}
+__device__ __forceinline__ uint32_t layer_bits_of(const unsigned long long* __restrict__ slots, uint32_t layer) {
+  return layer == 0u ? 0u : (uint32_t)slots[layer - 1];
 }
 
 // ------------------------------------------------------------------------------------------------
-// collide + external force, one thread per particle (current order).  Also accumulates the live
-// bounding box of base nodes for the next bin layout and registers collider-bit layers.
+// tile table (update_grid_nodes.rs:31-156 without the hash map rebuild: the table is cleared and
+// refilled every substep, so there are no stale nodes)
+__device__ __forceinline__ uint32_t tile_hash(unsigned long long k, uint32_t mask) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k & mask;
+}
+// returns the tile id, or TILE_PENDING when the tile capacity is exhausted (status bit set)
+__device__ __forceinline__ uint32_t tile_find_or_insert(const TileTable& T, unsigned long long key, StepScalars* S) {
+  uint32_t s = tile_hash(key, T.mask);
+  for (uint32_t tries = 0; tries <= T.mask; ++tries) {
+    unsigned long long cur = *(volatile unsigned long long*)&T.keys[s];
+    if (cur == TILE_EMPTY) {
+      cur = atomicCAS(&T.keys[s], TILE_EMPTY, key);
+      if (cur == TILE_EMPTY) {
+        const uint32_t id = atomicAdd(&S->n_tiles, 1u);
+        if (id < T.tile_cap) {
+          T.tile_key[id] = key;
+          __threadfence();
+          *(volatile uint32_t*)&T.vals[s] = id;
+          return id;
+        }
+        atomicOr(&S->status, ST_TILE_OVERFLOW);
+        *(volatile uint32_t*)&T.vals[s] = TILE_PENDING - 1;  // poisoned: waiters stop spinning
+        return TILE_PENDING;
+      }
+    }
+    if (cur == key) {
+      uint32_t v;
+      while ((v = *(volatile uint32_t*)&T.vals[s]) == TILE_PENDING) {}
+      return v == TILE_PENDING - 1 ? TILE_PENDING : v;
+    }
+    s = (s + 1) & T.mask;
+  }
+  atomicOr(&S->status, ST_TILE_OVERFLOW);
+  return TILE_PENDING;
+}
+__device__ __forceinline__ int tile_find(const TileTable& T, unsigned long long key) {
+  uint32_t s = tile_hash(key, T.mask);
+  for (uint32_t tries = 0; tries <= T.mask; ++tries) {
+    const unsigned long long cur = T.keys[s];
+    if (cur == key) {
+      const uint32_t v = T.vals[s];
+      return v >= TILE_PENDING - 1 ? -1 : (int)v;
+    }
+    if (cur == TILE_EMPTY) return -1;
+    s = (s + 1) & T.mask;
+  }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bin — collide + external force + binning, one thread per particle in the CURRENT order.
+//   * collide.rs / external_force.rs edit v and the collider bits in place (skipped on a re-bin redo);
+//   * the particle's tile (block of its base node, layer of its collider bits) is found or created in
+//     the tile table, warp-aggregated: lanes with equal keys elect one lane to touch the table;
+//   * the particle takes a slot in its cell: rank = atomicAdd(cell_count[tile*64 + cell]) (again one
+//     atomic per distinct cell per warp) — a single-pass counting sort on (tile, cell);
+//   * the tile remembers which of its 8 neighbour blocks its particles' stencils reach.
 struct GoalDev {
   const uint32_t* flags_a; const uint32_t* flags_b;   // original order, may be null
   const float* goal_a; const float* goal_b;           // 3 per particle, original order
 };
-template <bool HAS_MESH>
-__global__ void __launch_bounds__(256) k_force(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, GoalDev G, unsigned long long* layer_slots,
-                                               uint32_t n, float dt, float gx, float gy, float gz, float factor_b) {
+struct BinArrays {
+  uint32_t* pcell;        // [n] tile*64 + cell, 0xffffffff for tombstoned
+  uint32_t* prank;        // [n] slot inside the cell (or among the tombstoned)
+  uint32_t* cell_count;   // [tile_cap*64]
+  uint32_t* tile_touch;   // [tile_cap] 8-bit mask over neighbour offsets d
+  unsigned long long* layer_slots;
+  uint32_t* layer_list;
+};
+__global__ void k_reset_scalars(StepScalars* S, uint32_t n) {
+  if (threadIdx.x != 0) return;
+  const uint32_t sticky = S->sticky;
+  StepScalars z{};
+  z.n = n;
+  z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
+  z.sticky = sticky;
+  *S = z;
+}
+template <bool HAS_MESH, bool APPLY_FORCE>
+__global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, GoalDev G, TileTable T, BinArrays B, uint32_t n, float dt, float gx, float gy,
+                                             float gz, float factor_b) {
+  if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  int mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  const uint32_t lane = threadIdx.x & 31;
+  bool live = false, tomb = false;
+  unsigned long long key = TILE_EMPTY;
+  uint32_t cell = 0, touch = 0;
   if (i < n) {
     const uint32_t flags = P.u(PFLAGS)[i];
-    if (!(flags & F_TOMBSTONED)) {
+    tomb = (flags & F_TOMBSTONED) != 0;
+    if (!tomb) {
       const V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-      V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-      uint32_t bits = 0u;
-      if (HAS_MESH) {
-        const uint32_t old_bits = P.u(PBITS)[i];
-        bits = collide_particle(M, K, dt, x, v, old_bits);
-        if (bits != 0u) layer_insert(layer_slots, bits, S);
-      }
-      P.u(PBITS)[i] = bits;
-      bool goal = false;
-      if (G.flags_a) {
-        const uint32_t o = P.u(PORIG)[i];
-        if ((G.flags_a[o] & F_HAS_GOAL) && (G.flags_b[o] & F_HAS_GOAL)) {
-          const float fa = 1.f - factor_b;
-          const V3 ga = ld3(G.goal_a, o), gb = ld3(G.goal_b, o);
-          const V3 target = fa * ga + factor_b * gb;
-          v = (target - x) / dt;
-          goal = true;
+      uint32_t bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
+      if (APPLY_FORCE) {
+        V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+        if (HAS_MESH) bits = collide_particle(M, K, dt, x, v, bits);
+        P.u(PBITS)[i] = bits;
+        bool goal = false;
+        if (G.flags_a) {
+          const uint32_t o = P.u(PORIG)[i];
+          if ((G.flags_a[o] & F_HAS_GOAL) && (G.flags_b[o] & F_HAS_GOAL)) {
+            const float fa = 1.f - factor_b;
+            const V3 target = fa * ld3(G.goal_a, o) + factor_b * ld3(G.goal_b, o);
+            v = (target - x) / dt;
+            goal = true;
+          }
         }
+        if (!goal) v = v + dt * V3{gx, gy, gz};
+        P.f(PV)[i] = v.x; P.f(PV + 1)[i] = v.y; P.f(PV + 2)[i] = v.z;
       }
-      if (!goal) v = v + dt * V3{gx, gy, gz};
-      P.f(PV)[i] = v.x; P.f(PV + 1)[i] = v.y; P.f(PV + 2)[i] = v.z;
-      mn[0] = mx[0] = base_node(x.x, K.h);
-      mn[1] = mx[1] = base_node(x.y, K.h);
-      mn[2] = mx[2] = base_node(x.z, K.h);
+      const int s0 = base_node(x.x, K.h), s1 = base_node(x.y, K.h), s2 = base_node(x.z, K.h);
+      const int b0 = floor_div4(s0), b1 = floor_div4(s1), b2 = floor_div4(s2);
+      const int lim = BLOCK_BIAS - 2;
+      if (b0 < -lim || b0 > lim || b1 < -lim || b1 > lim || b2 < -lim || b2 > lim) {
+        atomicOr(&S->status, ST_KEY_RANGE);
+      } else {
+        live = true;
+        const uint32_t layer = HAS_MESH ? layer_find_or_insert(B.layer_slots, B.layer_list, bits, S) : 0u;
+        key = tile_key_pack(b0, b1, b2, layer);
+        cell = ((uint32_t)(s0 & 3) << 4) | ((uint32_t)(s1 & 3) << 2) | (uint32_t)(s2 & 3);
+        // neighbour offsets reached by the 3-node stencil: +1 on an axis iff the in-block coordinate >= 2
+        touch = 1u;
+        if (s0 & 2) touch |= touch << 1;
+        if (s1 & 2) touch |= touch << 2;
+        if (s2 & 2) touch |= touch << 4;
+      }
     }
   }
-  // block-level min/max, then at most 6 atomics per CTA — and only when they would change the box
-  // (same-address atomics from every warp serialise in L2: 32 k warps cost ~100 us at 1 M particles)
-  __shared__ int s_lo[3][8], s_hi[3][8];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    int lo = mn[a], hi = mx[a];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      lo = min(lo, __shfl_xor_sync(SVB_FULL, lo, o));
-      hi = max(hi, __shfl_xor_sync(SVB_FULL, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) { s_lo[a][threadIdx.x >> 5] = lo; s_hi[a][threadIdx.x >> 5] = hi; }
+  // ---- tile: one table access per distinct key in the warp
+  const unsigned peers = __match_any_sync(SVB_FULL, key);
+  const int leader = __ffs(peers) - 1;
+  uint32_t tile = TILE_PENDING;
+  if (live && (int)lane == leader) tile = tile_find_or_insert(T, key, S);
+  tile = __shfl_sync(SVB_FULL, tile, leader);
+  const uint32_t tm = __reduce_or_sync(peers, touch);
+  if (live && (int)lane == leader && tile != TILE_PENDING) {
+    if ((B.tile_touch[tile] & tm) != tm) atomicOr(&B.tile_touch[tile], tm);
   }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    const int a = threadIdx.x;
-    int lo = s_lo[a][0], hi = s_hi[a][0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) { lo = min(lo, s_lo[a][w]); hi = max(hi, s_hi[a][w]); }
-    if (lo <= hi) {
-      if (lo < *(volatile int*)&S->bbox_min[a]) atomicMin(&S->bbox_min[a], lo);
-      if (hi > *(volatile int*)&S->bbox_max[a]) atomicMax(&S->bbox_max[a], hi);
-    }
+  // ---- slot in the cell: one atomic per distinct (tile, cell) in the warp
+  const bool binned = live && tile != TILE_PENDING;
+  const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : 0xfffffffeu);
+  const unsigned cpeers = __match_any_sync(SVB_FULL, ci);
+  const int cleader = __ffs(cpeers) - 1;
+  uint32_t base = 0;
+  if ((int)lane == cleader) {
+    if (binned) base = atomicAdd(&B.cell_count[ci], (uint32_t)__popc(cpeers));
+    else if (tomb) base = atomicAdd(&S->n_tomb, (uint32_t)__popc(cpeers));
+  }
+  base = __shfl_sync(SVB_FULL, base, cleader);
+  if (i < n) {
+    B.pcell[i] = ci;
+    B.prank[i] = base + __popc(cpeers & ((1u << lane) - 1u));
   }
 }
 
-// One CTA: bin-key layout from the live bounding box + ranks of the collider-bit layers.
-__global__ void __launch_bounds__(1024) k_layout(StepScalars* S, BinLayout* L, const unsigned long long* __restrict__ layer_slots, uint32_t* slot_rank, uint32_t* layer_bits) {
-  __shared__ uint32_t vals[LAYER_CAP];
-  __shared__ uint32_t vslot[LAYER_CAP];
-  __shared__ uint32_t count;
-  if (threadIdx.x == 0) count = 0;
-  __syncthreads();
-  for (uint32_t s = threadIdx.x; s < LAYER_SLOTS; s += blockDim.x) {
-    const unsigned long long e = layer_slots[s];
-    if (e != 0ull) {
-      const uint32_t at = atomicAdd(&count, 1u);
-      if (at < LAYER_CAP - 1) { vals[at] = (uint32_t)e; vslot[at] = s; }
+// per particle-owning tile: exclusive scan of its 64 cell counts (in place) and the tile total
+__global__ void __launch_bounds__(256) k_cell_scan(StepScalars* S, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_total, uint32_t tile_cap) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_ptiles = min(S->n_tiles, tile_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) S->n_ptiles = n_ptiles;
+  if (SVB_ABORTED(S)) return;
+  for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_ptiles; t += warps) {
+    const uint2 c = *reinterpret_cast<const uint2*>(cell_count + (size_t)t * 64 + 2 * lane);
+    const uint32_t mine = c.x + c.y;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(SVB_FULL, inc, o);
+      if (lane >= (uint32_t)o) inc += v;
     }
-  }
-  __syncthreads();
-  uint32_t nvals = count;
-  if (nvals > LAYER_CAP - 1) {
-    nvals = LAYER_CAP - 1;
-    if (threadIdx.x == 0) atomicOr(&S->status, 1u);
-  }
-  for (uint32_t q = threadIdx.x; q < nvals; q += blockDim.x) {
-    const uint32_t v = vals[q];
-    uint32_t r = 1;
-    for (uint32_t o = 0; o < nvals; ++o) r += vals[o] < v ? 1u : 0u;
-    slot_rank[vslot[q]] = r;
-    layer_bits[r] = v;
-  }
-  if (threadIdx.x == 0) {
-    layer_bits[0] = 0u;
-    BinLayout l;
-    int total = 6;
-    for (int a = 0; a < 3; ++a) {
-      int lo = S->bbox_min[a], hi = S->bbox_max[a];
-      if (lo > hi) { lo = 0; hi = 0; }  // no live particle
-      l.cell_min[a] = lo; l.cell_max[a] = hi;
-      const int bmin = floor_div4(lo), bmax = floor_div4(hi + 2);
-      l.block_min[a] = bmin;
-      l.nb[a] = ceil_log2_u32((uint32_t)(bmax - bmin + 1));
-      total += l.nb[a];
-    }
-    l.n_layers = (int)nvals + 1;
-    l.nl = ceil_log2_u32((uint32_t)l.n_layers);
-    total += l.nl;
-    l.total_bits = total;
-    if (total > 62) atomicOr(&S->status, 0x80000000u);  // SVB_KEY_RANGE
-    *L = l;
-    S->layer_count = (uint32_t)l.n_layers;
-    S->n_live = 0; S->n_groups = 0; S->n_cand = 0; S->n_active = 0;
-    S->work_counter[0] = S->work_counter[1] = S->work_counter[2] = S->work_counter[3] = 0;
+    const uint32_t ex = inc - mine;
+    *reinterpret_cast<uint2*>(cell_count + (size_t)t * 64 + 2 * lane) = make_uint2(ex, ex + c.x);
+    if (lane == 31) tile_total[t] = inc;
   }
 }
 
-// bin key of every particle (cpu/src/phase/sort.rs:29-33 — the cell (i,j,k) is bit-exact; the ORDER
-// is block-major so that one run of the sorted array is one (block, layer) tile of work).
-__global__ void __launch_bounds__(256) k_keys(ParticleBuf P, const BinLayout* __restrict__ Lp, const unsigned long long* __restrict__ layer_slots,
-                                              const uint32_t* __restrict__ slot_rank, float h, uint32_t n, unsigned long long* __restrict__ keys, uint32_t* __restrict__ idx) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const BinLayout L = *Lp;
-  const uint32_t flags = P.u(PFLAGS)[i];
-  unsigned long long key;
-  if (flags & F_TOMBSTONED) {
-    key = 1ull << L.total_bits;
-  } else {
-    const int sx = base_node(P.f(PX)[i], h), sy = base_node(P.f(PX + 1)[i], h), sz = base_node(P.f(PX + 2)[i], h);
-    const unsigned long long bx = (unsigned long long)(floor_div4(sx) - L.block_min[0]);
-    const unsigned long long by = (unsigned long long)(floor_div4(sy) - L.block_min[1]);
-    const unsigned long long bz = (unsigned long long)(floor_div4(sz) - L.block_min[2]);
-    const uint32_t rank = L.nl ? layer_rank(layer_slots, slot_rank, P.u(PBITS)[i]) : 0u;
-    const uint32_t cell = ((uint32_t)(sx & 3) << 4) | ((uint32_t)(sy & 3) << 2) | (uint32_t)(sz & 3);
-    key = (((((bx << L.nb[1]) | by) << L.nb[2]) | bz) << L.nl | rank) << 6 | cell;
-  }
-  keys[i] = key;
-  idx[i] = i;
-}
-
-// physical re-bin: dst[f][i] = src[f][idx[i]] for every field
-__global__ void __launch_bounds__(256) k_permute(ParticleBuf src, ParticleBuf dst, const uint32_t* __restrict__ idx, uint32_t n) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t j = idx[i];
-  uint32_t v[NFIELDS];
-#pragma unroll
-  for (int f = 0; f < NFIELDS; ++f) v[f] = __ldg(src.base + (size_t)f * src.cap + j);
-#pragma unroll
-  for (int f = 0; f < NFIELDS; ++f) dst.base[(size_t)f * dst.cap + i] = v[f];
-}
-
-// ------------------------------------------------------------------------------------------------
-// run heads by a 3-kernel exclusive scan.  MODE 0: heads of (block, layer) runs in the sorted
-// particle keys (key >> 6 changes, tombstoned excluded) -> out_pos[g] = first particle of run g.
-// MODE 1: unique values of the sorted candidate keys (~0 = empty) -> out_key[a] = key.
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-template <int MODE>
-__device__ __forceinline__ bool head_flag(const unsigned long long* __restrict__ keys, uint32_t i, uint32_t n, int total_bits) {
-  if (i >= n) return false;
-  const unsigned long long k = keys[i];
-  if (MODE == 0) {
-    if (k >> total_bits) return false;
-    return i == 0 || (keys[i - 1] >> 6) != (k >> 6);
-  } else {
-    if (k >> (total_bits - 6)) return false;  // empty candidate slot (bit just above the tile-key range)
-    return i == 0 || keys[i - 1] != k;
-  }
-}
-template <int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) k_flag_count(const unsigned long long* __restrict__ keys, const uint32_t* n_ptr, uint32_t n_mul, const BinLayout* __restrict__ L,
-                                                             uint32_t* __restrict__ tile_count, StepScalars* S) {
-  const uint32_t n = n_ptr ? *n_ptr * n_mul : n_mul;
-  const int tb = L->total_bits;
-  uint32_t c = 0;
-  const uint32_t base = blockIdx.x * SCAN_TILE;
-#pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; ++q) {
-    const uint32_t i = base + q * SCAN_THREADS + threadIdx.x;
-    c += head_flag<MODE>(keys, i, n, tb) ? 1u : 0u;
-    if (MODE == 0 && i < n && !(keys[i] >> tb) && (i + 1 == n || (keys[i + 1] >> tb))) S->n_live = i + 1;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(SVB_FULL, c, o);
-  __shared__ uint32_t ws[SCAN_THREADS / 32];
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) t += ws[w];
-    tile_count[blockIdx.x] = t;
-  }
-}
-// single CTA: exclusive scan of the tile counts in place; total -> *total_out
-__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint32_t n_tiles, uint32_t* total_out) {
+// single CTA: exclusive scan in place; a[n] = total; *total_out = total
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* a, const uint32_t* n_ptr, uint32_t n_fixed, uint32_t* total_out) {
   __shared__ uint32_t ws[32];
   __shared__ uint32_t carry;
+  const uint32_t n = n_ptr ? *n_ptr : n_fixed;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (uint32_t base = 0; base < n_tiles; base += 1024) {
+  for (uint32_t base = 0; base < n; base += 1024) {
     const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < n_tiles ? tile_count[i] : 0u;
+    const uint32_t v = i < n ? a[i] : 0u;
     uint32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -478,110 +456,57 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* tile_count, uint3
     __syncthreads();
     const uint32_t warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0u;
     const uint32_t c = carry;
-    if (i < n_tiles) tile_count[i] = c + warp_off + inc - v;
+    if (i < n) a[i] = c + warp_off + inc - v;
     __syncthreads();
     if (threadIdx.x == 1023) carry = c + warp_off + inc;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total_out = carry;
-}
-template <int MODE>
-__global__ void __launch_bounds__(SCAN_THREADS) k_flag_write(const unsigned long long* __restrict__ keys, const uint32_t* n_ptr, uint32_t n_mul, const BinLayout* __restrict__ L,
-                                                             const uint32_t* __restrict__ tile_offset, uint32_t* __restrict__ out_pos, unsigned long long* __restrict__ out_key,
-                                                             uint32_t out_cap, StepScalars* S) {
-  const uint32_t n = n_ptr ? *n_ptr * n_mul : n_mul;
-  const int tb = L->total_bits;
-  // blocked arrangement so output order = input order
-  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  bool fl[SCAN_ITEMS];
-  uint32_t c = 0;
-#pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; ++q) {
-    fl[q] = head_flag<MODE>(keys, base + q, n, tb);
-    c += fl[q] ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    a[n] = carry;
+    if (total_out) *total_out = carry;
   }
-  uint32_t inc = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(SVB_FULL, inc, o);
-    if ((threadIdx.x & 31) >= o) inc += t;
-  }
-  __shared__ uint32_t ws[SCAN_THREADS / 32];
-  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
-  __syncthreads();
-  uint32_t off = tile_offset[blockIdx.x] + inc - c;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += ws[w];
-#pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; ++q)
-    if (fl[q]) {
-      if (off < out_cap) {
-        if (MODE == 0) out_pos[off] = base + q;
-        else out_key[off] = keys[base + q];
-      } else {
-        atomicOr(&S->status, 4u /*SVB_INDIRECT_LIMIT_EXCEEDED*/);
-      }
-      ++off;
-    }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Which of the 8 neighbour blocks (offsets d in {0,1}^3) does a run of particles touch?  A particle
-// whose base node sits at in-block coordinate c touches block +1 on an axis iff c >= 2 (stencil
-// c..c+2).  One warp per run; emits up to 8 candidate tile keys per run.
-__device__ __forceinline__ unsigned long long group_delta(const BinLayout& L, int d) {
-  unsigned long long r = 0;
-  if (d & 1) r += 1ull << (L.nb[1] + L.nb[2] + L.nl);
-  if (d & 2) r += 1ull << (L.nb[2] + L.nl);
-  if (d & 4) r += 1ull << L.nl;
-  return r;
-}
-__global__ void __launch_bounds__(256) k_group_touch(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ group_start, const BinLayout* __restrict__ Lp,
-                                                     const StepScalars* __restrict__ S, unsigned long long* __restrict__ cand, uint32_t* __restrict__ group_touch) {
-  const BinLayout L = *Lp;
-  const uint32_t n_groups = S->n_groups, n_live = S->n_live;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
-    const uint32_t start = group_start[g];
-    const uint32_t end = g + 1 < n_groups ? group_start[g + 1] : n_live;
-    uint32_t t = 0;
-    for (uint32_t i = start + lane; i < end; i += 32) {
-      const uint32_t cell = (uint32_t)keys[i] & 63u;
-      const uint32_t m = ((cell >> 5) & 1u) | (((cell >> 3) & 1u) << 1) | (((cell >> 1) & 1u) << 2);  // c >= 2 per axis
-      // subsets of m as a mask over d (bit0 = +x, bit1 = +y, bit2 = +z)
-      uint32_t sub = 1u;
-      if (m & 1u) sub |= sub << 1;
-      if (m & 2u) sub |= sub << 2;
-      if (m & 4u) sub |= sub << 4;
-      t |= sub;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t |= __shfl_xor_sync(SVB_FULL, t, o);
-    if (lane < 8) {
-      const unsigned long long gk = keys[start] >> 6;
-      cand[(size_t)g * 8 + lane] = ((t >> lane) & 1u) ? gk + group_delta(L, (int)lane) : (1ull << (L.total_bits - 6));
-    }
-    if (lane == 0) group_touch[g] = t;
-  }
-}
-__device__ __forceinline__ int find_key(const unsigned long long* __restrict__ a, uint32_t n, unsigned long long k) {
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (a[mid] < k) lo = mid + 1; else hi = mid;
-  }
-  return (lo < n && a[lo] == k) ? (int)lo : -1;
-}
-__global__ void __launch_bounds__(256) k_neighbors(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ group_start, const uint32_t* __restrict__ group_touch,
-                                                   const BinLayout* __restrict__ Lp, const StepScalars* __restrict__ S, const unsigned long long* __restrict__ active_keys,
-                                                   int* __restrict__ nbr) {
-  const BinLayout L = *Lp;
-  const uint32_t n_groups = S->n_groups, n_active = S->n_active;
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_groups * 8; q += gridDim.x * blockDim.x) {
-    const uint32_t g = q >> 3, d = q & 7;
+// per particle-owning tile: create the halo tiles its particles reach and record the 8 neighbour ids
+__global__ void __launch_bounds__(256) k_halo(StepScalars* S, TileTable T, const uint32_t* __restrict__ tile_touch, int* __restrict__ nbr) {
+  if (SVB_ABORTED(S)) return;
+  const uint32_t n_ptiles = S->n_ptiles;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_ptiles * 8; q += gridDim.x * blockDim.x) {
+    const uint32_t t = q >> 3, d = q & 7;
     int r = -1;
-    if ((group_touch[g] >> d) & 1u) r = find_key(active_keys, n_active, (keys[group_start[g]] >> 6) + group_delta(L, (int)d));
+    if (d == 0) r = (int)t;
+    else if ((tile_touch[t] >> d) & 1u) {
+      const uint32_t id = tile_find_or_insert(T, tile_key_offset(T.tile_key[t], (int)d), S);
+      r = id == TILE_PENDING ? -1 : (int)id;
+    }
     nbr[q] = r;
+  }
+}
+
+// physical re-bin (sort.rs:91-101): every field of particle i moves to its slot
+//   dst = tile_start[tile] + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
+__global__ void __launch_bounds__(256) k_permute(ParticleBuf src, ParticleBuf dst, const StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank,
+                                                 const uint32_t* __restrict__ cell_offset, const uint32_t* __restrict__ tile_start, uint32_t n) {
+  if (SVB_ABORTED(S)) return;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t ci = pcell[i];
+  uint32_t j;
+  if (ci == 0xffffffffu) j = S->n_live + prank[i];
+  else j = tile_start[ci >> 6] + cell_offset[ci] + prank[i];
+  uint32_t v[NFIELDS];
+#pragma unroll
+  for (int f = 0; f < NFIELDS; ++f) v[f] = __ldg(src.base + (size_t)f * src.cap + i);
+#pragma unroll
+  for (int f = 0; f < NFIELDS; ++f) dst.base[(size_t)f * dst.cap + j] = v[f];
+}
+
+__global__ void __launch_bounds__(256) k_zero_grid(const StepScalars* __restrict__ S, float4* __restrict__ grid, unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
+  if (SVB_ABORTED(S)) return;
+  const size_t total = (size_t)min(S->n_tiles, tile_cap) * 64;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+    grid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (node_mask && (q & 63) == 0) node_mask[q >> 6] = 0ull;
   }
 }
 
@@ -614,7 +539,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* my_tile = tiles + warp * TILE_NODES;
   float* stage = stage_all + warp * 32 * STAGE_STRIDE;
-  const uint32_t n_groups = S->n_groups, n_live = S->n_live;
+  if (SVB_ABORTED(S)) return;
+  const uint32_t n_groups = S->n_ptiles;
   const float scaling = dt * 4.f / (h * h);
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
@@ -632,7 +558,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
     const uint32_t g = s_group;
     if (g >= n_groups) break;
     const uint32_t start = group_start[g];
-    const uint32_t end = g + 1 < n_groups ? group_start[g + 1] : n_live;
+    const uint32_t end = group_start[g + 1];
     for (int q = threadIdx.x; q < P2G_WARPS * TILE_NODES; q += blockDim.x) tiles[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
@@ -752,49 +678,50 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// meld (meld_grid.rs:16-69) evaluated while loading a tile: node value seen by layer `bits` =
-// sum over the layers of the same block whose bits are compatible; velocity = momentum / mass.
-__device__ __forceinline__ float4 melded_node(const float4* __restrict__ grid, const unsigned long long* __restrict__ active_keys, const uint32_t* __restrict__ layer_bits,
-                                              uint32_t n_active, int nl, int e, int node) {
-  float4 s = grid[(size_t)e * 64 + node];
-  if (nl > 0) {
-    const unsigned long long k = active_keys[e];
-    const unsigned long long block = k >> nl;
-    const uint32_t mask = (1u << nl) - 1u;
-    const uint32_t mine = layer_bits[(uint32_t)k & mask];
-    for (int o = e - 1; o >= 0; --o) {
-      const unsigned long long ko = active_keys[o];
-      if ((ko >> nl) != block) break;
-      if (bits_compatible(mine, layer_bits[(uint32_t)ko & mask])) {
-        const float4 v = grid[(size_t)o * 64 + node];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-    }
-    for (uint32_t o = e + 1; o < n_active; ++o) {
-      const unsigned long long ko = active_keys[o];
-      if ((ko >> nl) != block) break;
-      if (bits_compatible(mine, layer_bits[(uint32_t)ko & mask])) {
-        const float4 v = grid[(size_t)o * 64 + node];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-    }
-  }
+// meld (meld_grid.rs:16-69) evaluated while loading a tile: node value seen by a layer = sum over the
+// layers of the same block whose collider bits are compatible; velocity = momentum / mass.
+struct MeldInfo {
+  const unsigned long long* layer_slots;
+  const uint32_t* layer_list;
+};
+__device__ __forceinline__ float4 finish_node(float4 s) {
   if (s.w > 0.f) { s.x /= s.w; s.y /= s.w; s.z /= s.w; }
   else { s.x = 0.f; s.y = 0.f; s.z = 0.f; }
   return s;
 }
+// sibling tiles (ids) of `key`'s block compatible with its layer, self first.  Returns the count.
+__device__ __forceinline__ int sibling_tiles(const TileTable& T, const MeldInfo& Mi, uint32_t n_layers, unsigned long long key, int self, int* out, StepScalars* S) {
+  int n = 0;
+  out[n++] = self;
+  if (n_layers == 0) return n;
+  const uint32_t lmask = (1u << LAYER_BITS) - 1u;
+  const uint32_t my_layer = (uint32_t)key & lmask;
+  const uint32_t mine = layer_bits_of(Mi.layer_slots, my_layer);
+  const unsigned long long block = key & ~(unsigned long long)lmask;
+  for (uint32_t q = 0; q <= n_layers; ++q) {
+    const uint32_t layer = q == 0 ? 0u : Mi.layer_list[q - 1];
+    if (layer == my_layer) continue;
+    if (!bits_compatible(mine, layer_bits_of(Mi.layer_slots, layer))) continue;
+    const int t = tile_find(T, block | layer);
+    if (t < 0) continue;
+    if (n < SIB_MAX) out[n++] = t;
+    else atomicOr(&S->status, 1u /*SVB_TABLE_TRIES_EXCEEDED*/);
+  }
+  return n;
+}
 
-// G2P (+ advance, return mapping, energy, cull when FUSE).  One CTA per (block, layer) run; the
+// G2P (+ advance, return mapping, energy, cull when FUSE).  One CTA per particle-owning tile; the
 // melded 6x6x6 velocity tile is staged in shared memory, then one thread per particle gathers.
 constexpr int G2P_THREADS = 128;
 template <bool FUSE, bool REDUCE>
 __global__ void __launch_bounds__(G2P_THREADS) k_g2p(ParticleBuf P, float* __restrict__ energy, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S,
-                                                     const float4* __restrict__ grid, const unsigned long long* __restrict__ active_keys, const uint32_t* __restrict__ layer_bits,
-                                                     const BinLayout* __restrict__ Lp, SimConsts K, float dt) {
+                                                     const float4* __restrict__ grid, TileTable T, MeldInfo Mi, SimConsts K, float dt) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
-  const uint32_t n_groups = S->n_groups, n_live = S->n_live, n_active = S->n_active;
-  const int nl = Lp->nl;
+  __shared__ int s_sib[8][SIB_MAX];
+  __shared__ int s_nsib[8];
+  if (SVB_ABORTED(S)) return;
+  const uint32_t n_groups = S->n_ptiles, n_layers = S->n_layers;
   const float h = K.h;
   int red_vel = INT32_MIN, red_def = INT32_MAX;
   uint32_t failed = 0;
@@ -805,12 +732,23 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(ParticleBuf P, float* __res
     const uint32_t g = s_group;
     if (g >= n_groups) break;
     const uint32_t start = group_start[g];
-    const uint32_t end = g + 1 < n_groups ? group_start[g + 1] : n_live;
+    const uint32_t end = group_start[g + 1];
+    if (threadIdx.x < 8) {
+      const int nb = nbr[(size_t)g * 8 + threadIdx.x];
+      s_nsib[threadIdx.x] = nb >= 0 ? sibling_tiles(T, Mi, n_layers, T.tile_key[nb], nb, s_sib[threadIdx.x], S) : 0;
+    }
+    __syncthreads();
     for (int t = threadIdx.x; t < TILE_NODES; t += blockDim.x) {
       const int ti = t / 36, tj = (t / 6) % 6, tk = t % 6;
       const int d = (ti >> 2) | ((tj >> 2) << 1) | ((tk >> 2) << 2);
-      const int nb = nbr[(size_t)g * 8 + d];
-      tile[t] = nb >= 0 ? melded_node(grid, active_keys, layer_bits, n_active, nl, nb, ((ti & 3) << 4) | ((tj & 3) << 2) | (tk & 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int node = ((ti & 3) << 4) | ((tj & 3) << 2) | (tk & 3);
+      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int ns = s_nsib[d];
+      for (int q = 0; q < ns; ++q) {
+        const float4 v = grid[(size_t)s_sib[d][q] * 64 + node];
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      }
+      tile[t] = finish_node(sum);
     }
     __syncthreads();
     for (uint32_t i = start + threadIdx.x; i < end; i += blockDim.x) {
@@ -890,7 +828,7 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(ParticleBuf P, float* __res
       if (red_def != INT32_MAX) atomicMin(&S->min_deformation_key, red_def);
     }
   }
-  if (FUSE && failed) atomicOr(&S->status, 8u /*SVB_PARTICLE_CLOSE_TO_INVERTED*/);
+  if (FUSE && failed) atomicOr(&S->sticky, 8u /*SVB_PARTICLE_CLOSE_TO_INVERTED*/);
 }
 
 // advance + cull as its own pass (adaptive time stepping: dt is only known after the G2P reductions)
@@ -910,7 +848,7 @@ __global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restric
   for (int q = 0; q < 9; ++q) F.m[q] += CF.m[q] * dt;
   float e;
   if (return_map_and_energy(flags, P.f(PP0)[i], P.f(PP1)[i], (flags & F_USE_SAND_ALPHA) ? P.f(PALPHA)[i] : 0.f, F, e)) energy[i] = e;
-  else { flags |= F_FAILED; atomicOr(&S->status, 8u); }
+  else { flags |= F_FAILED; atomicOr(&S->sticky, 8u); }
   const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
   if (!within) flags |= F_TOMBSTONED;
   P.f(PX)[i] = x.x; P.f(PX + 1)[i] = x.y; P.f(PX + 2)[i] = x.z;
@@ -953,12 +891,13 @@ __global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, StepScalars*
 // grid download helpers: which nodes of an active tile have >= 1 contributor
 __global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, const StepScalars* __restrict__ S, float h,
                                                      unsigned long long* __restrict__ node_mask) {
-  const uint32_t n_groups = S->n_groups, n_live = S->n_live;
+  if (SVB_ABORTED(S)) return;
+  const uint32_t n_groups = S->n_ptiles;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
     const uint32_t start = group_start[g];
-    const uint32_t end = g + 1 < n_groups ? group_start[g + 1] : n_live;
+    const uint32_t end = group_start[g + 1];
     for (uint32_t i = start + lane; i < end; i += 32) {
       const int s0 = base_node(P.f(PX)[i], h) & 3, s1 = base_node(P.f(PX + 1)[i], h) & 3, s2 = base_node(P.f(PX + 2)[i], h) & 3;
       for (int a = 0; a < 3; ++a)
@@ -972,28 +911,34 @@ __global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32
     }
   }
 }
-__global__ void __launch_bounds__(64) k_emit_grid(const float4* __restrict__ grid, const unsigned long long* __restrict__ active_keys, const uint32_t* __restrict__ layer_bits,
-                                                  const BinLayout* __restrict__ Lp, const unsigned long long* __restrict__ node_mask, const uint32_t* __restrict__ node_offset,
-                                                  uint32_t n_active, int32_t* __restrict__ node_ids, uint32_t* __restrict__ out_bits, float* __restrict__ masses, float* __restrict__ velocities) {
+__global__ void __launch_bounds__(64) k_emit_grid(const float4* __restrict__ grid, TileTable T, MeldInfo Mi, StepScalars* S, const unsigned long long* __restrict__ node_mask,
+                                                  const uint32_t* __restrict__ node_offset, int32_t* __restrict__ node_ids, uint32_t* __restrict__ out_bits, float* __restrict__ masses,
+                                                  float* __restrict__ velocities) {
   const uint32_t e = blockIdx.x;
   const int node = threadIdx.x;
+  __shared__ int sib[SIB_MAX];
+  __shared__ int nsib;
+  const unsigned long long k = T.tile_key[e];
+  if (threadIdx.x == 0) nsib = sibling_tiles(T, Mi, S->n_layers, k, (int)e, sib, S);
+  __syncthreads();
   const unsigned long long mask = node_mask[e];
   if (!((mask >> node) & 1ull)) return;
-  const BinLayout L = *Lp;
   const uint32_t at = node_offset[e] + __popcll(mask & ((1ull << node) - 1ull));
-  const unsigned long long k = active_keys[e];
-  const uint32_t rank = (uint32_t)k & ((1u << L.nl) - 1u);
-  unsigned long long b = k >> L.nl;
-  const int bz = (int)(b & ((1ull << L.nb[2]) - 1ull)); b >>= L.nb[2];
-  const int by = (int)(b & ((1ull << L.nb[1]) - 1ull)); b >>= L.nb[1];
-  const int bx = (int)b;
-  node_ids[3 * at] = ((bx + L.block_min[0]) << 2) + (node >> 4);
-  node_ids[3 * at + 1] = ((by + L.block_min[1]) << 2) + ((node >> 2) & 3);
-  node_ids[3 * at + 2] = ((bz + L.block_min[2]) << 2) + (node & 3);
-  out_bits[at] = layer_bits[rank];
-  const float4 v = melded_node(grid, active_keys, layer_bits, n_active, L.nl, (int)e, node);
-  masses[at] = v.w;
-  velocities[3 * at] = v.x; velocities[3 * at + 1] = v.y; velocities[3 * at + 2] = v.z;
+  int bx, by, bz;
+  uint32_t layer;
+  tile_key_unpack(k, bx, by, bz, layer);
+  node_ids[3 * at] = (bx << 2) + (node >> 4);
+  node_ids[3 * at + 1] = (by << 2) + ((node >> 2) & 3);
+  node_ids[3 * at + 2] = (bz << 2) + (node & 3);
+  out_bits[at] = layer_bits_of(Mi.layer_slots, layer);
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < nsib; ++q) {
+    const float4 v = grid[(size_t)sib[q] * 64 + node];
+    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+  }
+  sum = finish_node(sum);
+  masses[at] = sum.w;
+  velocities[3 * at] = sum.x; velocities[3 * at + 1] = sum.y; velocities[3 * at + 2] = sum.z;
 }
 __global__ void __launch_bounds__(64) k_mask_from_values(const float4* __restrict__ grid, unsigned long long* __restrict__ node_mask) {
   const float4 v = grid[(size_t)blockIdx.x * 64 + threadIdx.x];
@@ -1008,20 +953,14 @@ __global__ void k_popc_masks(const unsigned long long* __restrict__ node_mask, u
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) counts[i] = __popcll(node_mask[i]);
 }
-__global__ void k_decode_active(const unsigned long long* __restrict__ active_keys, const uint32_t* __restrict__ layer_bits, const BinLayout* __restrict__ Lp, uint32_t n_active,
-                                int32_t* __restrict__ block_ids, uint32_t* __restrict__ out_bits) {
+__global__ void k_decode_active(TileTable T, const unsigned long long* __restrict__ layer_slots, uint32_t n_active, int32_t* __restrict__ block_ids, uint32_t* __restrict__ out_bits) {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_active) return;
-  const BinLayout L = *Lp;
-  const unsigned long long k = active_keys[e];
-  const uint32_t rank = (uint32_t)k & ((1u << L.nl) - 1u);
-  unsigned long long b = k >> L.nl;
-  const int bz = (int)(b & ((1ull << L.nb[2]) - 1ull)); b >>= L.nb[2];
-  const int by = (int)(b & ((1ull << L.nb[1]) - 1ull)); b >>= L.nb[1];
-  block_ids[3 * e] = (int)b + L.block_min[0];
-  block_ids[3 * e + 1] = by + L.block_min[1];
-  block_ids[3 * e + 2] = bz + L.block_min[2];
-  out_bits[e] = layer_bits[rank];
+  int bx, by, bz;
+  uint32_t layer;
+  tile_key_unpack(T.tile_key[e], bx, by, bz, layer);
+  block_ids[3 * e] = bx; block_ids[3 * e + 1] = by; block_ids[3 * e + 2] = bz;
+  out_bits[e] = layer_bits_of(layer_slots, layer);
 }
 __global__ void k_cells(ParticleBuf P, float h, uint32_t n, int32_t* __restrict__ cells) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
