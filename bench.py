@@ -204,7 +204,7 @@ def main():
     scene.frame_input.consts.frames_per_second = 1  # one long frame: the bench never crosses a keyframe boundary
     dt = scene.time_step
     config = {"workload": f"{args.scene}: {scene.description}", "particles_per_gpu": scene.n, "time_step": dt, "adaptive_time_steps": bool(args.adaptive),
-              "rebin": "every substep (key + radix sort + physical permutation)", "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush"}
+              "rebin": "every substep (counting sort on (tile, cell) + physical permutation of the SoA state)", "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
@@ -272,16 +272,27 @@ def main():
                                   "frac": scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9 / peak},
                 "stage_ms_per_substep": stages}
 
-    # ---------------- end to end through the public API with host buffers
+    # ---------------- end to end through the public API with host buffers (page-locked, as the contract asks)
     state.close()
-    host_state = scene.io_state
+    import dataclasses
+    from squishy_volumes_b200.types import IoState, Particles
+    keep = []
+
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)), pin_memory=True)
+        keep.append(t)
+        v = t.numpy()
+        v[...] = a
+        return v
+    host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)}))
+    out_buffers = Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)})
     h2d = sum(getattr(host_state.particles, f).nbytes for f in ("flags", "mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha", "viscosity_dynamic",
                                                                  "viscosity_bulk", "positions", "position_gradients", "velocities", "velocity_gradients", "elastic_energies", "collider_bits"))
     d2h = h2d
     barrier(dist, local)
     te = time.perf_counter()
     st2 = B200State.from_io_state(host_state, fi, device=local)
-    out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+    out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
     barrier(dist, local)
     e2e_s = all_max(dist, local, time.perf_counter() - te)
     e2e_done = st2.substeps

@@ -62,7 +62,7 @@ struct SvbHandle {
   DevBuf energy;
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
   // binning scratch + tile table (rebuilt every substep)
-  DevBuf pcell, prank, table_keys, table_vals, tile_key, tile_touch, cell_count, tile_start, nbr, grid, node_mask, node_offset, scratch;
+  DevBuf pcell, prank, src_of, table_keys, table_vals, tile_key, tile_touch, cell_count, tile_start, nbr, grid, node_mask, node_offset, scratch;
   size_t tile_cap = 0;      // tiles the per-tile arrays can hold
   uint32_t table_mask = 0;  // open-addressing slots - 1
   DevBuf scalars, layer_slots, layer_list;
@@ -245,14 +245,13 @@ int enqueue_rebin(SvbHandle* h) {
   const uint32_t n = h->n;
   StepScalars* S = h->scalars.as<StepScalars>();
   stage_begin(h, ST_PERMUTE);
-  k_permute<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), n);
+  k_invert<<<blocks_for(n, 256), 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->src_of.as<uint32_t>(), n);
   LAUNCH_CHECK();
-  h->cur ^= 1;
   k_zero_grid<<<148 * 8, 256, 0, s>>>(S, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
   LAUNCH_CHECK();
   h->masks_valid = false;
   if (h->store_grid) {
-    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
+    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
     LAUNCH_CHECK();
     h->masks_valid = true;
   }
@@ -261,7 +260,7 @@ int enqueue_rebin(SvbHandle* h) {
 }
 
 // wait for the front half's scalars; on tile overflow grow the capacity and redo the binning
-// (the particle order is untouched until k_permute runs, and k_permute / P2G / G2P no-op on overflow)
+// (the state is only rewritten by G2P, and k_invert / P2G / G2P no-op on overflow)
 int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
   for (int attempt = 0;; ++attempt) {
     CK(cudaEventSynchronize(h->ev_front));
@@ -281,7 +280,7 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
     }
     if (attempt > 8) return fail(h, SVB_CUDA_ERROR, "tile capacity did not settle");
     CK(cudaStreamSynchronize(h->stream));
-    if (back_enqueued) h->cur ^= 1;  // the queued k_permute was a no-op: undo the buffer swap
+    if (back_enqueued) h->cur ^= 1;  // the queued G2P was a no-op: undo the buffer swap
     back_enqueued = false;
     if (int rc = ensure_tile_capacity(h, (size_t)r.n_tiles * 2 + 1024)) return rc;
     if (int rc = enqueue_front(h, in, /*apply_force=*/false, 0.f)) return rc;
@@ -338,12 +337,15 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     const float dt = h->adaptive.allowed();
     if (int rc = enqueue_rebin(h)) return rc;
     stage_begin(h, ST_P2G);
-    k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+    k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
     LAUNCH_CHECK();
     stage_end(h);
     stage_begin(h, ST_G2P);
-    k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T, meld_info(h), h->K, dt);
+    k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T, meld_info(h), h->K, dt);
     LAUNCH_CHECK();
+    k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), n);
+    LAUNCH_CHECK();
+    h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
     stage_end(h);
     const int rc = settle_front(h, in, /*back_enqueued=*/true);
     if (rc < 0) return rc;
@@ -351,10 +353,13 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     if (rc == 1) {  // the binning was redone with a larger tile capacity: queue the back half again
       const TileTable T2 = tile_table(h);
       if (int rc2 = enqueue_rebin(h)) return rc2;
-      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
       LAUNCH_CHECK();
-      k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt);
+      k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt);
       LAUNCH_CHECK();
+      k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), n);
+      LAUNCH_CHECK();
+      h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
     }
     h->have_grid = true;
     h->time += (double)dt;
@@ -391,12 +396,16 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   // -- ScatterMomentum, MeldGrid + CollectVelocity
   const float dt_scatter = h->adaptive.allowed();
   stage_begin(h, ST_P2G);
-  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt_scatter);
+  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt_scatter);
   LAUNCH_CHECK();
   stage_end(h);
   stage_begin(h, ST_G2P);
-  k_g2p<false, true><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt_scatter);
+  k_g2p<false, true><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt_scatter);
   LAUNCH_CHECK();
+  k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), n);
+  LAUNCH_CHECK();
+  h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
+
   // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
@@ -488,6 +497,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(h->scalars.ensure(sizeof(StepScalars)));
   CK(h->pcell.ensure(h->cap * 4));
   CK(h->prank.ensure(h->cap * 4));
+  CK(h->src_of.ensure(h->cap * 4));
   CK(h->scratch.ensure(4096));
   CK(h->layer_slots.ensure(LAYER_SLOTS * 8));
   CK(h->layer_list.ensure(LAYER_SLOTS * 4));
@@ -509,13 +519,15 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
       CK(cudaMemcpyAsync(P.u(field), src, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
       return 0;
     };
+    size_t stage_off = 0;  // every wire array gets its own region of the spare buffer (24 n words <= 34 cap): no sync in between
     auto vec = [&](const float* src, int field, int k) -> int {
       if (!src) return 0;
-      CK(cudaMemcpyAsync(stagef, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
-      if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(stagef, P.f(field), h->cap, n);
-      else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(stagef, P.f(field), h->cap, n);
+      float* st = stagef + stage_off;
+      stage_off += (size_t)h->cap * k;
+      CK(cudaMemcpyAsync(st, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
+      if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
+      else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
       LAUNCH_CHECK();
-      CK(cudaStreamSynchronize(h->stream));
       return 0;
     };
     int rc = 0;
@@ -541,7 +553,7 @@ void svb_destroy(SvbHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->table_keys, &h->table_vals, &h->tile_key, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
+  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_keys, &h->table_vals, &h->tile_key, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
                    &h->grid, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
@@ -688,14 +700,16 @@ int32_t svb_download(SvbHandle* h, SvbParticles* out) {
   const uint32_t* orig = P.u(PORIG);
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();  // the spare buffer is free between substeps
   const uint32_t blocks = blocks_for(n, 256);
+  size_t stage_off = 0;  // one region per field (34 n words in total): all gathers and copies queue back to back
   auto field = [&](void* dst, const float* src_field, int k) -> int {
     if (!dst) return 0;
-    if (k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, stagef, n);
-    else if (k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, stagef, n);
-    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, stagef, n);
+    float* st = stagef + stage_off;
+    stage_off += (size_t)h->cap * k;
+    if (k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, st, n);
+    else if (k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, st, n);
+    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, st, n);
     LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(dst, stagef, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(dst, st, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
     return 0;
   };
   int rc = 0;
@@ -703,8 +717,16 @@ int32_t svb_download(SvbHandle* h, SvbParticles* out) {
       (rc = field(out->mu_or_bulk_modulus, P.f(PP0), 1)) || (rc = field(out->lambda_or_exponent, P.f(PP1), 1)) || (rc = field(out->sand_alpha, P.f(PALPHA), 1)) ||
       (rc = field(out->viscosity_dynamic, P.f(PVD), 1)) || (rc = field(out->viscosity_bulk, P.f(PVB), 1)) || (rc = field(out->collider_bits, P.f(PBITS), 1)) ||
       (rc = field(out->positions, P.f(PX), 3)) || (rc = field(out->velocities, P.f(PV), 3)) || (rc = field(out->velocity_gradients, P.f(PC), 9)) ||
-      (rc = field(out->position_gradients, P.f(PF), 9)) || (rc = field(out->elastic_energies, h->energy.as<float>(), 1)))
+      (rc = field(out->position_gradients, P.f(PF), 9)))
     return rc;
+  // energies are the 35th word: park them in the node-mask scratch if the spare buffer is full
+  if (out->elastic_energies) {
+    CK(h->scratch.ensure((size_t)h->cap * 4));
+    k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(h->energy.as<float>(), h->cap, orig, h->scratch.as<float>(), n);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(out->elastic_energies, h->scratch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
   if (out->initial_positions) std::memcpy(out->initial_positions, h->initial_positions.data(), (size_t)n * 12);
   return 0;
 }

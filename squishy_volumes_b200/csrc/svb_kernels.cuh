@@ -483,10 +483,14 @@ __global__ void __launch_bounds__(256) k_halo(StepScalars* S, TileTable T, const
   }
 }
 
-// physical re-bin (sort.rs:91-101): every field of particle i moves to its slot
-//   dst = tile_start[tile] + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
-__global__ void __launch_bounds__(256) k_permute(ParticleBuf src, ParticleBuf dst, const StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank,
-                                                 const uint32_t* __restrict__ cell_offset, const uint32_t* __restrict__ tile_start, uint32_t n) {
+// re-bin (sort.rs:91-101).  Slot of particle i in the binned order:
+//   j = tile_start[tile] + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
+// Only the inverse map src_of[j] = i is materialised here (4 B per particle).  P2G gathers its inputs
+// through it and G2P writes its results — and the fields it merely carries — to slot j of the other
+// buffer, so the physical permutation of the 136-byte state costs no pass of its own: consecutive
+// slots come from (nearly) consecutive rows of the previous order, the gathers stay coalesced.
+__global__ void __launch_bounds__(256) k_invert(const StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank,
+                                                const uint32_t* __restrict__ cell_offset, const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ src_of, uint32_t n) {
   if (SVB_ABORTED(S)) return;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -494,11 +498,17 @@ __global__ void __launch_bounds__(256) k_permute(ParticleBuf src, ParticleBuf ds
   uint32_t j;
   if (ci == 0xffffffffu) j = S->n_live + prank[i];
   else j = tile_start[ci >> 6] + cell_offset[ci] + prank[i];
-  uint32_t v[NFIELDS];
+  src_of[j] = i;
+}
+// tombstoned particles take no part in P2G / G2P: carry their rows over as they are
+__global__ void __launch_bounds__(256) k_copy_tomb(ParticleBuf src, ParticleBuf dst, const StepScalars* __restrict__ S, const uint32_t* __restrict__ src_of, uint32_t n) {
+  if (SVB_ABORTED(S)) return;
+  const uint32_t n_live = S->n_live;
+  for (uint32_t j = n_live + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t i = src_of[j];
 #pragma unroll
-  for (int f = 0; f < NFIELDS; ++f) v[f] = __ldg(src.base + (size_t)f * src.cap + i);
-#pragma unroll
-  for (int f = 0; f < NFIELDS; ++f) dst.base[(size_t)f * dst.cap + j] = v[f];
+    for (int f = 0; f < NFIELDS; ++f) dst.base[(size_t)f * dst.cap + j] = src.base[(size_t)f * src.cap + i];
+  }
 }
 
 __global__ void __launch_bounds__(256) k_zero_grid(const StepScalars* __restrict__ S, float4* __restrict__ grid, unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
@@ -521,6 +531,15 @@ __global__ void __launch_bounds__(256) k_zero_grid(const StepScalars* __restrict
 // 6x6x6 tile (plain read-modify-write, no shared atomics: fp32 shared atomics are CAS loops).  At
 // the end the warps' tiles are summed and every non-zero tile node goes to HBM with one
 // red.global.add.v4.f32.
+// Stencil weights from the base node: `shifted` = x/h - base in [1/2, 3/2).  Branch-free forms of
+// kernel_quadratic(shifted - a), a = 0,1,2 (cpu/src/kernels.rs:17-26 evaluated on the branch each a falls in;
+// both branches agree at the hand-over points).
+__device__ __forceinline__ void quad_weights(float shifted, float* w) {
+  const float a0 = fmaxf(1.5f - shifted, 0.f), a1 = shifted - 1.f, a2 = fmaxf(shifted - 0.5f, 0.f);
+  w[0] = 0.5f * a0 * a0;
+  w[1] = 0.75f - a1 * a1;
+  w[2] = 0.5f * a2 * a2;
+}
 constexpr int P2G_WARPS = 4;
 constexpr int TILE_NODES = 216;
 constexpr int STAGE_STRIDE = 36;  // floats per staged particle: 16-byte aligned rows, conflict-free float4 stores
@@ -530,8 +549,8 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S, float4* __restrict__ grid,
-                                                           float h, float dt) {
+__global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr,
+                                                           StepScalars* S, float4* __restrict__ grid, float h, float dt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   float* stage_all = reinterpret_cast<float*>(smem_raw + P2G_WARPS * TILE_NODES * 16);
@@ -563,11 +582,11 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
     __syncthreads();
 
     for (uint32_t chunk = start + warp * 32; chunk < end; chunk += P2G_WARPS * 32) {
-      const uint32_t i = chunk + lane;
       // ---- per-particle evaluation by the owning lane
       float4 st[8];
       int cell = -1;
-      if (i < end) {
+      if (chunk + lane < end) {
+        const uint32_t i = src_of[chunk + lane];  // row of this particle in the pre-bin order
         const float x0 = P.f(PX)[i], x1 = P.f(PX + 1)[i], x2 = P.f(PX + 2)[i];
         const float n0 = __fdiv_rn(x0, h), n1 = __fdiv_rn(x1, h), n2 = __fdiv_rn(x2, h);
         const int s0 = (int)floorf(__fsub_rn(n0, 0.5f)), s1 = (int)floorf(__fsub_rn(n1, 0.5f)), s2 = (int)floorf(__fsub_rn(n2, 0.5f));
@@ -576,8 +595,13 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
           const float dn0 = (float)(s0 + a) - n0, dn1 = (float)(s1 + a) - n1, dn2 = (float)(s2 + a) - n2;
-          w[a] = kernel_quadratic(dn0); w[3 + a] = kernel_quadratic(dn1); w[6 + a] = kernel_quadratic(dn2);
           d[a] = dn0 * h; d[3 + a] = dn1 * h; d[6 + a] = dn2 * h;
+          // kernel_quadratic(dn) on the branch stencil node a falls in: |dn| in [1/2, 3/2] for a = 0, 2 and <= 1/2 for a = 1
+          if (a == 1) { w[1] = 0.75f - dn0 * dn0; w[4] = 0.75f - dn1 * dn1; w[7] = 0.75f - dn2 * dn2; }
+          else {
+            const float e0 = fmaxf(1.5f - fabsf(dn0), 0.f), e1 = fmaxf(1.5f - fabsf(dn1), 0.f), e2 = fmaxf(1.5f - fabsf(dn2), 0.f);
+            w[a] = 0.5f * e0 * e0; w[3 + a] = 0.5f * e1 * e1; w[6 + a] = 0.5f * e2 * e2;
+          }
         }
         M3 C, F;
 #pragma unroll
@@ -641,9 +665,9 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
           const float4 A0 = *reinterpret_cast<const float4*>(sp + 24);   // A0..A3
           const float4 A1 = *reinterpret_cast<const float4*>(sp + 28);   // A4..A7
           const float wgt = wx.x * wy.x * wz.x;
-          const float m0 = mvA.x + (A0.x * wx.y + A0.w * wy.y + A1.z * wz.y);
-          const float m1 = mvA.y + (A0.y * wx.y + A1.x * wy.y + A1.w * wz.y);
-          const float m2 = mvA.z + (A0.z * wx.y + A1.y * wy.y + mvA.w * wz.y);
+          const float m0 = fmaf(A1.z, wz.y, fmaf(A0.w, wy.y, fmaf(A0.x, wx.y, mvA.x)));
+          const float m1 = fmaf(A1.w, wz.y, fmaf(A1.x, wy.y, fmaf(A0.y, wx.y, mvA.y)));
+          const float m2 = fmaf(mvA.w, wz.y, fmaf(A1.y, wy.y, fmaf(A0.z, wx.y, mvA.z)));
           acc.x += wgt * m0; acc.y += wgt * m1; acc.z += wgt * m2; acc.w += wgt * mass;
           px += STAGE_STRIDE; py += STAGE_STRIDE; pz += STAGE_STRIDE; sp += STAGE_STRIDE;
         }
@@ -713,9 +737,11 @@ __device__ __forceinline__ int sibling_tiles(const TileTable& T, const MeldInfo&
 // G2P (+ advance, return mapping, energy, cull when FUSE).  One CTA per particle-owning tile; the
 // melded 6x6x6 velocity tile is staged in shared memory, then one thread per particle gathers.
 constexpr int G2P_THREADS = 128;
+// Reads the particle through src_of from the pre-bin buffer `P`, writes every field of it to slot i of
+// `D` (this is where the physical re-bin happens).
 template <bool FUSE, bool REDUCE>
-__global__ void __launch_bounds__(G2P_THREADS) k_g2p(ParticleBuf P, float* __restrict__ energy, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S,
-                                                     const float4* __restrict__ grid, TileTable T, MeldInfo Mi, SimConsts K, float dt) {
+__global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy, const uint32_t* __restrict__ group_start,
+                                                        const int* __restrict__ nbr, StepScalars* S, const float4* __restrict__ grid, TileTable T, MeldInfo Mi, SimConsts K, float dt) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
   __shared__ int s_sib[8][SIB_MAX];
@@ -752,44 +778,53 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(ParticleBuf P, float* __res
     }
     __syncthreads();
     for (uint32_t i = start + threadIdx.x; i < end; i += blockDim.x) {
-      V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+      const uint32_t si = src_of[i];
+      V3 x = V3{P.f(PX)[si], P.f(PX + 1)[si], P.f(PX + 2)[si]};
+      // issue the loads of everything this thread carries / updates before the gather needs them
+      uint32_t flags = P.u(PFLAGS)[si];
+      M3 F;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) F.m[q] = P.f(PF + q)[si];
+      float carry[7];
+#pragma unroll
+      for (int q = 0; q < 7; ++q) carry[q] = P.f(PMASS + q)[si];
+      const uint32_t bits = P.u(PBITS)[si], orig = P.u(PORIG)[si];
       const V3 nrm = V3{__fdiv_rn(x.x, h), __fdiv_rn(x.y, h), __fdiv_rn(x.z, h)};
       const V3 shift = V3{floorf(__fsub_rn(nrm.x, 0.5f)), floorf(__fsub_rn(nrm.y, 0.5f)), floorf(__fsub_rn(nrm.z, 0.5f))};
       const int s0 = (int)shift.x, s1 = (int)shift.y, s2 = (int)shift.z;
       const V3 shifted = nrm - shift;
-      float wx[3], wy[3], wz[3];
+      float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
+      quad_weights(shifted.x, wx); quad_weights(shifted.y, wy); quad_weights(shifted.z, wz);
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        wx[a] = kernel_quadratic(shifted.x - (float)a);
-        wy[a] = kernel_quadratic(shifted.y - (float)a);
-        wz[a] = kernel_quadratic(shifted.z - (float)a);
+        dx[a] = (float)(s0 + a) * h - x.x;   // collect_velocity.rs:52-53: node position - particle position
+        dy[a] = (float)(s1 + a) * h - x.y;
+        dz[a] = (float)(s2 + a) * h - x.z;
       }
+      const float wzd[3] = {wz[0] * dz[0], wz[1] * dz[1], wz[2] * dz[2]};
       V3 v = V3{0.f, 0.f, 0.f};
       M3 C;
 #pragma unroll
       for (int q = 0; q < 9; ++q) C.m[q] = 0.f;
       const int tb = ((s0 & 3) * 6 + (s1 & 3)) * 6 + (s2 & 3);
+      // v = sum w v_n ; C = sum (w v_n) (x_n - x)^T, factored along z so each node costs 6 FMAs
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int b = 0; b < 3; ++b)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float w = wx[a] * wy[b] * wz[c];
-            const float4 gv = tile[tb + (a * 6 + b) * 6 + c];
-            const V3 to_node = V3{(float)(s0 + a) * h - x.x, (float)(s1 + b) * h - x.y, (float)(s2 + c) * h - x.z};
-            const V3 wv = V3{gv.x * w, gv.y * w, gv.z * w};
-            v = v + wv;
-            C.m[0] += wv.x * to_node.x; C.m[1] += wv.y * to_node.x; C.m[2] += wv.z * to_node.x;
-            C.m[3] += wv.x * to_node.y; C.m[4] += wv.y * to_node.y; C.m[5] += wv.z * to_node.y;
-            C.m[6] += wv.x * to_node.z; C.m[7] += wv.y * to_node.z; C.m[8] += wv.z * to_node.z;
-          }
+        for (int b = 0; b < 3; ++b) {
+          const float4 g0 = tile[tb + (a * 6 + b) * 6], g1 = tile[tb + (a * 6 + b) * 6 + 1], g2 = tile[tb + (a * 6 + b) * 6 + 2];
+          const V3 t = V3{wz[0] * g0.x + wz[1] * g1.x + wz[2] * g2.x, wz[0] * g0.y + wz[1] * g1.y + wz[2] * g2.y, wz[0] * g0.z + wz[1] * g1.z + wz[2] * g2.z};
+          const V3 tz = V3{wzd[0] * g0.x + wzd[1] * g1.x + wzd[2] * g2.x, wzd[0] * g0.y + wzd[1] * g1.y + wzd[2] * g2.y, wzd[0] * g0.z + wzd[1] * g1.z + wzd[2] * g2.z};
+          const float wxy = wx[a] * wy[b];
+          const float wxd = wxy * dx[a], wyd = wxy * dy[b];
+          v.x += wxy * t.x; v.y += wxy * t.y; v.z += wxy * t.z;
+          C.m[0] += wxd * t.x; C.m[1] += wxd * t.y; C.m[2] += wxd * t.z;
+          C.m[3] += wyd * t.x; C.m[4] += wyd * t.y; C.m[5] += wyd * t.z;
+          C.m[6] += wxy * tz.x; C.m[7] += wxy * tz.y; C.m[8] += wxy * tz.z;
+        }
       const float cs = 4.f / h / h;
 #pragma unroll
       for (int q = 0; q < 9; ++q) C.m[q] *= cs;
-      P.f(PV)[i] = v.x; P.f(PV + 1)[i] = v.y; P.f(PV + 2)[i] = v.z;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) P.f(PC + q)[i] = C.m[q];
       if (REDUCE) {
         red_vel = max(red_vel, total_key(norm(v)));
 #pragma unroll
@@ -797,24 +832,23 @@ __global__ void __launch_bounds__(G2P_THREADS) k_g2p(ParticleBuf P, float* __res
       }
       if (FUSE) {
         // advance_particles.rs:41-86, cull_particles.rs:31-39
-        uint32_t flags = P.u(PFLAGS)[i];
-        M3 F;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) F.m[q] = P.f(PF + q)[i];
         x = x + v * dt;
         const M3 CF = mul(C, F);
 #pragma unroll
         for (int q = 0; q < 9; ++q) F.m[q] += CF.m[q] * dt;
         float e;
-        if (return_map_and_energy(flags, P.f(PP0)[i], P.f(PP1)[i], (flags & F_USE_SAND_ALPHA) ? P.f(PALPHA)[i] : 0.f, F, e)) energy[i] = e;
+        if (return_map_and_energy(flags, carry[PP0 - PMASS], carry[PP1 - PMASS], (flags & F_USE_SAND_ALPHA) ? carry[PALPHA - PMASS] : 0.f, F, e)) energy[i] = e;
         else { flags |= F_FAILED; failed = 1; }
         const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
         if (!within) flags |= F_TOMBSTONED;
-        P.f(PX)[i] = x.x; P.f(PX + 1)[i] = x.y; P.f(PX + 2)[i] = x.z;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) P.f(PF + q)[i] = F.m[q];
-        P.u(PFLAGS)[i] = flags;
       }
+      D.f(PX)[i] = x.x; D.f(PX + 1)[i] = x.y; D.f(PX + 2)[i] = x.z;
+      D.f(PV)[i] = v.x; D.f(PV + 1)[i] = v.y; D.f(PV + 2)[i] = v.z;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) { D.f(PC + q)[i] = C.m[q]; D.f(PF + q)[i] = F.m[q]; }
+#pragma unroll
+      for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
+      D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
     }
   }
   if (REDUCE) {
@@ -889,8 +923,8 @@ __global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, StepScalars*
 
 // ------------------------------------------------------------------------------------------------
 // grid download helpers: which nodes of an active tile have >= 1 contributor
-__global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, const StepScalars* __restrict__ S, float h,
-                                                     unsigned long long* __restrict__ node_mask) {
+__global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr,
+                                                     const StepScalars* __restrict__ S, float h, unsigned long long* __restrict__ node_mask) {
   if (SVB_ABORTED(S)) return;
   const uint32_t n_groups = S->n_ptiles;
   const uint32_t lane = threadIdx.x & 31;
@@ -898,7 +932,8 @@ __global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32
   for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
     const uint32_t start = group_start[g];
     const uint32_t end = group_start[g + 1];
-    for (uint32_t i = start + lane; i < end; i += 32) {
+    for (uint32_t j = start + lane; j < end; j += 32) {
+      const uint32_t i = src_of[j];
       const int s0 = base_node(P.f(PX)[i], h) & 3, s1 = base_node(P.f(PX + 1)[i], h) & 3, s2 = base_node(P.f(PX + 2)[i], h) & 3;
       for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)

@@ -111,15 +111,17 @@ class B200State:
             raise FatalError(rc, L.svb_last_error(self._h).decode())
         return SimulationError(rc, L.svb_last_error(self._h).decode()) if rc > 0 else None
 
-    def produce_next_state(self, harness: Optional[Harness], frame_input: FrameInput, params: RunParameters):
-        """-> (IoState, SimulationError | None); raises FatalError for the reference's outer Err."""
+    def produce_next_state(self, harness: Optional[Harness], frame_input: FrameInput, params: RunParameters, out: Optional[Particles] = None):
+        """-> (IoState, SimulationError | None); raises FatalError for the reference's outer Err.
+        `out` (optional) are caller-owned result arrays, e.g. page-locked ones, reused across frames."""
         err = self.advance(harness, frame_input, params)
-        return self.to_io_state(params.store_grid), err
+        return self.to_io_state(params.store_grid, out=out), err
 
     # ------------------------------------------------------------------ readback
-    def to_io_state(self, store_grid: bool = False) -> IoState:
+    def to_io_state(self, store_grid: bool = False, out: Optional[Particles] = None) -> IoState:
         L = abi.load()
-        out = Particles.empty(self.n)
+        if out is None:
+            out = Particles.empty(self.n)
         s = cs.particles_struct(out)
         rc = L.svb_download(self._h, C.byref(s))
         if rc != 0:
