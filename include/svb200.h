@@ -169,6 +169,9 @@ int32_t svb_comm_unique_id(uint8_t out[128]);
 int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, int32_t n_ranks,
                       int32_t slab_lo_block_x, int32_t slab_hi_block_x, uint64_t original_offset);
 uint64_t svb_particle_count(const SvbHandle* h);      /* particles currently resident on this rank */
+/* Global original index of every uploaded row (call right after svb_create, before any substep) when the
+ * rank's rows are not a contiguous range of the global particle order. */
+int32_t svb_set_original_indices(SvbHandle* h, const uint32_t* original_index, uint64_t n);
 /* Download in resident order together with the global original index of each row. */
 int32_t svb_download_resident(SvbHandle* h, SvbParticles* out, uint64_t* original_index);
 

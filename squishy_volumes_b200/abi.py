@@ -106,5 +106,13 @@ def load():
     L.svb_restore.argtypes = [vp]
     L.svb_particle_count.restype = C.c_uint64
     L.svb_particle_count.argtypes = [vp]
+    L.svb_comm_unique_id.restype = C.c_int32
+    L.svb_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
+    L.svb_comm_init.restype = C.c_int32
+    L.svb_comm_init.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
+    L.svb_set_original_indices.restype = C.c_int32
+    L.svb_set_original_indices.argtypes = [vp, cs.c_u32p, C.c_uint64]
+    L.svb_download_resident.restype = C.c_int32
+    L.svb_download_resident.argtypes = [vp, C.POINTER(cs.SvbParticles), C.POINTER(C.c_uint64)]
     _lib = L
     return L

@@ -6,6 +6,7 @@
 // CUDA kernel from svb_kernels.cuh; the host only sequences launches, keeps the f64 clock and the
 // adaptive time-step history, and builds the (tiny) collider topology / BVH per keyframe.
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -45,8 +46,8 @@ struct DevBuf {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Stage : int { ST_MESH = 0, ST_BIN, ST_OFFSETS, ST_PERMUTE, ST_LIMIT, ST_P2G, ST_G2P, ST_ADVANCE, ST_COUNT };
-const char* const kStageNames[ST_COUNT] = {"mesh_interpolate", "collide_force_bin", "offsets_halo", "permute", "limit_time_step", "p2g", "g2p", "advance"};
+enum Stage : int { ST_MESH = 0, ST_BIN, ST_OFFSETS, ST_PERMUTE, ST_LIMIT, ST_P2G, ST_G2P, ST_ADVANCE, ST_HALO, ST_MIGRATE, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"mesh_interpolate", "collide_force_bin", "offsets_halo", "invert_zero", "limit_time_step", "p2g", "g2p", "advance", "halo_exchange", "migrate"};
 
 }  // namespace
 
@@ -85,6 +86,17 @@ struct SvbHandle {
   svbh::FlatBvh bvh;
   MeshDev M{};
 
+  // multi-GPU slabs
+  bool slabs = false;
+  ncclComm_t comm = nullptr;
+  int rank = 0, n_ranks = 1, slab_lo = 0, slab_hi = 0, reach_lo = 0, reach_hi = 0;
+  uint64_t orig_offset = 0;
+  uint32_t n_global = 0;
+  DevBuf comm_counts, halo_send[2], halo_recv[2], mig_send[2], mig_recv[2];
+  uint32_t* h_counts = nullptr;  // pinned
+  size_t halo_cap = 0, mig_cap = 0, halo_margin = 2048;
+  uint64_t halo_tiles_sent = 0, migrated_out = 0;
+
   double time = 0;
   svbh::AdaptiveTimeStep adaptive;
   uint64_t substeps = 0;
@@ -97,6 +109,7 @@ struct SvbHandle {
   double snap_time = 0;
   svbh::AdaptiveTimeStep snap_adaptive;
   uint64_t snap_substeps = 0;
+  uint32_t snap_n = 0;
   bool have_snapshot = false;
 
   // stage timing
@@ -287,6 +300,10 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
   }
 }
 
+int halo_exchange(SvbHandle* h);
+int migrate(SvbHandle* h);
+int substep_slab(SvbHandle* h, const StepInputs& in);
+
 // ---- one substep: the 12 phases of cpu/src/phase/mod.rs:27-41 in the reference's order
 int substep(SvbHandle* h, bool adaptive_steps) {
   cudaStream_t s = h->stream;
@@ -316,6 +333,10 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     k_mesh_vertex_normals<<<blocks_for(h->topo.n_vertices, 256), 256, 0, s>>>(h->M);
     LAUNCH_CHECK();
     stage_end(h);
+  }
+  if (h->slabs) {
+    if (adaptive_steps) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps are not supported with slab decomposition yet");
+    return substep_slab(h, in);
   }
   if (n == 0) {
     h->time += (double)h->adaptive.allowed();
@@ -427,6 +448,64 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   stage_end(h);
   h->have_grid = true;
   h->time += (double)h->adaptive.allowed();
+  ++h->substeps;
+  return 0;
+}
+
+// one fixed-dt substep of a slab rank: like the single-GPU flow, with the halo exchange between P2G
+// and G2P and the particle migration after the advance.  Runs even with zero resident particles
+// (the neighbours still expect this rank's messages).
+int substep_slab(SvbHandle* h, const StepInputs& in) {
+  cudaStream_t s = h->stream;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  const float hh = h->K.h;
+  const float dt = h->adaptive.allowed();
+  bool apply_force = true;
+  for (int attempt = 0;; ++attempt) {
+    if (int rc = enqueue_front(h, in, apply_force, dt)) return rc;
+    const int rc = settle_front(h, in, /*back_enqueued=*/false);
+    if (rc < 0) return rc;
+    // tiles arriving with the halo need room in the table; growing it loses its contents, so re-bin
+    const size_t want = (size_t)h->n_tiles + h->halo_margin;
+    if (want <= h->tile_cap) break;
+    if (attempt > 4) return fail(h, SVB_COMM_ERROR, "tile capacity did not settle");
+    CK(cudaStreamSynchronize(s));
+    if (int rc2 = ensure_tile_capacity(h, want + want / 2)) return rc2;
+    apply_force = false;
+  }
+  const uint32_t n_after = h->h_scalars->n_live + h->h_scalars->n_tomb;  // rows of migrated particles are dropped by the re-bin
+  if (int rc = enqueue_rebin(h)) return rc;
+  const TileTable T = tile_table(h);
+  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
+  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
+  stage_begin(h, ST_P2G);
+  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+  LAUNCH_CHECK();
+  stage_end(h);
+  stage_begin(h, ST_HALO);
+  if (int rc = halo_exchange(h)) return rc;
+  stage_end(h);
+  stage_begin(h, ST_G2P);
+  k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T, meld_info(h), h->K, dt);
+  LAUNCH_CHECK();
+  k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), h->n);
+  LAUNCH_CHECK();
+  h->cur ^= 1;
+  h->n = n_after;
+  // a FAILED particle on any rank stops every rank after this substep
+  uint32_t* flag = h->comm_counts.as<uint32_t>() + 8;
+  CK(cudaMemcpyAsync(flag, &S->sticky, 4, cudaMemcpyDeviceToDevice, s));
+  if (ncclAllReduce(flag, flag, 1, ncclUint32, ncclMax, h->comm, s) != ncclSuccess) return fail(h, SVB_COMM_ERROR, "ncclAllReduce failed");
+  CK(cudaMemcpyAsync(h->h_counts + 8, flag, 4, cudaMemcpyDeviceToHost, s));
+  stage_end(h);
+  stage_begin(h, ST_MIGRATE);
+  if (int rc = migrate(h)) return rc;  // synchronises the stream
+  stage_end(h);
+  h->status |= h->h_counts[8] & 0xffffu;
+  h->have_grid = true;
+  h->time += (double)dt;
   ++h->substeps;
   return 0;
 }
@@ -557,10 +636,13 @@ void svb_destroy(SvbHandle* h) {
                    &h->grid, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
-                   &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e};
+                   &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e,
+                   &h->comm_counts, &h->halo_send[0], &h->halo_send[1], &h->halo_recv[0], &h->halo_recv[1], &h->mig_send[0], &h->mig_send[1], &h->mig_recv[0], &h->mig_recv[1]};
   for (DevBuf* b : all) b->release();
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->ev_front) cudaEventDestroy(h->ev_front);
+  if (h->comm) ncclCommDestroy(h->comm);
+  if (h->h_counts) cudaFreeHost(h->h_counts);
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_adv)
@@ -599,7 +681,7 @@ int32_t svb_set_keyframes(SvbHandle* h, uint64_t frame, const SvbKeyframe* a, co
   if (!h || !a) return SVB_BAD_ARGUMENT;
   if (int rc = set_device(h)) return rc;
   const auto& T = h->topo;
-  const uint32_t nv = T.n_vertices, nt = T.n_triangles, n = h->n;
+  const uint32_t nv = T.n_vertices, nt = T.n_triangles, n = h->n_global ? h->n_global : h->n;  // goal arrays are in (global) original order
   if (nv && (!a->vertex_positions || (b && !b->vertex_positions))) return fail(h, SVB_BAD_ARGUMENT, "keyframe lacks vertex_positions");
   h->frame = frame;
   h->has_b = b != nullptr;
@@ -847,6 +929,7 @@ void svb_enable_stage_timing(SvbHandle* h, int32_t on) {
 void svb_set_option(SvbHandle* h, const char* name, double value) {
   if (!h || !name) return;
   if (!std::strcmp(name, "store_grid")) h->store_grid = value != 0.0;  // CpuRunParameters::store_grid
+  if (!std::strcmp(name, "global_particles")) h->n_global = (uint32_t)value;  // slab ranks: size of the original-order keyframe arrays
 }
 
 int32_t svb_snapshot(SvbHandle* h) {
@@ -860,6 +943,7 @@ int32_t svb_snapshot(SvbHandle* h) {
   h->snap_time = h->time;
   h->snap_adaptive = h->adaptive;
   h->snap_substeps = h->substeps;
+  h->snap_n = h->n;
   h->have_snapshot = true;
   return 0;
 }
@@ -873,24 +957,272 @@ int32_t svb_restore(SvbHandle* h) {
   h->time = h->snap_time;
   h->adaptive = h->snap_adaptive;
   h->substeps = h->snap_substeps;
+  h->n = h->snap_n;
   h->have_grid = false;
   return 0;
 }
 
 }  // extern "C"
 
-// ---- multi-GPU slab decomposition: see svb_comm.cuh (round 1: not wired yet) ----
+// ================================================================================================
+// multi-GPU slab decomposition along x.  One process per GPU; neighbours exchange
+// one block column of grid tiles after P2G and the particles that left the slab after the advance,
+// with ncclSend / ncclRecv over NVLink.  Fixed time step only (the adaptive reductions would need an
+// all-reduce per limit phase).
+namespace {
+
+#define NCK(call)                                                                                                   \
+  do {                                                                                                              \
+    ncclResult_t r_ = (call);                                                                                       \
+    if (r_ != ncclSuccess) return fail(h, SVB_COMM_ERROR, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+// re-stride the particle buffers to a larger per-field capacity (field f of row i = base[f*cap + i])
+int resize_particles(SvbHandle* h, size_t new_cap) {
+  new_cap = (new_cap + 63) & ~(size_t)63;
+  if (new_cap <= h->cap) return 0;
+  CK(cudaStreamSynchronize(h->stream));
+  DevBuf nb[2], ne;
+  for (int b = 0; b < 2; ++b) CK(nb[b].ensure(new_cap * NFIELDS * 4));
+  CK(ne.ensure(new_cap * 4));
+  for (int f = 0; f < NFIELDS; ++f)
+    CK(cudaMemcpyAsync(nb[h->cur].as<uint32_t>() + (size_t)f * new_cap, h->pbuf[h->cur].as<uint32_t>() + (size_t)f * h->cap, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(ne.p, h->energy.p, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int b = 0; b < 2; ++b) { h->pbuf[b].release(); h->pbuf[b] = nb[b]; }
+  h->energy.release();
+  h->energy = ne;
+  h->cap = new_cap;
+  CK(h->pcell.ensure(new_cap * 4));
+  CK(h->prank.ensure(new_cap * 4));
+  CK(h->src_of.ensure(new_cap * 4));
+  h->have_snapshot = false;
+  return 0;
+}
+
+// exchange two counters with the slab neighbours (left = rank-1, right = rank+1)
+int exchange_counts(SvbHandle* h, const uint32_t send[2], uint32_t recv[2]) {
+  uint32_t* d = h->comm_counts.as<uint32_t>();  // [0..1] send, [2..3] recv
+  h->h_counts[0] = send[0]; h->h_counts[1] = send[1]; h->h_counts[2] = 0; h->h_counts[3] = 0;
+  CK(cudaMemcpyAsync(d, h->h_counts, 16, cudaMemcpyHostToDevice, h->stream));
+  NCK(ncclGroupStart());
+  if (h->rank > 0) { NCK(ncclSend(d + 0, 1, ncclUint32, h->rank - 1, h->comm, h->stream)); NCK(ncclRecv(d + 2, 1, ncclUint32, h->rank - 1, h->comm, h->stream)); }
+  if (h->rank + 1 < h->n_ranks) { NCK(ncclSend(d + 1, 1, ncclUint32, h->rank + 1, h->comm, h->stream)); NCK(ncclRecv(d + 3, 1, ncclUint32, h->rank + 1, h->comm, h->stream)); }
+  NCK(ncclGroupEnd());
+  CK(cudaMemcpyAsync(h->h_counts, d, 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  recv[0] = h->h_counts[2];
+  recv[1] = h->h_counts[3];
+  return 0;
+}
+int exchange_payload(SvbHandle* h, const void* send_l, const void* send_r, void* recv_l, void* recv_r, const uint32_t send[2], const uint32_t recv[2], size_t elem_bytes) {
+  NCK(ncclGroupStart());
+  if (h->rank > 0) {
+    if (send[0]) NCK(ncclSend(send_l, (size_t)send[0] * elem_bytes, ncclUint8, h->rank - 1, h->comm, h->stream));
+    if (recv[0]) NCK(ncclRecv(recv_l, (size_t)recv[0] * elem_bytes, ncclUint8, h->rank - 1, h->comm, h->stream));
+  }
+  if (h->rank + 1 < h->n_ranks) {
+    if (send[1]) NCK(ncclSend(send_r, (size_t)send[1] * elem_bytes, ncclUint8, h->rank + 1, h->comm, h->stream));
+    if (recv[1]) NCK(ncclRecv(recv_r, (size_t)recv[1] * elem_bytes, ncclUint8, h->rank + 1, h->comm, h->stream));
+  }
+  NCK(ncclGroupEnd());
+  return 0;
+}
+
+// after P2G: add the neighbour's partial sums of the shared block column into this rank's tiles
+int halo_exchange(SvbHandle* h) {
+  cudaStream_t s = h->stream;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  const TileTable T = tile_table(h);
+  uint32_t* cnt = h->comm_counts.as<uint32_t>() + 4;  // [4] left, [5] right
+  uint32_t sendc[2] = {0, 0}, recvc[2] = {0, 0};
+  for (int attempt = 0;; ++attempt) {
+    CK(cudaMemsetAsync(cnt, 0, 8, s));
+    // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right
+    if (h->rank > 0)
+      k_pack_column<<<148 * 4, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->halo_send[0].as<HaloEntry>(), cnt + 0, (uint32_t)h->halo_cap);
+    if (h->rank + 1 < h->n_ranks)
+      k_pack_column<<<148 * 4, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_hi, h->halo_send[1].as<HaloEntry>(), cnt + 1, (uint32_t)h->halo_cap);
+    h->launches += 2;
+    CK(cudaMemcpyAsync(h->h_counts + 4, cnt, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    sendc[0] = h->h_counts[4];
+    sendc[1] = h->h_counts[5];
+    if (int rc = exchange_counts(h, sendc, recvc)) return rc;
+    const size_t need = std::max(std::max(sendc[0], sendc[1]), std::max(recvc[0], recvc[1]));
+    if (need <= h->halo_cap) break;
+    if (attempt > 2) return fail(h, SVB_COMM_ERROR, "halo buffers did not settle");
+    const size_t c = need + need / 2 + 256;  // both ranks of a pair see the same counts, so both re-pack
+    for (int k = 0; k < 2; ++k) { CK(h->halo_send[k].ensure(c * sizeof(HaloEntry))); CK(h->halo_recv[k].ensure(c * sizeof(HaloEntry))); }
+    h->halo_cap = c;
+  }
+  if (int rc = exchange_payload(h, h->halo_send[0].p, h->halo_send[1].p, h->halo_recv[0].p, h->halo_recv[1].p, sendc, recvc, sizeof(HaloEntry))) return rc;
+  // incoming tiles may be new to this rank: make room (tile arrays keep their contents)
+  if ((size_t)h->n_tiles + recvc[0] + recvc[1] > h->tile_cap) return fail(h, SVB_COMM_ERROR, "tile capacity too small for the halo (%u + %u + %u > %zu)", h->n_tiles, recvc[0], recvc[1], h->tile_cap);
+  for (int k = 0; k < 2; ++k)
+    if (recvc[k]) {
+      k_unpack_add<<<std::min<uint32_t>(blocks_for((uint64_t)recvc[k] * 32, 256), 148 * 8), 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(),
+                                                                                                         h->grid.as<float4>(), h->halo_recv[k].as<HaloEntry>(), recvc[k]);
+      LAUNCH_CHECK();
+    }
+  h->halo_tiles_sent += sendc[0] + sendc[1];
+  h->halo_margin = std::max<size_t>(h->halo_margin, 2 * ((size_t)recvc[0] + recvc[1]) + 2048);
+  return 0;
+}
+
+// after the advance: hand particles that left [lo, hi) to the neighbour, append the ones coming in
+int migrate(SvbHandle* h) {
+  cudaStream_t s = h->stream;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  uint32_t* cnt = h->comm_counts.as<uint32_t>() + 4;
+  uint32_t sendc[2] = {0, 0}, recvc[2] = {0, 0};
+  const uint32_t n = h->n;
+  CK(cudaMemsetAsync(cnt, 0, 8, s));
+  if (n) {
+    k_migrate_pack<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, h->K.h, h->slab_lo, h->slab_hi, h->reach_lo, h->reach_hi, h->mig_send[0].as<uint32_t>(),
+                                                     h->mig_send[1].as<uint32_t>(), cnt, (uint32_t)h->mig_cap, n);
+    LAUNCH_CHECK();
+  }
+  CK(cudaMemcpyAsync(h->h_counts + 4, cnt, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h->h_scalars->status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a particle crossed more than one slab in a single substep");
+  sendc[0] = h->h_counts[4];
+  sendc[1] = h->h_counts[5];
+  if (std::max(sendc[0], sendc[1]) > h->mig_cap) return fail(h, SVB_COMM_ERROR, "migration buffer too small (%u rows > %zu)", std::max(sendc[0], sendc[1]), h->mig_cap);
+  if (int rc = exchange_counts(h, sendc, recvc)) return rc;
+  if (std::max(recvc[0], recvc[1]) > h->mig_cap) return fail(h, SVB_COMM_ERROR, "migration buffer too small (%u rows > %zu)", std::max(recvc[0], recvc[1]), h->mig_cap);
+  if ((size_t)n + recvc[0] + recvc[1] > h->cap)
+    if (int rc = resize_particles(h, ((size_t)n + recvc[0] + recvc[1]) * 5 / 4 + 4096)) return rc;
+  if (int rc = exchange_payload(h, h->mig_send[0].p, h->mig_send[1].p, h->mig_recv[0].p, h->mig_recv[1].p, sendc, recvc, MIG_WORDS * 4)) return rc;
+  uint32_t base = n;
+  for (int k = 0; k < 2; ++k)
+    if (recvc[k]) {
+      k_migrate_unpack<<<blocks_for(recvc[k], 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), h->mig_recv[k].as<uint32_t>(), recvc[k], base);
+      LAUNCH_CHECK();
+      base += recvc[k];
+    }
+  h->n = base;
+  h->migrated_out += sendc[0] + sendc[1];
+  return 0;
+}
+
+}  // namespace
+
 extern "C" {
+
 int32_t svb_comm_unique_id(uint8_t out[128]) {
-  (void)out;
-  return SVB_COMM_ERROR;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return SVB_COMM_ERROR;
+  std::memcpy(out, &id, 128);
+  return 0;
 }
+
 int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, int32_t n_ranks, int32_t slab_lo_block_x, int32_t slab_hi_block_x, uint64_t original_offset) {
-  (void)unique_id; (void)rank; (void)n_ranks; (void)slab_lo_block_x; (void)slab_hi_block_x; (void)original_offset;
-  return fail(h, SVB_COMM_ERROR, "multi-GPU slab exchange is not available in this build");
+  if (!h || !unique_id || rank < 0 || rank >= n_ranks || slab_lo_block_x >= slab_hi_block_x) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, 128);
+  NCK(ncclCommInitRank(&h->comm, n_ranks, id, rank));
+  h->rank = rank;
+  h->n_ranks = n_ranks;
+  h->slab_lo = slab_lo_block_x;
+  h->slab_hi = slab_hi_block_x;
+  // every rank learns every slab: a particle may only travel into the adjacent slab within one substep
+  CK(h->comm_counts.ensure(64 + (size_t)n_ranks * 8));
+  CK(cudaMallocHost(&h->h_counts, 64 + (size_t)n_ranks * 8));
+  int32_t* d_all = reinterpret_cast<int32_t*>(h->comm_counts.as<uint32_t>() + 16);
+  int32_t mine[2] = {slab_lo_block_x, slab_hi_block_x};
+  CK(cudaMemcpyAsync(d_all + 2 * rank, mine, 8, cudaMemcpyHostToDevice, h->stream));
+  NCK(ncclAllGather(d_all + 2 * rank, d_all, 2, ncclInt32, h->comm, h->stream));
+  std::vector<int32_t> all(2 * (size_t)n_ranks);
+  CK(cudaMemcpyAsync(all.data(), d_all, all.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r + 1 < n_ranks; ++r)
+    if (all[2 * r + 1] != all[2 * (r + 1)]) return fail(h, SVB_BAD_ARGUMENT, "slabs are not contiguous: rank %d ends at %d, rank %d starts at %d", r, all[2 * r + 1], r + 1, all[2 * (r + 1)]);
+  h->reach_lo = rank > 0 ? all[2 * (rank - 1)] : slab_lo_block_x;
+  h->reach_hi = rank + 1 < n_ranks ? all[2 * (rank + 1) + 1] : slab_hi_block_x;
+  // global original indices travel with the particles
+  if (h->n && original_offset) {
+    k_add_u32<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->Pc().u(PORIG), h->n, (uint32_t)original_offset);
+    LAUNCH_CHECK();
+  }
+  h->orig_offset = original_offset;
+  // room for incoming particles and halo tiles
+  if (int rc = resize_particles(h, (size_t)h->n * 3 / 2 + 65536)) return rc;
+  h->mig_cap = (size_t)h->n / 8 + 65536;
+  h->halo_cap = 4096;
+  for (int k = 0; k < 2; ++k) {
+    CK(h->mig_send[k].ensure(h->mig_cap * MIG_WORDS * 4));
+    CK(h->mig_recv[k].ensure(h->mig_cap * MIG_WORDS * 4));
+    CK(h->halo_send[k].ensure(h->halo_cap * sizeof(HaloEntry)));
+    CK(h->halo_recv[k].ensure(h->halo_cap * sizeof(HaloEntry)));
+  }
+  if (int rc = ensure_tile_capacity(h, h->tile_cap * 2 + 8192)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->slabs = true;
+  return 0;
 }
+
+int32_t svb_set_original_indices(SvbHandle* h, const uint32_t* original_index, uint64_t n) {
+  if (!h || !original_index || n != h->n) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  if (n) CK(cudaMemcpyAsync(h->Pc().u(PORIG), original_index, n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int32_t svb_download_resident(SvbHandle* h, SvbParticles* out, uint64_t* original_index) {
-  (void)out; (void)original_index;
-  return fail(h, SVB_COMM_ERROR, "multi-GPU slab exchange is not available in this build");
+  if (!h || !out) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  const uint32_t n = h->n;
+  out->n = 0;
+  if (!n) return 0;
+  cudaStream_t s = h->stream;
+  ParticleBuf P = h->Pc();
+  uint32_t* rows = h->src_of.as<uint32_t>();  // free between substeps
+  uint32_t* cnt = h->scratch.as<uint32_t>();
+  CK(cudaMemsetAsync(cnt, 0, 4, s));
+  k_resident_rows<<<blocks_for(n, 256), 256, 0, s>>>(P, n, rows, cnt);
+  LAUNCH_CHECK();
+  uint32_t m = 0;
+  CK(cudaMemcpyAsync(&m, cnt, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  out->n = m;
+  if (!m) return 0;
+  float* stagef = h->pbuf[h->cur ^ 1].as<float>();
+  const uint32_t blocks = blocks_for(m, 256);
+  size_t stage_off = 0;
+  auto field = [&](void* dst, const float* src_field, int k) -> int {
+    if (!dst) return 0;
+    float* st = stagef + stage_off;
+    stage_off += (size_t)h->cap * k;
+    if (k == 1) k_rows_to_wire<1><<<blocks, 256, 0, s>>>(src_field, h->cap, rows, st, m);
+    else if (k == 3) k_rows_to_wire<3><<<blocks, 256, 0, s>>>(src_field, h->cap, rows, st, m);
+    else k_rows_to_wire<9><<<blocks, 256, 0, s>>>(src_field, h->cap, rows, st, m);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(dst, st, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+    return 0;
+  };
+  int rc = 0;
+  std::vector<uint32_t> orig32(original_index ? m : 0);
+  if ((rc = field(out->flags, P.f(PFLAGS), 1)) || (rc = field(out->mass, P.f(PMASS), 1)) || (rc = field(out->initial_volume, P.f(PVOL), 1)) ||
+      (rc = field(out->mu_or_bulk_modulus, P.f(PP0), 1)) || (rc = field(out->lambda_or_exponent, P.f(PP1), 1)) || (rc = field(out->sand_alpha, P.f(PALPHA), 1)) ||
+      (rc = field(out->viscosity_dynamic, P.f(PVD), 1)) || (rc = field(out->viscosity_bulk, P.f(PVB), 1)) || (rc = field(out->collider_bits, P.f(PBITS), 1)) ||
+      (rc = field(out->positions, P.f(PX), 3)) || (rc = field(out->velocities, P.f(PV), 3)) || (rc = field(out->velocity_gradients, P.f(PC), 9)) ||
+      (rc = field(out->position_gradients, P.f(PF), 9)) || (rc = field(original_index ? orig32.data() : nullptr, P.f(PORIG), 1)))
+    return rc;
+  if (out->elastic_energies) {
+    CK(h->node_offset.ensure((size_t)m * 4));
+    k_rows_to_wire<1><<<blocks, 256, 0, s>>>(h->energy.as<float>(), h->cap, rows, h->node_offset.as<float>(), m);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(out->elastic_energies, h->node_offset.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  if (original_index)
+    for (uint32_t i = 0; i < m; ++i) original_index[i] = orig32[i];
+  return 0;
 }
-}
+
+}  // extern "C"

@@ -96,6 +96,7 @@ struct StepScalars {
   uint32_t n_tiles;    // active (block, layer) grid tiles
   uint32_t n_ptiles;   // tiles that own particles = ids [0, n_ptiles): the work list of P2G / G2P
   uint32_t n_layers;   // distinct non-zero collider-bit patterns
+  uint32_t n_tiles_zeroed;  // tiles cleared by k_zero_grid (tiles created later by a halo message are stored, not added)
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];
   // adaptive time step reductions (f32::total_cmp keys)

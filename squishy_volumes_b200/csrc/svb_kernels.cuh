@@ -333,13 +333,14 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
-  bool live = false, tomb = false;
+  bool live = false, tomb = false, gone = false;
   unsigned long long key = TILE_EMPTY;
   uint32_t cell = 0, touch = 0;
   if (i < n) {
     const uint32_t flags = P.u(PFLAGS)[i];
-    tomb = (flags & F_TOMBSTONED) != 0;
-    if (!tomb) {
+    gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
+    tomb = !gone && (flags & F_TOMBSTONED) != 0;
+    if (!tomb && !gone) {
       const V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
       uint32_t bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
       if (APPLY_FORCE) {
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   }
   // ---- slot in the cell: one atomic per distinct (tile, cell) in the warp
   const bool binned = live && tile != TILE_PENDING;
-  const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : 0xfffffffeu);
+  const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : (gone ? 0xfffffffdu : 0xfffffffeu));
   const unsigned cpeers = __match_any_sync(SVB_FULL, ci);
   const int cleader = __ffs(cpeers) - 1;
   uint32_t base = 0;
@@ -496,14 +497,17 @@ __global__ void __launch_bounds__(256) k_invert(const StepScalars* __restrict__ 
   if (i >= n) return;
   const uint32_t ci = pcell[i];
   uint32_t j;
-  if (ci == 0xffffffffu) j = S->n_live + prank[i];
-  else j = tile_start[ci >> 6] + cell_offset[ci] + prank[i];
+  if (ci >= 0xfffffffdu) {
+    if (ci != 0xffffffffu) return;  // migrated away (or unbinned after an abort): no slot
+    j = S->n_live + prank[i];
+  } else j = tile_start[ci >> 6] + cell_offset[ci] + prank[i];
   src_of[j] = i;
 }
 // tombstoned particles take no part in P2G / G2P: carry their rows over as they are
 __global__ void __launch_bounds__(256) k_copy_tomb(ParticleBuf src, ParticleBuf dst, const StepScalars* __restrict__ S, const uint32_t* __restrict__ src_of, uint32_t n) {
   if (SVB_ABORTED(S)) return;
   const uint32_t n_live = S->n_live;
+  n = n_live + S->n_tomb;  // rows of migrated particles are gone
   for (uint32_t j = n_live + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const uint32_t i = src_of[j];
 #pragma unroll
@@ -511,13 +515,14 @@ __global__ void __launch_bounds__(256) k_copy_tomb(ParticleBuf src, ParticleBuf 
   }
 }
 
-__global__ void __launch_bounds__(256) k_zero_grid(const StepScalars* __restrict__ S, float4* __restrict__ grid, unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
+__global__ void __launch_bounds__(256) k_zero_grid(StepScalars* __restrict__ S, float4* __restrict__ grid, unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
   if (SVB_ABORTED(S)) return;
   const size_t total = (size_t)min(S->n_tiles, tile_cap) * 64;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
     grid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (node_mask && (q & 63) == 0) node_mask[q >> 6] = 0ull;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) S->n_tiles_zeroed = (uint32_t)(total >> 6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -919,6 +924,121 @@ __global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, StepScalars*
     atomicMin(&S->min_isolated_key, ki);
     atomicAdd(&S->live_count, live);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU slabs (no reference counterpart).  A rank owns the particles whose base
+// node lies in block columns [lo, hi) along x.
+//   halo: after P2G the tiles of one block column are packed as (block key, collider bits, 64 x float4),
+//   exchanged with the neighbour rank and added into (or created in) the receiver's tile table;
+//   migration: after the advance, particles whose block column left [lo, hi) are packed as 35-word
+//   rows, flagged F_GONE locally (dropped by the next re-bin) and appended on the neighbour.
+struct HaloEntry {
+  unsigned long long block_key;  // tile key with the layer field cleared
+  uint32_t bits;                 // collider bits of the layer (layer ids are rank-local)
+  uint32_t pad;
+  float4 node[64];
+};
+__global__ void __launch_bounds__(256) k_pack_column(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid,
+                                                     int column, HaloEntry* __restrict__ out, uint32_t* __restrict__ count, uint32_t cap) {
+  if (SVB_ABORTED(S)) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_tiles = min(S->n_tiles, T.tile_cap);
+  for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps) {
+    const unsigned long long k = T.tile_key[t];
+    int bx, by, bz;
+    uint32_t layer;
+    tile_key_unpack(k, bx, by, bz, layer);
+    if (bx != column) continue;
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(count, 1u);
+    slot = __shfl_sync(SVB_FULL, slot, 0);
+    if (slot >= cap) continue;  // the host sees count > cap and grows the buffers
+    HaloEntry* e = out + slot;
+    if (lane == 0) {
+      e->block_key = k & ~(unsigned long long)((1u << LAYER_BITS) - 1u);
+      e->bits = layer_bits_of(layer_slots, layer);
+      e->pad = 0;
+    }
+    e->node[lane] = grid[(size_t)t * 64 + lane];
+    e->node[lane + 32] = grid[(size_t)t * 64 + lane + 32];
+  }
+}
+__global__ void __launch_bounds__(256) k_unpack_add(StepScalars* S, TileTable T, unsigned long long* layer_slots, uint32_t* layer_list, float4* __restrict__ grid,
+                                                    const HaloEntry* __restrict__ in, uint32_t count) {
+  if (SVB_ABORTED(S)) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t zeroed = S->n_tiles_zeroed;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < count; q += warps) {
+    const HaloEntry* e = in + q;
+    uint32_t id = TILE_PENDING;
+    if (lane == 0) {
+      const uint32_t layer = layer_find_or_insert(layer_slots, layer_list, e->bits, S);
+      id = tile_find_or_insert(T, e->block_key | layer, S);
+    }
+    id = __shfl_sync(SVB_FULL, id, 0);
+    if (id == TILE_PENDING) continue;
+    float4* dst = grid + (size_t)id * 64;
+    if (id >= zeroed) {  // created by this message: the tile was never zeroed, so store instead of add
+      dst[lane] = e->node[lane];
+      dst[lane + 32] = e->node[lane + 32];
+    } else {
+      red_add_v4(dst + lane, e->node[lane]);
+      red_add_v4(dst + lane + 32, e->node[lane + 32]);
+    }
+  }
+}
+constexpr int MIG_WORDS = NFIELDS + 1;  // the 34 state words + the elastic energy
+__global__ void __launch_bounds__(256) k_migrate_pack(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, float h, int lo, int hi, int reach_lo, int reach_hi,
+                                                      uint32_t* __restrict__ out_left, uint32_t* __restrict__ out_right, uint32_t* __restrict__ counts, uint32_t cap, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t flags = P.u(PFLAGS)[i];
+  if (flags & (F_TOMBSTONED | F_GONE)) return;
+  const int bx = floor_div4(base_node(P.f(PX)[i], h));
+  if (bx >= lo && bx < hi) return;
+  if (bx < reach_lo || bx >= reach_hi) { atomicOr(&S->status, ST_KEY_RANGE); return; }  // crossed more than one slab in a substep
+  const int side = bx < lo ? 0 : 1;
+  const uint32_t slot = atomicAdd(&counts[side], 1u);
+  P.u(PFLAGS)[i] = flags | F_GONE;
+  if (slot >= cap) return;
+  uint32_t* row = (side ? out_right : out_left) + (size_t)slot * MIG_WORDS;
+#pragma unroll
+  for (int f = 0; f < NFIELDS; ++f) row[f] = P.base[(size_t)f * P.cap + i];
+  row[NFIELDS] = __float_as_uint(energy[i]);
+}
+__global__ void __launch_bounds__(256) k_migrate_unpack(ParticleBuf P, float* __restrict__ energy, const uint32_t* __restrict__ in, uint32_t count, uint32_t base) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const uint32_t* row = in + (size_t)q * MIG_WORDS;
+  const uint32_t i = base + q;
+#pragma unroll
+  for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
+  energy[i] = __uint_as_float(row[NFIELDS]);
+}
+__global__ void k_add_u32(uint32_t* a, uint32_t n, uint32_t add) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += add;
+}
+// rows that are still resident (not migrated away), compacted in arbitrary order
+__global__ void __launch_bounds__(256) k_resident_rows(ParticleBuf P, uint32_t n, uint32_t* __restrict__ rows, uint32_t* __restrict__ count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool keep = i < n && !(P.u(PFLAGS)[i] & F_GONE);
+  const unsigned m = __ballot_sync(SVB_FULL, keep);
+  uint32_t base = 0;
+  if ((threadIdx.x & 31) == 0 && m) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(SVB_FULL, base, 0);
+  if (keep) rows[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = i;
+}
+template <int K>
+__global__ void k_rows_to_wire(const float* __restrict__ src, size_t cap, const uint32_t* __restrict__ rows, float* __restrict__ dst, uint32_t n) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const uint32_t i = rows[q];
+#pragma unroll
+  for (int k = 0; k < K; ++k) dst[(size_t)q * K + k] = src[(size_t)k * cap + i];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,7 @@ enum : uint32_t {
   F_HAS_GOAL = 1u << 4,
   F_TOMBSTONED = 1u << 5,
   F_FAILED = 1u << 6,
+  F_GONE = 1u << 30,  // internal (never leaves the device): the row migrated to a neighbour slab
 };
 
 // util/src/consts.rs:11-14

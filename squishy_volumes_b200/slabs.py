@@ -1,0 +1,150 @@
+"""Slab decomposition of the MPM domain across the GPUs of one box (the reference has
+no multi-GPU path, its parity oracle is the single-domain result).
+
+The domain is cut along x on grid-block planes (a block = 4 grid nodes, the tile size of the device
+grid).  Rank r owns the particles whose base node `floor(x/h - 1/2)` lies in block columns
+[lo_r, hi_r).  This module holds the host-side logic — planning the cut, splitting an `IoState`,
+re-assembling results by original particle index — and `SlabState`, which drives one rank's
+`libsvb200.so` handle (halo exchange and particle migration happen inside `svb_advance` over NCCL).
+Pure numpy except for `SlabState`; `torch.distributed` (gloo or nccl) is only used to hand the NCCL
+unique id around and to gather results.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import cstructs as cs
+from .types import FatalError, FrameInput, IoState, Particles, RunParameters, SimulationError
+
+BLOCK = 4                    # grid nodes per block edge (svb_device.cuh)
+FAR = 1 << 15                # "infinity" in block units, inside the +-2^16 key range
+
+
+def block_x(positions: np.ndarray, h: float) -> np.ndarray:
+    """Block column of every particle: floor(floor(x/h - 1/2) / 4), in f32 like the device."""
+    x = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)[:, 0]
+    cell = np.floor(x / np.float32(h) - np.float32(0.5)).astype(np.int64)
+    return np.floor_divide(cell, BLOCK)
+
+
+def plan_slabs(positions: np.ndarray, h: float, n_ranks: int) -> List[Tuple[int, int]]:
+    """Cut points on block planes that balance the particle count; the outer slabs extend to +-FAR.
+    Every slab is at least one block wide; with fewer occupied columns than ranks the tail ranks
+    get empty slabs beyond the material."""
+    bx = block_x(positions, h)
+    if bx.size == 0:
+        lo0 = 0
+        cuts = [lo0 + r for r in range(1, n_ranks)]
+    else:
+        cols, counts = np.unique(bx, return_counts=True)
+        cum = np.cumsum(counts)
+        total = int(cum[-1])
+        cuts = []
+        prev = int(cols[0])
+        for r in range(1, n_ranks):
+            target = total * r / n_ranks
+            k = int(np.searchsorted(cum, target, side="left"))
+            cut = int(cols[min(k, len(cols) - 1)]) + 1      # cut after column k
+            cut = max(cut, prev + 1)
+            cuts.append(cut)
+            prev = cut
+    bounds = [-FAR] + cuts + [FAR]
+    return [(bounds[r], bounds[r + 1]) for r in range(n_ranks)]
+
+
+def slab_of(positions: np.ndarray, h: float, plan: Sequence[Tuple[int, int]]) -> np.ndarray:
+    bx = block_x(positions, h)
+    cuts = np.array([hi for _, hi in plan[:-1]], dtype=np.int64)
+    return np.searchsorted(cuts, bx, side="right").astype(np.int32)
+
+
+def split_state(io_state: IoState, h: float, plan: Sequence[Tuple[int, int]], rank: int) -> Tuple[IoState, np.ndarray]:
+    """-> (local IoState, original indices of its rows)."""
+    owner = slab_of(io_state.particles.positions, h, plan)
+    idx = np.nonzero(owner == rank)[0]
+    return IoState(io_state.time, io_state.particles.select(idx)), idx.astype(np.int64)
+
+
+def assemble(n: int, parts: Sequence[Tuple[np.ndarray, Particles]], template: Particles) -> Particles:
+    """Scatter per-rank results (original index, rows) back into original particle order."""
+    out = template.copy()
+    seen = np.zeros(n, dtype=np.int32)
+    for idx, p in parts:
+        idx = np.asarray(idx, dtype=np.int64)
+        np.add.at(seen, idx, 1)
+        for f in dataclasses.fields(Particles):
+            if f.name == "initial_positions":
+                continue
+            getattr(out, f.name)[idx] = getattr(p, f.name)
+    if not np.all(seen == 1):
+        raise ValueError(f"slab results do not partition the particles: {int((seen == 0).sum())} missing, {int((seen > 1).sum())} duplicated")
+    return out
+
+
+class SlabState:
+    """One rank of a slab-decomposed run.  Same surface as `B200State`, plus `resident()`."""
+
+    def __init__(self, inner, plan, rank: int, world: int, n_global: int):
+        self.inner = inner
+        self.plan = list(plan)
+        self.rank = rank
+        self.world = world
+        self.n_global = n_global
+
+    @classmethod
+    def from_io_state(cls, io_state: IoState, frame_input: FrameInput, rank: int, world: int, device: int, unique_id: bytes,
+                      plan: Optional[Sequence[Tuple[int, int]]] = None) -> "SlabState":
+        from . import abi
+        from .state import B200State
+        h = frame_input.consts.scaled_grid_node_size()
+        if plan is None:
+            plan = plan_slabs(io_state.particles.positions, h, world)
+        local, idx = split_state(io_state, h, plan, rank)
+        inner = B200State.from_io_state(local, frame_input, device=device)
+        inner.n = io_state.particles.n          # keyframe particle arrays stay in global original order
+        L = abi.load()
+        L.svb_set_option(inner._h, b"global_particles", float(io_state.particles.n))
+        # the rows uploaded here are a subset of the global particle order: tell the device their global indices
+        idx32 = np.ascontiguousarray(idx, dtype=np.uint32)
+        if idx32.size:
+            rc = L.svb_set_original_indices(inner._h, cs.uptr(idx32), idx32.size)
+            if rc != 0:
+                raise FatalError(rc, L.svb_last_error(inner._h).decode())
+        uid = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        lo, hi = plan[rank]
+        rc = L.svb_comm_init(inner._h, uid, rank, world, int(lo), int(hi), 0)
+        if rc != 0:
+            raise FatalError(rc, L.svb_last_error(inner._h).decode())
+        return cls(inner, plan, rank, world, io_state.particles.n)
+
+    def advance(self, harness, frame_input: FrameInput, params: RunParameters) -> Optional[SimulationError]:
+        return self.inner.advance(harness, frame_input, params)
+
+    def resident(self) -> Tuple[np.ndarray, Particles]:
+        """(global original indices, rows) of the particles currently on this rank."""
+        from . import abi
+        L = abi.load()
+        cap = int(L.svb_particle_count(self.inner._h))
+        out = Particles.empty(max(cap, 1))
+        s = cs.particles_struct(out)
+        orig = np.zeros(max(cap, 1), dtype=np.uint64)
+        rc = L.svb_download_resident(self.inner._h, C.byref(s), orig.ctypes.data_as(C.POINTER(C.c_uint64)))
+        if rc != 0:
+            raise FatalError(rc, L.svb_last_error(self.inner._h).decode())
+        m = int(s.n)
+        return orig[:m].astype(np.int64), out.select(np.arange(m))
+
+    @property
+    def time(self) -> float:
+        return self.inner.time
+
+    @property
+    def substeps(self) -> int:
+        return self.inner.substeps
+
+    def close(self) -> None:
+        self.inner.close()
