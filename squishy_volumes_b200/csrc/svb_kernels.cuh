@@ -1007,6 +1007,7 @@ __global__ void __launch_bounds__(256) k_migrate_pack(ParticleBuf P, const float
   uint32_t* row = (side ? out_right : out_left) + (size_t)slot * MIG_WORDS;
 #pragma unroll
   for (int f = 0; f < NFIELDS; ++f) row[f] = P.base[(size_t)f * P.cap + i];
+  row[PFLAGS] = flags;  // the row travels without the local F_GONE mark
   row[NFIELDS] = __float_as_uint(energy[i]);
 }
 __global__ void __launch_bounds__(256) k_migrate_unpack(ParticleBuf P, float* __restrict__ energy, const uint32_t* __restrict__ in, uint32_t count, uint32_t base) {

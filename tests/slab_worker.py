@@ -61,6 +61,7 @@ def main():
     dist.all_gather_object(gathered, (idx, rows, st.substeps, None if err is None else err.status))
     ok = True
     if rank == 0:
+        print('resident per rank', [len(g[0]) for g in gathered], 'sum', sum(len(g[0]) for g in gathered), 'of', sc.n, 'unique', len(np.unique(np.concatenate([g[0] for g in gathered]))), flush=True)
         assert all(g[2] == steps for g in gathered), [g[2] for g in gathered]
         got = slabs.assemble(sc.n, [(g[0], g[1]) for g in gathered], sc.io_state.particles)
         single = B200State.from_io_state(sc.io_state, sc.frame_input, device=local)
