@@ -13,7 +13,7 @@ import subprocess
 from . import cstructs as cs
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsvb200.so")
+LIB_PATH = os.environ.get("SVB200_LIB") or os.path.join(_HERE, "lib", "libsvb200.so")  # SVB200_LIB: developer override for A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svb200.h")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]

@@ -10,6 +10,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -63,7 +64,7 @@ struct SvbHandle {
   DevBuf energy;
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
   // binning scratch + tile table (rebuilt every substep)
-  DevBuf pcell, prank, src_of, table_keys, table_vals, tile_key, tile_touch, cell_count, tile_start, nbr, grid, node_mask, node_offset, scratch;
+  DevBuf pcell, prank, src_of, table_keys, table_vals, tile_key, tile_touch, cell_count, tile_start, nbr, grid, melded, node_mask, node_offset, scratch;
   size_t tile_cap = 0;      // tiles the per-tile arrays can hold
   uint32_t table_mask = 0;  // open-addressing slots - 1
   DevBuf scalars, layer_slots, layer_list;
@@ -300,6 +301,36 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
   }
 }
 
+// MeldGrid + CollectVelocity (+ Advance + Cull when fused).  Collider scenes first meld the sibling layers
+// into a velocity grid; without colliders G2P divides by the mass while it stages a tile.
+int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
+  cudaStream_t s = h->stream;
+  StepScalars* S = h->scalars.as<StepScalars>();
+  const float4* src = h->grid.as<float4>();
+  if (has_mesh) {
+    CK(h->melded.ensure(h->tile_cap * 64 * 16));
+    k_meld<<<148 * 8, 256, 0, s>>>(S, h->grid.as<float4>(), h->melded.as<float4>(), tile_table(h), meld_info(h));
+    LAUNCH_CHECK();
+    src = h->melded.as<float4>();
+  }
+  const ParticleBuf P = h->Pc(), D = h->P(h->cur ^ 1);
+  const uint32_t* src_of = h->src_of.as<uint32_t>();
+  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  float* en = h->energy.as<float>();
+  const int* nb = h->nbr.as<int>();
+  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
+  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
+#define SVB_G2P(F, R, M) k_g2p<F, R, M><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt)
+  if (fuse) { if (has_mesh) SVB_G2P(true, false, true); else SVB_G2P(true, false, false); }
+  else { if (has_mesh) SVB_G2P(false, true, true); else SVB_G2P(false, true, false); }
+#undef SVB_G2P
+  LAUNCH_CHECK();
+  k_copy_tomb<<<64, 256, 0, s>>>(P, D, S, src_of, h->n);
+  LAUNCH_CHECK();
+  h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
+  return 0;
+}
+
 int halo_exchange(SvbHandle* h);
 int migrate(SvbHandle* h);
 int substep_slab(SvbHandle* h, const StepInputs& in);
@@ -362,11 +393,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     LAUNCH_CHECK();
     stage_end(h);
     stage_begin(h, ST_G2P);
-    k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T, meld_info(h), h->K, dt);
-    LAUNCH_CHECK();
-    k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), n);
-    LAUNCH_CHECK();
-    h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc;
     stage_end(h);
     const int rc = settle_front(h, in, /*back_enqueued=*/true);
     if (rc < 0) return rc;
@@ -376,11 +403,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
       if (int rc2 = enqueue_rebin(h)) return rc2;
       k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
       LAUNCH_CHECK();
-      k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt);
-      LAUNCH_CHECK();
-      k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), n);
-      LAUNCH_CHECK();
-      h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
+      if (int rc2 = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc2;
     }
     h->have_grid = true;
     h->time += (double)dt;
@@ -421,11 +444,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   LAUNCH_CHECK();
   stage_end(h);
   stage_begin(h, ST_G2P);
-  k_g2p<false, true><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T2, meld_info(h), h->K, dt_scatter);
-  LAUNCH_CHECK();
-  k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), n);
-  LAUNCH_CHECK();
-  h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/false, dt_scatter)) return rc;
 
   // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
@@ -488,11 +507,7 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   if (int rc = halo_exchange(h)) return rc;
   stage_end(h);
   stage_begin(h, ST_G2P);
-  k_g2p<true, false><<<g2p_grid, G2P_THREADS, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), h->src_of.as<uint32_t>(), h->energy.as<float>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), T, meld_info(h), h->K, dt);
-  LAUNCH_CHECK();
-  k_copy_tomb<<<64, 256, 0, s>>>(h->Pc(), h->P(h->cur ^ 1), S, h->src_of.as<uint32_t>(), h->n);
-  LAUNCH_CHECK();
-  h->cur ^= 1;
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc;
   h->n = n_after;
   // a FAILED particle on any rank stops every rank after this substep
   uint32_t* flag = h->comm_counts.as<uint32_t>() + 8;
@@ -633,7 +648,7 @@ void svb_destroy(SvbHandle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_keys, &h->table_vals, &h->tile_key, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
-                   &h->grid, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
+                   &h->grid, &h->melded, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
                    &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e,

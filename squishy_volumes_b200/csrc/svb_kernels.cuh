@@ -714,7 +714,7 @@ struct MeldInfo {
   const uint32_t* layer_list;
 };
 __device__ __forceinline__ float4 finish_node(float4 s) {
-  if (s.w > 0.f) { s.x /= s.w; s.y /= s.w; s.z /= s.w; }
+  if (s.w > 0.f) { const float r = __frcp_rn(s.w); s.x *= r; s.y *= r; s.z *= r; }  // p/m within 1 ulp of the division
   else { s.x = 0.f; s.y = 0.f; s.z = 0.f; }
   return s;
 }
@@ -739,47 +739,68 @@ __device__ __forceinline__ int sibling_tiles(const TileTable& T, const MeldInfo&
   return n;
 }
 
-// G2P (+ advance, return mapping, energy, cull when FUSE).  One CTA per particle-owning tile; the
-// melded 6x6x6 velocity tile is staged in shared memory, then one thread per particle gathers.
+// melded velocity grid (collider scenes only): per tile, sum the compatible sibling layers and divide by
+// the mass once per node (meld_grid.rs:41-66), so that G2P can bulk-copy finished tiles.
+__global__ void __launch_bounds__(256) k_meld(const StepScalars* __restrict__ S, const float4* __restrict__ grid, float4* __restrict__ melded, TileTable T, MeldInfo Mi) {
+  if (SVB_ABORTED(S)) return;
+  __shared__ int sib[4][SIB_MAX];
+  __shared__ int nsib[4];
+  const uint32_t n_tiles = min(S->n_tiles, T.tile_cap), n_layers = S->n_layers;
+  const int sub = threadIdx.x >> 6, node = threadIdx.x & 63;
+  for (uint32_t base = blockIdx.x * 4; base < n_tiles; base += gridDim.x * 4) {
+    const uint32_t t = base + sub;
+    __syncthreads();
+    if (node == 0 && t < n_tiles) nsib[sub] = sibling_tiles(T, Mi, n_layers, T.tile_key[t], (int)t, sib[sub], const_cast<StepScalars*>(S));
+    __syncthreads();
+    if (t >= n_tiles) continue;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < nsib[sub]; ++q) {
+      const float4 v = grid[(size_t)sib[sub][q] * 64 + node];
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    melded[(size_t)t * 64 + node] = finish_node(sum);
+  }
+}
+
+// G2P (+ advance, return mapping, energy, cull when FUSE).  One CTA per particle-owning tile ; the 6x6x6 velocity tile is staged in shared memory, then one thread per particle
+// gathers with compile-time offsets.  Collider scenes read the melded velocity grid of k_meld.
+// (Two software-pipelined variants — TMA bulk tile copies + cp.async particle staging, per CTA and per
+// warp — were measured slower: 4-byte cp.async doubles the LSU instructions per particle and the
+// staging buffers cost occupancy; see profiles/README.md r1c-r1g.)
 constexpr int G2P_THREADS = 128;
 // Reads the particle through src_of from the pre-bin buffer `P`, writes every field of it to slot i of
 // `D` (this is where the physical re-bin happens).
-template <bool FUSE, bool REDUCE>
-__global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy, const uint32_t* __restrict__ group_start,
-                                                        const int* __restrict__ nbr, StepScalars* S, const float4* __restrict__ grid, TileTable T, MeldInfo Mi, SimConsts K, float dt) {
+template <bool FUSE, bool REDUCE, bool MELDED>
+__global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
+                                                        const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S,
+                                                        const float4* __restrict__ grid, SimConsts K, float dt) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
-  __shared__ int s_sib[8][SIB_MAX];
-  __shared__ int s_nsib[8];
+  __shared__ int s_nbr[8];
   if (SVB_ABORTED(S)) return;
-  const uint32_t n_groups = S->n_ptiles, n_layers = S->n_layers;
-  const float h = K.h;
+  const uint32_t n_groups = S->n_ptiles;
+  const float h = K.h, inv_h = 1.f / K.h;
   int red_vel = INT32_MIN, red_def = INT32_MAX;
   uint32_t failed = 0;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_group = atomicAdd(&S->work_counter[1], 1u);
+    if (threadIdx.x < 8) {
+      uint32_t g0 = 0;
+      if (threadIdx.x == 0) s_group = g0 = atomicAdd(&S->work_counter[1], 1u);
+      g0 = __shfl_sync(0xffu, g0, 0);
+      if (g0 < n_groups) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
+    }
     __syncthreads();
     const uint32_t g = s_group;
     if (g >= n_groups) break;
     const uint32_t start = group_start[g];
     const uint32_t end = group_start[g + 1];
-    if (threadIdx.x < 8) {
-      const int nb = nbr[(size_t)g * 8 + threadIdx.x];
-      s_nsib[threadIdx.x] = nb >= 0 ? sibling_tiles(T, Mi, n_layers, T.tile_key[nb], nb, s_sib[threadIdx.x], S) : 0;
-    }
-    __syncthreads();
     for (int t = threadIdx.x; t < TILE_NODES; t += blockDim.x) {
       const int ti = t / 36, tj = (t / 6) % 6, tk = t % 6;
-      const int d = (ti >> 2) | ((tj >> 2) << 1) | ((tk >> 2) << 2);
-      const int node = ((ti & 3) << 4) | ((tj & 3) << 2) | (tk & 3);
-      float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int ns = s_nsib[d];
-      for (int q = 0; q < ns; ++q) {
-        const float4 v = grid[(size_t)s_sib[d][q] * 64 + node];
-        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
-      }
-      tile[t] = finish_node(sum);
+      const int nb = s_nbr[(ti >> 2) | ((tj >> 2) << 1) | ((tk >> 2) << 2)];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nb >= 0) v = grid[(size_t)nb * 64 + (((ti & 3) << 4) | ((tj & 3) << 2) | (tk & 3))];
+      tile[t] = MELDED ? v : finish_node(v);
     }
     __syncthreads();
     for (uint32_t i = start + threadIdx.x; i < end; i += blockDim.x) {
@@ -794,10 +815,12 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
 #pragma unroll
       for (int q = 0; q < 7; ++q) carry[q] = P.f(PMASS + q)[si];
       const uint32_t bits = P.u(PBITS)[si], orig = P.u(PORIG)[si];
+      // (deriving the base node from the binned cell id instead of three IEEE divisions was measured slower:
+      // the extra gathered 4-byte load costs more than the divisions)
       const V3 nrm = V3{__fdiv_rn(x.x, h), __fdiv_rn(x.y, h), __fdiv_rn(x.z, h)};
-      const V3 shift = V3{floorf(__fsub_rn(nrm.x, 0.5f)), floorf(__fsub_rn(nrm.y, 0.5f)), floorf(__fsub_rn(nrm.z, 0.5f))};
-      const int s0 = (int)shift.x, s1 = (int)shift.y, s2 = (int)shift.z;
-      const V3 shifted = nrm - shift;
+      const V3 shiftf = V3{floorf(__fsub_rn(nrm.x, 0.5f)), floorf(__fsub_rn(nrm.y, 0.5f)), floorf(__fsub_rn(nrm.z, 0.5f))};
+      const int s0 = (int)shiftf.x, s1 = (int)shiftf.y, s2 = (int)shiftf.z;
+      const V3 shifted = nrm - shiftf;
       float wx[3], wy[3], wz[3], dx[3], dy[3], dz[3];
       quad_weights(shifted.x, wx); quad_weights(shifted.y, wy); quad_weights(shifted.z, wz);
 #pragma unroll
@@ -827,7 +850,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
           C.m[3] += wyd * t.x; C.m[4] += wyd * t.y; C.m[5] += wyd * t.z;
           C.m[6] += wxy * tz.x; C.m[7] += wxy * tz.y; C.m[8] += wxy * tz.z;
         }
-      const float cs = 4.f / h / h;
+      const float cs = 4.f * inv_h * inv_h;
 #pragma unroll
       for (int q = 0; q < 9; ++q) C.m[q] *= cs;
       if (REDUCE) {
