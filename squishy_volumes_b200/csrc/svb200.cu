@@ -64,8 +64,10 @@ struct SvbHandle {
   DevBuf energy;
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
   // binning scratch + tile table (rebuilt every substep)
-  DevBuf pcell, prank, src_of, table_keys, table_vals, tile_key, tile_touch, cell_count, tile_start, nbr, grid, melded, node_mask, node_offset, scratch;
+  DevBuf pcell, prank, src_of, table_slots, tile_key, tile_slot, tile_touch, cell_count, tile_start, nbr, grid, melded, node_mask, node_offset, scratch;
   size_t tile_cap = 0;      // tiles the per-tile arrays can hold
+  bool tables_fresh = true; // tables were (re)allocated: memset them once, later substeps undo only what they used
+  int s_cur = 0;            // half of the scalars double buffer this substep writes
   uint32_t table_mask = 0;  // open-addressing slots - 1
   DevBuf scalars, layer_slots, layer_list;
   StepScalars* h_scalars = nullptr;  // pinned
@@ -177,9 +179,9 @@ int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
   const size_t c = tiles + tiles / 2 + 1024;
   size_t slots = 1024;
   while (slots < 4 * c) slots <<= 1;
-  CK(h->table_keys.ensure(slots * 8));
-  CK(h->table_vals.ensure(slots * 4));
+  CK(h->table_slots.ensure(slots * 16));
   CK(h->tile_key.ensure(c * 8));
+  CK(h->tile_slot.ensure(c * 4));
   CK(h->tile_touch.ensure(c * 4));
   CK(h->cell_count.ensure(c * 64 * 4));
   CK(h->tile_start.ensure((c + 1) * 4));
@@ -189,6 +191,7 @@ int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
   CK(h->node_offset.ensure((c + 1) * 4));
   h->tile_cap = c;
   h->table_mask = (uint32_t)(slots - 1);
+  h->tables_fresh = true;  // new allocations: the next substep memsets them instead of undoing the previous one
   return 0;
 }
 
@@ -197,8 +200,10 @@ int set_device(SvbHandle* h) {
   return 0;
 }
 
+StepScalars* cur_scalars(SvbHandle* h) { return h->scalars.as<StepScalars>() + h->s_cur; }
+
 TileTable tile_table(SvbHandle* h) {
-  return TileTable{h->table_keys.as<unsigned long long>(), h->table_vals.as<uint32_t>(), h->table_mask, h->tile_key.as<unsigned long long>(), (uint32_t)h->tile_cap};
+  return TileTable{h->table_slots.as<ulonglong2>(), h->table_mask, h->tile_key.as<unsigned long long>(), h->tile_slot.as<uint32_t>(), (uint32_t)h->tile_cap};
 }
 MeldInfo meld_info(SvbHandle* h) { return MeldInfo{h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>()}; }
 
@@ -213,15 +218,19 @@ struct StepInputs {
 int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt_force) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->n;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  const StepScalars* S_prev = cur_scalars(h);
+  h->s_cur ^= 1;
+  StepScalars* S = cur_scalars(h);
   stage_begin(h, ST_BIN);
-  k_reset_scalars<<<1, 32, 0, s>>>(S, n);
+  if (h->tables_fresh) {
+    CK(cudaMemsetAsync(h->table_slots.p, 0xff, ((size_t)h->table_mask + 1) * 16, s));
+    CK(cudaMemsetAsync(h->cell_count.p, 0, h->tile_cap * 64 * 4, s));
+    CK(cudaMemsetAsync(h->tile_touch.p, 0, h->tile_cap * 4, s));
+    CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
+  }
+  k_begin<<<148, 256, 0, s>>>(S_prev, S, tile_table(h), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), n, h->tables_fresh ? 1 : 0);
   LAUNCH_CHECK();
-  CK(cudaMemsetAsync(h->table_keys.p, 0xff, ((size_t)h->table_mask + 1) * 8, s));
-  CK(cudaMemsetAsync(h->table_vals.p, 0xff, ((size_t)h->table_mask + 1) * 4, s));
-  CK(cudaMemsetAsync(h->cell_count.p, 0, h->tile_cap * 64 * 4, s));
-  CK(cudaMemsetAsync(h->tile_touch.p, 0, h->tile_cap * 4, s));
-  if (in.has_mesh) CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
+  h->tables_fresh = false;
   GoalDev G{nullptr, nullptr, nullptr, nullptr};
   if (h->has_goals) {
     G.flags_a = h->d_flags_a.as<uint32_t>();
@@ -232,7 +241,7 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   const TileTable T = tile_table(h);
   const BinArrays B{h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(),
                     h->layer_list.as<uint32_t>()};
-  const uint32_t blocks = blocks_for(n, 256);
+  const uint32_t blocks = std::max<uint32_t>(blocks_for(n, 256), 1);
 #define SVB_BIN(MESH, FORCE) k_bin<MESH, FORCE><<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, T, B, n, dt_force, in.g[0], in.g[1], in.g[2], in.factor_b)
   if (in.has_mesh) { if (apply_force) SVB_BIN(true, true); else SVB_BIN(true, false); }
   else { if (apply_force) SVB_BIN(false, true); else SVB_BIN(false, false); }
@@ -241,11 +250,9 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   stage_end(h);
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
-  k_cell_scan<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), (uint32_t)h->tile_cap);
+  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
   LAUNCH_CHECK();
   k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_start.as<uint32_t>(), &S->n_ptiles, 0, &S->n_live);
-  LAUNCH_CHECK();
-  k_halo<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 8 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(h->ev_front, s));
@@ -257,11 +264,11 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
 int enqueue_rebin(SvbHandle* h) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->n;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  StepScalars* S = cur_scalars(h);
   stage_begin(h, ST_PERMUTE);
-  k_invert<<<blocks_for(n, 256), 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->src_of.as<uint32_t>(), n);
-  LAUNCH_CHECK();
-  k_zero_grid<<<148 * 8, 256, 0, s>>>(S, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
+  const uint32_t invert_blocks = blocks_for(n, 256);
+  k_invert_zero<<<invert_blocks + 148 * 2, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->src_of.as<uint32_t>(), n, invert_blocks,
+                                                        h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
   LAUNCH_CHECK();
   h->masks_valid = false;
   if (h->store_grid) {
@@ -305,7 +312,7 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
 // into a velocity grid; without colliders G2P divides by the mass while it stages a tile.
 int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
   cudaStream_t s = h->stream;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  StepScalars* S = cur_scalars(h);
   const float4* src = h->grid.as<float4>();
   if (has_mesh) {
     CK(h->melded.ensure(h->tile_cap * 64 * 16));
@@ -325,8 +332,6 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
   else { if (has_mesh) SVB_G2P(false, true, true); else SVB_G2P(false, true, false); }
 #undef SVB_G2P
   LAUNCH_CHECK();
-  k_copy_tomb<<<64, 256, 0, s>>>(P, D, S, src_of, h->n);
-  LAUNCH_CHECK();
   h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
   return 0;
 }
@@ -339,7 +344,7 @@ int substep_slab(SvbHandle* h, const StepInputs& in);
 int substep(SvbHandle* h, bool adaptive_steps) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->n;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  // the scalars pointer flips inside enqueue_front (double buffer): always ask for the current half
   const float hh = h->K.h;
 
   if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
@@ -389,7 +394,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     const float dt = h->adaptive.allowed();
     if (int rc = enqueue_rebin(h)) return rc;
     stage_begin(h, ST_P2G);
-    k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+    k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
     LAUNCH_CHECK();
     stage_end(h);
     stage_begin(h, ST_G2P);
@@ -401,7 +406,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     if (rc == 1) {  // the binning was redone with a larger tile capacity: queue the back half again
       const TileTable T2 = tile_table(h);
       if (int rc2 = enqueue_rebin(h)) return rc2;
-      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
       LAUNCH_CHECK();
       if (int rc2 = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc2;
     }
@@ -422,9 +427,9 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   tile_start = h->tile_start.as<uint32_t>();
   // -- LimitTimeStepBeforeForce (limit_time_step.rs:25-33)
   stage_begin(h, ST_LIMIT);
-  k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), S, hh, n);
+  k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), cur_scalars(h), hh, n);
   LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_scalars, cur_scalars(h), sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   stage_end(h);
   {
@@ -440,14 +445,14 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   // -- ScatterMomentum, MeldGrid + CollectVelocity
   const float dt_scatter = h->adaptive.allowed();
   stage_begin(h, ST_P2G);
-  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt_scatter);
+  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt_scatter);
   LAUNCH_CHECK();
   stage_end(h);
   stage_begin(h, ST_G2P);
   if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/false, dt_scatter)) return rc;
 
   // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
-  CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_scalars, cur_scalars(h), sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   stage_end(h);
   {
@@ -462,7 +467,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   }
   // -- AdvanceParticles + CullParticles
   stage_begin(h, ST_ADVANCE);
-  k_advance<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, h->K, n, h->adaptive.allowed());
+  k_advance<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, h->adaptive.allowed());
   LAUNCH_CHECK();
   stage_end(h);
   h->have_grid = true;
@@ -476,7 +481,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
 // (the neighbours still expect this rank's messages).
 int substep_slab(SvbHandle* h, const StepInputs& in) {
   cudaStream_t s = h->stream;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  // the scalars pointer flips inside enqueue_front (double buffer): always ask for the current half
   const float hh = h->K.h;
   const float dt = h->adaptive.allowed();
   bool apply_force = true;
@@ -500,7 +505,7 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
   const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
   stage_begin(h, ST_P2G);
-  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
   LAUNCH_CHECK();
   stage_end(h);
   stage_begin(h, ST_HALO);
@@ -511,7 +516,7 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   h->n = n_after;
   // a FAILED particle on any rank stops every rank after this substep
   uint32_t* flag = h->comm_counts.as<uint32_t>() + 8;
-  CK(cudaMemcpyAsync(flag, &S->sticky, 4, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(flag, &cur_scalars(h)->sticky, 4, cudaMemcpyDeviceToDevice, s));
   if (ncclAllReduce(flag, flag, 1, ncclUint32, ncclMax, h->comm, s) != ncclSuccess) return fail(h, SVB_COMM_ERROR, "ncclAllReduce failed");
   CK(cudaMemcpyAsync(h->h_counts + 8, flag, 4, cudaMemcpyDeviceToHost, s));
   stage_end(h);
@@ -526,7 +531,7 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
 }
 
 int read_status(SvbHandle* h) {
-  StepScalars* S = h->scalars.as<StepScalars>();
+  StepScalars* S = cur_scalars(h);
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->status |= (h->h_scalars->status | h->h_scalars->sticky) & 0xffffu;
@@ -588,7 +593,8 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
     CK(h->pbuf[b].ensure(h->cap * NFIELDS * 4));
   }
   CK(h->energy.ensure(h->cap * 4));
-  CK(h->scalars.ensure(sizeof(StepScalars)));
+  CK(h->scalars.ensure(2 * sizeof(StepScalars)));
+  CK(cudaMemsetAsync(h->scalars.p, 0, 2 * sizeof(StepScalars), h->stream));
   CK(h->pcell.ensure(h->cap * 4));
   CK(h->prank.ensure(h->cap * 4));
   CK(h->src_of.ensure(h->cap * 4));
@@ -647,7 +653,7 @@ void svb_destroy(SvbHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_keys, &h->table_vals, &h->tile_key, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
+  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_slots, &h->tile_key, &h->tile_slot, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
                    &h->grid, &h->melded, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
@@ -766,7 +772,11 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (int rc = set_device(h)) return rc;
   h->adaptive.max_time_step = max_time_step;
   h->status = 0;
-  CK(cudaMemsetAsync(h->scalars.p, 0, sizeof(StepScalars), h->stream));
+  {  // a new advance starts without status bits; the tile bookkeeping of the last substep stays (k_begin undoes it)
+    StepScalars* S = cur_scalars(h);
+    CK(cudaMemsetAsync(&S->status, 0, 4, h->stream));
+    CK(cudaMemsetAsync(&S->sticky, 0, 4, h->stream));
+  }
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
   CK(cudaEventRecord(h->ev_adv[0], h->stream));
@@ -871,7 +881,7 @@ int32_t svb_download_grid(SvbHandle* h, SvbGrid* out) {
   CK(bits.ensure((size_t)total * 4));
   CK(masses.ensure((size_t)total * 4));
   CK(vels.ensure((size_t)total * 12));
-  k_emit_grid<<<h->n_tiles, 64, 0, h->stream>>>(h->grid.as<float4>(), tile_table(h), meld_info(h), h->scalars.as<StepScalars>(), h->node_mask.as<unsigned long long>(),
+  k_emit_grid<<<h->n_tiles, 64, 0, h->stream>>>(h->grid.as<float4>(), tile_table(h), meld_info(h), cur_scalars(h), h->node_mask.as<unsigned long long>(),
                                               h->node_offset.as<uint32_t>(), ids.as<int32_t>(), bits.as<uint32_t>(), masses.as<float>(), vels.as<float>());
   LAUNCH_CHECK();
   if (out->node_ids) CK(cudaMemcpyAsync(out->node_ids, ids.p, (size_t)total * 12, cudaMemcpyDeviceToHost, h->stream));
@@ -1047,7 +1057,7 @@ int exchange_payload(SvbHandle* h, const void* send_l, const void* send_r, void*
 // after P2G: add the neighbour's partial sums of the shared block column into this rank's tiles
 int halo_exchange(SvbHandle* h) {
   cudaStream_t s = h->stream;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  StepScalars* S = cur_scalars(h);
   const TileTable T = tile_table(h);
   uint32_t* cnt = h->comm_counts.as<uint32_t>() + 4;  // [4] left, [5] right
   uint32_t sendc[2] = {0, 0}, recvc[2] = {0, 0};
@@ -1088,7 +1098,7 @@ int halo_exchange(SvbHandle* h) {
 // after the advance: hand particles that left [lo, hi) to the neighbour, append the ones coming in
 int migrate(SvbHandle* h) {
   cudaStream_t s = h->stream;
-  StepScalars* S = h->scalars.as<StepScalars>();
+  StepScalars* S = cur_scalars(h);
   uint32_t* cnt = h->comm_counts.as<uint32_t>() + 4;
   uint32_t sendc[2] = {0, 0}, recvc[2] = {0, 0};
   const uint32_t n = h->n;

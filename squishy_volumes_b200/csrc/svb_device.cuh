@@ -78,10 +78,10 @@ __host__ __device__ inline unsigned long long tile_key_offset(unsigned long long
 }
 
 struct TileTable {
-  unsigned long long* keys;   // [mask + 1], TILE_EMPTY when free
-  uint32_t* vals;             // [mask + 1], tile id (TILE_PENDING until published)
+  ulonglong2* slots;          // [mask + 1] {key (TILE_EMPTY when free), tile id (TILE_PENDING until published)}: one 16-byte load per probe
   uint32_t mask;
   unsigned long long* tile_key;  // [tile_cap] key of tile id
+  uint32_t* tile_slot;           // [tile_cap] table slot of tile id (the next substep clears exactly the used slots)
   uint32_t tile_cap;
 };
 
@@ -99,6 +99,7 @@ struct StepScalars {
   uint32_t n_tiles_zeroed;  // tiles cleared by k_zero_grid (tiles created later by a halo message are stored, not added)
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];
+  uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
   // adaptive time step reductions (f32::total_cmp keys)
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;

@@ -254,30 +254,36 @@ __device__ __forceinline__ uint32_t tile_hash(unsigned long long k, uint32_t mas
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (uint32_t)k & mask;
 }
+__device__ __forceinline__ ulonglong2 slot_load(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
 // returns the tile id, or TILE_PENDING when the tile capacity is exhausted (status bit set)
 __device__ __forceinline__ uint32_t tile_find_or_insert(const TileTable& T, unsigned long long key, StepScalars* S) {
   uint32_t s = tile_hash(key, T.mask);
   for (uint32_t tries = 0; tries <= T.mask; ++tries) {
-    unsigned long long cur = *(volatile unsigned long long*)&T.keys[s];
-    if (cur == TILE_EMPTY) {
-      cur = atomicCAS(&T.keys[s], TILE_EMPTY, key);
-      if (cur == TILE_EMPTY) {
+    ulonglong2 cur = slot_load(&T.slots[s]);
+    if (cur.x == TILE_EMPTY) {
+      cur.x = atomicCAS(&T.slots[s].x, TILE_EMPTY, key);
+      if (cur.x == TILE_EMPTY) {
         const uint32_t id = atomicAdd(&S->n_tiles, 1u);
         if (id < T.tile_cap) {
           T.tile_key[id] = key;
+          T.tile_slot[id] = s;
           __threadfence();
-          *(volatile uint32_t*)&T.vals[s] = id;
+          *(volatile unsigned long long*)&T.slots[s].y = id;
           return id;
         }
         atomicOr(&S->status, ST_TILE_OVERFLOW);
-        *(volatile uint32_t*)&T.vals[s] = TILE_PENDING - 1;  // poisoned: waiters stop spinning
+        *(volatile unsigned long long*)&T.slots[s].y = TILE_PENDING - 1;  // poisoned: waiters stop spinning
         return TILE_PENDING;
       }
+      cur.y = ~0ull;
     }
-    if (cur == key) {
-      uint32_t v;
-      while ((v = *(volatile uint32_t*)&T.vals[s]) == TILE_PENDING) {}
-      return v == TILE_PENDING - 1 ? TILE_PENDING : v;
+    if (cur.x == key) {
+      while ((uint32_t)cur.y == TILE_PENDING) cur.y = *(volatile unsigned long long*)&T.slots[s].y;
+      return (uint32_t)cur.y == TILE_PENDING - 1 ? TILE_PENDING : (uint32_t)cur.y;
     }
     s = (s + 1) & T.mask;
   }
@@ -287,12 +293,9 @@ __device__ __forceinline__ uint32_t tile_find_or_insert(const TileTable& T, unsi
 __device__ __forceinline__ int tile_find(const TileTable& T, unsigned long long key) {
   uint32_t s = tile_hash(key, T.mask);
   for (uint32_t tries = 0; tries <= T.mask; ++tries) {
-    const unsigned long long cur = T.keys[s];
-    if (cur == key) {
-      const uint32_t v = T.vals[s];
-      return v >= TILE_PENDING - 1 ? -1 : (int)v;
-    }
-    if (cur == TILE_EMPTY) return -1;
+    const ulonglong2 cur = T.slots[s];
+    if (cur.x == key) return (uint32_t)cur.y >= TILE_PENDING - 1 ? -1 : (int)(uint32_t)cur.y;
+    if (cur.x == TILE_EMPTY) return -1;
     s = (s + 1) & T.mask;
   }
   return -1;
@@ -318,19 +321,35 @@ struct BinArrays {
   unsigned long long* layer_slots;
   uint32_t* layer_list;
 };
-__global__ void k_reset_scalars(StepScalars* S, uint32_t n) {
-  if (threadIdx.x != 0) return;
-  const uint32_t sticky = S->sticky;
-  StepScalars z{};
-  z.n = n;
-  z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
-  z.sticky = sticky;
-  *S = z;
+// Start of a substep: undo exactly what the previous substep left in the per-substep tables (its tiles'
+// hash slots, touch masks and cell counters; the layer set) instead of memset-ing whole allocations, and
+// initialise this substep's scalars.  `prev` / `cur` are the two halves of a double buffer, so no thread
+// of this launch reads what another one writes.
+__global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ prev, StepScalars* __restrict__ cur, TileTable T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_touch,
+                                               unsigned long long* __restrict__ layer_slots, uint32_t n, int tables_fresh) {
+  // tables_fresh: the host has just (re)allocated and memset the tables, tile_slot holds nothing to undo
+  const uint32_t n_tiles = tables_fresh ? 0u : min(prev->n_tiles, T.tile_cap), n_ptiles = tables_fresh ? 0u : min(prev->n_ptiles, T.tile_cap);
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (uint32_t t = gtid; t < n_tiles; t += gsz) {
+    T.slots[T.tile_slot[t]] = make_ulonglong2(TILE_EMPTY, ~0ull);
+    tile_touch[t] = 0u;
+  }
+  uint4* cc = reinterpret_cast<uint4*>(cell_count);
+  for (uint32_t q = gtid; q < n_ptiles * 16u; q += gsz) cc[q] = make_uint4(0u, 0u, 0u, 0u);
+  if (prev->n_layers && !tables_fresh)
+    for (uint32_t q = gtid; q < LAYER_SLOTS; q += gsz) layer_slots[q] = 0ull;
+  if (gtid == 0) {
+    StepScalars z{};
+    z.n = n;
+    z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
+    z.sticky = prev->sticky;
+    *cur = z;
+  }
 }
 template <bool HAS_MESH, bool APPLY_FORCE>
 __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, GoalDev G, TileTable T, BinArrays B, uint32_t n, float dt, float gx, float gy,
                                              float gz, float factor_b) {
-  if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is
+  if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is (every later kernel no-ops too)
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
   bool live = false, tomb = false, gone = false;
@@ -385,9 +404,7 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   if (live && (int)lane == leader) tile = tile_find_or_insert(T, key, S);
   tile = __shfl_sync(SVB_FULL, tile, leader);
   const uint32_t tm = __reduce_or_sync(peers, touch);
-  if (live && (int)lane == leader && tile != TILE_PENDING) {
-    if ((B.tile_touch[tile] & tm) != tm) atomicOr(&B.tile_touch[tile], tm);
-  }
+  if (live && (int)lane == leader && tile != TILE_PENDING) atomicOr(&B.tile_touch[tile], tm);  // result unused: a fire-and-forget RED
   // ---- slot in the cell: one atomic per distinct (tile, cell) in the warp
   const bool binned = live && tile != TILE_PENDING;
   const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : (gone ? 0xfffffffdu : 0xfffffffeu));
@@ -403,16 +420,31 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
     B.pcell[i] = ci;
     B.prank[i] = base + __popc(cpeers & ((1u << lane) - 1u));
   }
+  // the last block to finish publishes the number of particle-owning tiles (halo tiles get ids after them)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&S->bin_blocks_done, 1u) == gridDim.x - 1) S->n_ptiles = min(atomicAdd(&S->n_tiles, 0u), T.tile_cap);
+  }
 }
 
-// per particle-owning tile: exclusive scan of its 64 cell counts (in place) and the tile total
-__global__ void __launch_bounds__(256) k_cell_scan(StepScalars* S, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_total, uint32_t tile_cap) {
+// per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile total,
+// and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
+// (update_grid_nodes.rs:102-108)
+__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_total, const uint32_t* __restrict__ tile_touch,
+                                                 int* __restrict__ nbr) {
+  if (SVB_ABORTED(S)) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n_ptiles = min(S->n_tiles, tile_cap);
-  if (blockIdx.x == 0 && threadIdx.x == 0) S->n_ptiles = n_ptiles;
-  if (SVB_ABORTED(S)) return;
+  const uint32_t n_ptiles = S->n_ptiles;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_ptiles; t += warps) {
+    // halo first: its table probes overlap the scan below
+    int r = -1;
+    if (lane == 0) r = (int)t;
+    else if (lane < 8 && ((tile_touch[t] >> lane) & 1u)) {
+      const uint32_t id = tile_find_or_insert(T, tile_key_offset(T.tile_key[t], (int)lane), S);
+      r = id == TILE_PENDING ? -1 : (int)id;
+    }
     const uint2 c = *reinterpret_cast<const uint2*>(cell_count + (size_t)t * 64 + 2 * lane);
     const uint32_t mine = c.x + c.y;
     uint32_t inc = mine;
@@ -424,6 +456,7 @@ __global__ void __launch_bounds__(256) k_cell_scan(StepScalars* S, uint32_t* __r
     const uint32_t ex = inc - mine;
     *reinterpret_cast<uint2*>(cell_count + (size_t)t * 64 + 2 * lane) = make_uint2(ex, ex + c.x);
     if (lane == 31) tile_total[t] = inc;
+    if (lane < 8) nbr[(size_t)t * 8 + lane] = r;
   }
 }
 
@@ -468,31 +501,27 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* a, const uint32_t
   }
 }
 
-// per particle-owning tile: create the halo tiles its particles reach and record the 8 neighbour ids
-__global__ void __launch_bounds__(256) k_halo(StepScalars* S, TileTable T, const uint32_t* __restrict__ tile_touch, int* __restrict__ nbr) {
-  if (SVB_ABORTED(S)) return;
-  const uint32_t n_ptiles = S->n_ptiles;
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_ptiles * 8; q += gridDim.x * blockDim.x) {
-    const uint32_t t = q >> 3, d = q & 7;
-    int r = -1;
-    if (d == 0) r = (int)t;
-    else if ((tile_touch[t] >> d) & 1u) {
-      const uint32_t id = tile_find_or_insert(T, tile_key_offset(T.tile_key[t], (int)d), S);
-      r = id == TILE_PENDING ? -1 : (int)id;
-    }
-    nbr[q] = r;
-  }
-}
-
 // re-bin (sort.rs:91-101).  Slot of particle i in the binned order:
 //   j = tile_start[tile] + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
 // Only the inverse map src_of[j] = i is materialised here (4 B per particle).  P2G gathers its inputs
 // through it and G2P writes its results — and the fields it merely carries — to slot j of the other
 // buffer, so the physical permutation of the 136-byte state costs no pass of its own: consecutive
 // slots come from (nearly) consecutive rows of the previous order, the gathers stay coalesced.
-__global__ void __launch_bounds__(256) k_invert(const StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank,
-                                                const uint32_t* __restrict__ cell_offset, const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ src_of, uint32_t n) {
+// The same launch also clears the grid tiles of this substep (blocks beyond the particle range).
+__global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank, const uint32_t* __restrict__ cell_offset,
+                                                     const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
+                                                     unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
   if (SVB_ABORTED(S)) return;
+  if (blockIdx.x >= invert_blocks) {
+    const size_t total = (size_t)min(S->n_tiles, tile_cap) * 64;
+    const size_t stride = (size_t)(gridDim.x - invert_blocks) * blockDim.x;
+    for (size_t q = (size_t)(blockIdx.x - invert_blocks) * blockDim.x + threadIdx.x; q < total; q += stride) {
+      grid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (node_mask && (q & 63) == 0) node_mask[q >> 6] = 0ull;
+    }
+    if (blockIdx.x == invert_blocks && threadIdx.x == 0) S->n_tiles_zeroed = (uint32_t)(total >> 6);
+    return;
+  }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t ci = pcell[i];
@@ -503,28 +532,6 @@ __global__ void __launch_bounds__(256) k_invert(const StepScalars* __restrict__ 
   } else j = tile_start[ci >> 6] + cell_offset[ci] + prank[i];
   src_of[j] = i;
 }
-// tombstoned particles take no part in P2G / G2P: carry their rows over as they are
-__global__ void __launch_bounds__(256) k_copy_tomb(ParticleBuf src, ParticleBuf dst, const StepScalars* __restrict__ S, const uint32_t* __restrict__ src_of, uint32_t n) {
-  if (SVB_ABORTED(S)) return;
-  const uint32_t n_live = S->n_live;
-  n = n_live + S->n_tomb;  // rows of migrated particles are gone
-  for (uint32_t j = n_live + blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const uint32_t i = src_of[j];
-#pragma unroll
-    for (int f = 0; f < NFIELDS; ++f) dst.base[(size_t)f * dst.cap + j] = src.base[(size_t)f * src.cap + i];
-  }
-}
-
-__global__ void __launch_bounds__(256) k_zero_grid(StepScalars* __restrict__ S, float4* __restrict__ grid, unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
-  if (SVB_ABORTED(S)) return;
-  const size_t total = (size_t)min(S->n_tiles, tile_cap) * 64;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
-    grid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (node_mask && (q & 63) == 0) node_mask[q >> 6] = 0ull;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) S->n_tiles_zeroed = (uint32_t)(total >> 6);
-}
-
 // ------------------------------------------------------------------------------------------------
 // P2G (scatter_momentum.rs:22-93).  One CTA per (block, layer) run of particles, claimed from a
 // work counter.  Each warp takes 32 consecutive particles: every lane evaluates ITS particle once
@@ -877,6 +884,15 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
 #pragma unroll
       for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
       D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
+    }
+  }
+  // tombstoned particles take no part in P2G / G2P: carry their rows over as they are (behind the live ones)
+  {
+    const uint32_t n_live = S->n_live, n_end = n_live + S->n_tomb;  // rows of migrated particles are gone
+    for (uint32_t j = n_live + blockIdx.x * blockDim.x + threadIdx.x; j < n_end; j += gridDim.x * blockDim.x) {
+      const uint32_t i = src_of[j];
+#pragma unroll 1
+      for (int f = 0; f < NFIELDS; ++f) D.base[(size_t)f * D.cap + j] = P.base[(size_t)f * P.cap + i];
     }
   }
   if (REDUCE) {
