@@ -47,12 +47,15 @@ A_G2P = 56.0 + 96.0
 A_GRID = 8.0
 A_NOSORT = 280.0
 A_SORT_EXTRA = 272.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
+# committed `ncu --set full` capture (profiles/r1b_top_kernels_jelly1M.txt)
+TRAFFIC = {"p2g": 125.8e6 + 5.0e6, "g2p": 97.7e6 + 95.9e6}
 
 
-def make_scene(name: str, scale: float):
+def make_scene(name: str, scale: float, length: int = 1):
     if name == "jelly_collision":
         side = max(4, int(round(80 * scale ** (1.0 / 3.0))))
-        return scenes.jelly_collision(side=side)
+        return scenes.jelly_collision(side=side, length=length)
     if name == "elastic_cube":
         return scenes.elastic_cube(side=max(4, int(round(46 * scale ** (1.0 / 3.0)))))
     if name == "sand_torus":
@@ -156,6 +159,8 @@ def dist_setup(n_gpus: int):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
+        # torch.distributed (NCCL) carries the control plane: unique-id hand-over, barriers, max over ranks.  The data
+        # path — halo sums and migrating particles — runs on the library's own NCCL communicator (svb_comm_init).
         dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
     return rank, world, local, dist
@@ -181,6 +186,7 @@ def all_sum(dist, local, value: float) -> float:
 
 def barrier(dist, local):
     import torch
+    torch.cuda.synchronize(local)
     if dist is not None:
         dist.barrier(device_ids=[local])
     torch.cuda.synchronize(local)
@@ -200,11 +206,19 @@ def main():
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
 
-    scene = make_scene(args.scene, args.scale)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env > 1 and args.scene != "jelly_collision":
+        raise SystemExit("multi-GPU bench: only the jelly_collision workload is slab-decomposed here")
+    # N > 1: weak scaling — the blocks grow along x with the GPU count, the slab decomposition cuts them on
+    # block planes, neighbours exchange grid-halo sums after P2G and migrating particles after the advance.
+    scene = make_scene(args.scene, args.scale, length=world_env)
     scene.frame_input.consts.frames_per_second = 1  # one long frame: the bench never crosses a keyframe boundary
     dt = scene.time_step
-    config = {"workload": f"{args.scene}: {scene.description}", "particles_per_gpu": scene.n, "time_step": dt, "adaptive_time_steps": bool(args.adaptive),
-              "rebin": "every substep (counting sort on (tile, cell) + physical permutation of the SoA state)", "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush"}
+    config = {"workload": f"{args.scene}: {scene.description}", "particles_total": scene.n, "particles_per_gpu": scene.n // max(world_env, 1),
+              "time_step": dt, "adaptive_time_steps": bool(args.adaptive),
+              "rebin": "every substep (counting sort on (tile, cell); the physical permutation rides on the G2P write)",
+              "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush",
+              "decomposition": "single GPU" if world_env == 1 else f"{world_env} slabs along x, NCCL halo-column exchange + particle migration every substep"}
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
@@ -223,57 +237,73 @@ def main():
     rank, world, local, dist = dist_setup(args.gpus)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback")
-
-    # ---------------- device-resident throughput
-    state = B200State.from_io_state(scene.io_state, scene.frame_input, device=local)
     fi = scene.frame_input
     t0 = scene.io_state.time
-    params = lambda k: RunParameters(target_time=t0 + (k - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive)
-    state.snapshot()
+
+    def run_params(state, k):
+        return RunParameters(target_time=state.time + (k - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive)
+
+    def fresh_unique_id():
+        """An NCCL unique id serves one communicator: every slab state gets its own, handed over by rank 0."""
+        from squishy_volumes_b200 import abi
+        import ctypes as C
+        box = [None]
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            assert abi.load().svb_comm_unique_id(buf) == 0
+            box[0] = bytes(buf)
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def make_state(io_state):
+        """-> (object with .advance/.time, the B200State that owns the device handle)"""
+        if world == 1:
+            st = B200State.from_io_state(io_state, fi, device=local)
+            return st, st
+        from squishy_volumes_b200 import slabs
+        st = slabs.SlabState.from_io_state(io_state, fi, rank, world, local, fresh_unique_id())
+        return st, st.inner
+
+    # ---------------- device-resident throughput
+    state, inner = make_state(scene.io_state)
     if warmup:
-        state.advance(None, fi, params(warmup))
-    state.restore()
-    if warmup:
-        state.advance(None, fi, params(warmup))   # state now `warmup` substeps in: contact has begun
-    k0 = state.substeps
-    launches0 = state.kernel_launches
+        state.advance(None, fi, run_params(state, warmup))   # contact has begun, buffers have settled
+    launches0 = inner.kernel_launches
     barrier(dist, local)
     with ClockSampler(local) as clocks:
-        state.advance(None, fi, RunParameters(target_time=state.time + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
-        ms = state.last_advance_ms
+        state.advance(None, fi, run_params(state, steps))
+        ms = inner.last_advance_ms
         barrier(dist, local)
+        gpu_launches = inner.kernel_launches - launches0
         # keep sampling clocks over a few more identical passes so short runs still get samples
         extra = 0
         while len(clocks.samples) < 3 and extra < 20:
-            state.advance(None, fi, RunParameters(target_time=state.time + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+            state.advance(None, fi, run_params(state, steps))
             extra += 1
     done = steps
-    gpu_launches = (state.kernel_launches - launches0) // (1 + extra)
     ms_max = all_max(dist, local, ms)
-    total_particles = all_sum(dist, local, float(scene.n))
+    total_particles = float(scene.n)
     value = total_particles * done / (ms_max * 1e-3)
 
     # ---------------- per-stage pass (instrumented: one event pair + sync per stage) -> roofline
-    state.restore()
-    if warmup:
-        state.advance(None, fi, params(warmup))
-    state.enable_stage_timing(True)
-    state.advance(None, fi, RunParameters(target_time=state.time + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
-    stages = {k: v / steps for k, v in state.stage_times().items()}
-    state.enable_stage_timing(False)
+    inner.enable_stage_timing(True)
+    state.advance(None, fi, run_params(state, steps))
+    stages = {k: v / steps for k, v in inner.stage_times().items()}
+    inner.enable_stage_timing(False)
     peak, peak_kind = measured_peak()
+    n_local = scene.n / world
     dom = max(("p2g", "g2p"), key=lambda s: stages.get(s, 0.0))
-    alg_bytes = scene.n * ((A_P2G if dom == "p2g" else A_G2P) + A_GRID / 2)
+    alg_bytes = n_local * ((A_P2G if dom == "p2g" else A_G2P) + A_GRID / 2)
     dom_ms = max(stages.get(dom, 0.0), 1e-9)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    whole = scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
-                "whole_substep": {"algorithmic_bytes": scene.n * (A_NOSORT + A_SORT_EXTRA), "achieved": scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9,
-                                  "frac": scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9 / peak},
-                "stage_ms_per_substep": stages}
+                "frac": achieved / peak, "traffic": TRAFFIC.get(dom), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
+                "whole_substep": {"algorithmic_bytes": scene.n * (A_NOSORT + A_SORT_EXTRA), "achieved": whole, "frac": whole / (peak * world)},
+                "stage_ms_per_substep": stages, "stage_note": "rank 0, instrumented pass (one event pair and a sync per stage)"}
+    state.close()
 
     # ---------------- end to end through the public API with host buffers (page-locked, as the contract asks)
-    state.close()
     import dataclasses
     from squishy_volumes_b200.types import IoState, Particles
     keep = []
@@ -284,21 +314,35 @@ def main():
         v = t.numpy()
         v[...] = a
         return v
-    host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)}))
-    out_buffers = Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)})
-    h2d = sum(getattr(host_state.particles, f).nbytes for f in ("flags", "mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha", "viscosity_dynamic",
-                                                                 "viscosity_bulk", "positions", "position_gradients", "velocities", "velocity_gradients", "elastic_energies", "collider_bits"))
+    fields = ("flags", "mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha", "viscosity_dynamic", "viscosity_bulk", "positions",
+              "position_gradients", "velocities", "velocity_gradients", "elastic_energies", "collider_bits")
+    if world == 1:
+        host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)}))
+        out_buffers = Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)})
+        h2d = sum(getattr(host_state.particles, f).nbytes for f in fields)
+        barrier(dist, local)
+        te = time.perf_counter()
+        st2 = B200State.from_io_state(host_state, fi, device=local)
+        out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
+        barrier(dist, local)
+        e2e_s = time.perf_counter() - te
+        e2e_done = st2.substeps
+        st2.close()
+        what = f"from_io_state (H2D of the whole state) + produce_next_state ({e2e_done} substeps + D2H of the IoState), wall clock"
+    else:
+        h2d = sum(getattr(scene.io_state.particles, f).nbytes for f in fields)   # summed over ranks: every particle goes up once and comes back once
+        barrier(dist, local)
+        te = time.perf_counter()
+        st2, inner2 = make_state(scene.io_state)       # splits the host state, uploads this rank's slab
+        st2.advance(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+        idx, rows = st2.resident()                      # D2H of the rows this rank holds now
+        barrier(dist, local)
+        e2e_s = all_max(dist, local, time.perf_counter() - te)
+        e2e_done = st2.substeps
+        st2.close()
+        what = f"SlabState.from_io_state (split + H2D of each slab) + {e2e_done} substeps with halo exchange and migration + D2H of the resident rows, wall clock, max over ranks"
     d2h = h2d
-    barrier(dist, local)
-    te = time.perf_counter()
-    st2 = B200State.from_io_state(host_state, fi, device=local)
-    out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
-    barrier(dist, local)
-    e2e_s = all_max(dist, local, time.perf_counter() - te)
-    e2e_done = st2.substeps
-    st2.close()
-    e2e = {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": d2h / e2e_done,
-           "what": f"from_io_state (H2D of the whole state) + produce_next_state ({e2e_done} substeps + D2H of the IoState), wall clock, max over ranks"}
+    e2e = {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": d2h / e2e_done, "what": what}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": warmup, "ms_per_step": ms_max / done, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "roofline": roofline, "e2e": e2e, "gpu_launches": int(gpu_launches),

@@ -1,11 +1,12 @@
 """Aggregate an exported ncu source page (ncu -i X.ncu-rep --page source --csv --print-source sass,cuda) by CUDA source line:
-executed warp instructions and stall samples per line of svb_kernels.cuh.  Usage: python profiles/srcpage.py src.csv [top_n]"""
+executed warp instructions and stall samples per line of svb_kernels.cuh.  Usage: python profiles/srcpage.py src.csv [top_n] [kernel substring]"""
 import csv
 import sys
 import collections
 
 path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+only = sys.argv[3] if len(sys.argv) > 3 else ""   # substring of the kernel name
 rows = list(csv.reader(open(path)))
 # locate header rows; the file holds one table per function/file
 agg = collections.OrderedDict()
@@ -20,7 +21,7 @@ for r in rows:
     if r[0] == "Line No":
         hdr = r
         continue
-    if hdr is None or len(r) < len(hdr) or not r[0].strip().isdigit():
+    if hdr is None or len(r) < len(hdr) or not r[0].strip().isdigit() or (only and only not in (fn or "")):
         continue
     d = dict(zip(hdr, r))
     try:

@@ -180,13 +180,16 @@ def elastic_cube(side: int = 46, h: float = 0.04, n_keyframes: int = 12) -> Scen
                  f"{p.n}-particle elastic cube (E=1e4, nu=0.3) on a 2-triangle ground plane, h={h}")
 
 
-def jelly_collision(side: int = 80, h: float = 0.04, n_keyframes: int = 4) -> Scene:
-    """Config 2: two Neo-Hookean blocks (2*side^3 particles; side=80 -> 1.02 M) approaching at +-1 m/s."""
+def jelly_collision(side: int = 80, h: float = 0.04, n_keyframes: int = 4, length: int = 1) -> Scene:
+    """Config 2: two Neo-Hookean blocks (2*side^3 particles; side=80 -> 1.02 M) approaching at +-1 m/s.
+    `length` stretches both blocks along x (length*side x side x side each): the weak-scaling workload of
+    the slab decomposition, 1.02 M particles and a constant 80 x 80-cell cut face per GPU."""
     sp = h / 2
     gap = 2 * h
-    a = make_particles(lattice((side,) * 3, sp, (-side * sp - gap / 2, -side * sp / 2, -side * sp / 2), seed=SEED),
+    sx = side * length
+    a = make_particles(lattice((sx, side, side), sp, (-sx * sp - gap / 2, -side * sp / 2, -side * sp / 2), seed=SEED),
                        sp, Material("solid", 1000.0, 1e4, 0.3), velocity=(1.0, 0.0, 0.0))
-    b = make_particles(lattice((side,) * 3, sp, (gap / 2, -side * sp / 2, -side * sp / 2), seed=SEED + 1),
+    b = make_particles(lattice((sx, side, side), sp, (gap / 2, -side * sp / 2, -side * sp / 2), seed=SEED + 1),
                        sp, Material("solid", 1000.0, 1e5, 0.3), velocity=(-1.0, 0.0, 0.0))
     p = Particles.concatenate([a, b])
     fi = _frame_input(_consts(h, 100.0), [], p.n, (0, 0, 0), [], [], n_keyframes)
