@@ -99,6 +99,14 @@ struct SvbHandle {
   uint32_t* h_counts = nullptr;  // pinned
   size_t halo_cap = 0, mig_cap = 0, halo_margin = 2048;
   uint64_t halo_tiles_sent = 0, migrated_out = 0;
+  // peer-memory exchange (CUDA IPC mailboxes; the NCCL path above stays as the fallback when IPC is unavailable)
+  bool p2p = false;
+  DevBuf mailbox;                       // this rank's mailbox: SlabHeader | halo in (left, right) | rows in (left, right)
+  void* peer_mailbox[16] = {};          // every rank's mailbox mapped into this process (null for self)
+  size_t mb_halo_cap = 0, mb_mig_cap = 0, mb_halo_off[2] = {0, 0}, mb_mig_off[2] = {0, 0};
+  uint32_t slab_seq = 0;                // message sequence number = slab substeps started
+  uint32_t* n_dev = nullptr;            // device word: rows currently in the particle buffer
+  uint32_t* p2p_local = nullptr;        // device scratch of the sending kernels (slot counters, blocks done)
 
   double time = 0;
   svbh::AdaptiveTimeStep adaptive;
@@ -217,7 +225,7 @@ struct StepInputs {
 // while the back half is already queued behind it.
 int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt_force) {
   cudaStream_t s = h->stream;
-  const uint32_t n = h->n;
+  const uint32_t n = h->p2p ? (uint32_t)h->cap : h->n;   // peer-memory slabs: the exact row count lives on the device, launch for the capacity
   const StepScalars* S_prev = cur_scalars(h);
   h->s_cur ^= 1;
   StepScalars* S = cur_scalars(h);
@@ -228,7 +236,7 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
     CK(cudaMemsetAsync(h->tile_touch.p, 0, h->tile_cap * 4, s));
     CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
   }
-  k_begin<<<148, 256, 0, s>>>(S_prev, S, tile_table(h), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), n, h->tables_fresh ? 1 : 0);
+  k_begin<<<148, 256, 0, s>>>(S_prev, S, tile_table(h), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), n, h->p2p ? h->n_dev : nullptr, h->tables_fresh ? 1 : 0);
   LAUNCH_CHECK();
   h->tables_fresh = false;
   GoalDev G{nullptr, nullptr, nullptr, nullptr};
@@ -263,7 +271,7 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
 // re-bin + grid preparation that follows the front half
 int enqueue_rebin(SvbHandle* h) {
   cudaStream_t s = h->stream;
-  const uint32_t n = h->n;
+  const uint32_t n = h->p2p ? (uint32_t)h->cap : h->n;
   StepScalars* S = cur_scalars(h);
   stage_begin(h, ST_PERMUTE);
   const uint32_t invert_blocks = blocks_for(n, 256);
@@ -339,6 +347,9 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
 int halo_exchange(SvbHandle* h);
 int migrate(SvbHandle* h);
 int substep_slab(SvbHandle* h, const StepInputs& in);
+int substep_slab_p2p(SvbHandle* h, const StepInputs& in);
+int setup_peer_mailboxes(SvbHandle* h);
+int resize_particles(SvbHandle* h, size_t new_cap);
 
 // ---- one substep: the 12 phases of cpu/src/phase/mod.rs:27-41 in the reference's order
 int substep(SvbHandle* h, bool adaptive_steps) {
@@ -372,7 +383,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   }
   if (h->slabs) {
     if (adaptive_steps) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps are not supported with slab decomposition yet");
-    return substep_slab(h, in);
+    return h->p2p ? substep_slab_p2p(h, in) : substep_slab(h, in);
   }
   if (n == 0) {
     h->time += (double)h->adaptive.allowed();
@@ -530,6 +541,96 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   return 0;
 }
 
+// one fixed-dt substep of a slab rank over peer memory: nothing on the data path returns to the host.  The whole
+// substep is queued, then the host looks at the front half's scalars (one substep of lag at most).
+int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
+  cudaStream_t s = h->stream;
+  const float hh = h->K.h;
+  const float dt = h->adaptive.allowed();
+  const uint32_t seq = ++h->slab_seq;
+  if (int rc = enqueue_front(h, in, /*apply_force=*/true, dt)) return rc;
+  if (int rc = enqueue_rebin(h)) return rc;
+  StepScalars* S = cur_scalars(h);
+  const TileTable T = tile_table(h);
+  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
+  stage_begin(h, ST_P2G);
+  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
+  LAUNCH_CHECK();
+  stage_end(h);
+  stage_begin(h, ST_HALO);
+  SlabHeader* my_hdr = h->mailbox.as<SlabHeader>();
+  unsigned char* my_mb = h->mailbox.as<unsigned char>();
+  const bool has[2] = {h->rank > 0, h->rank + 1 < h->n_ranks};
+  for (int side = 0; side < 2; ++side)
+    if (has[side]) {
+      // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right; the message lands in
+      // the neighbour's slot for "from the right" (side 0) / "from the left" (side 1)
+      unsigned char* peer = static_cast<unsigned char*>(h->peer_mailbox[h->rank + (side ? 1 : -1)]);
+      SlabHeader* ph = reinterpret_cast<SlabHeader*>(peer);
+      const int their = side ? 0 : 1;
+      k_halo_send<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), side ? h->slab_hi : h->slab_lo, reinterpret_cast<HaloEntry*>(peer + h->mb_halo_off[their]),
+                                      &ph->halo_count[their], &ph->halo_seq[their], (uint32_t)h->mb_halo_cap, seq, h->p2p_local + 4 * side);
+      LAUNCH_CHECK();
+    }
+  for (int side = 0; side < 2; ++side)
+    if (has[side]) {
+      k_halo_recv<<<148 * 2, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(), h->grid.as<float4>(),
+                                          reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[side]), &my_hdr->halo_count[side], &my_hdr->halo_seq[side], seq);
+      LAUNCH_CHECK();
+    }
+  stage_end(h);
+  stage_begin(h, ST_G2P);
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc;
+  stage_end(h);
+  stage_begin(h, ST_MIGRATE);
+  SlabPeers peers{};
+  peers.n_ranks = h->n_ranks;
+  for (int side = 0; side < 2; ++side)
+    if (has[side]) {
+      unsigned char* peer = static_cast<unsigned char*>(h->peer_mailbox[h->rank + (side ? 1 : -1)]);
+      SlabHeader* ph = reinterpret_cast<SlabHeader*>(peer);
+      const int their = side ? 0 : 1;
+      peers.rows[side] = reinterpret_cast<uint32_t*>(peer + h->mb_mig_off[their]);
+      peers.count[side] = &ph->mig_count[their];
+      peers.seq[side] = &ph->mig_seq[their];
+    }
+  for (int r = 0; r < h->n_ranks; ++r)
+    if (r != h->rank) {
+      SlabHeader* ph = reinterpret_cast<SlabHeader*>(h->peer_mailbox[r]);
+      peers.err_seq[r] = &ph->err_seq[h->rank];
+      peers.err_val[r] = &ph->err_val[h->rank];
+    }
+  k_migrate_send<<<148 * 4, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, hh, h->slab_lo, h->slab_hi, h->reach_lo, h->reach_hi, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 8);
+  LAUNCH_CHECK();
+  k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev);
+  LAUNCH_CHECK();
+  stage_end(h);
+  // ---- the host catches up with the front half of this substep (the back half keeps the GPU busy meanwhile)
+  CK(cudaEventSynchronize(h->ev_front));
+  const StepScalars& r = *h->h_scalars;
+  if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys");
+  if (r.status & ST_TILE_OVERFLOW) return fail(h, SVB_COMM_ERROR, "tile capacity exceeded on a slab rank (%u tiles > %zu)", r.n_tiles, h->tile_cap);
+  if (r.sticky) {  // the previous substep failed somewhere: this one was a no-op on every rank
+    h->status |= r.sticky & 0xffffu;
+    return 0;
+  }
+  h->n_tiles = r.n_tiles;
+  h->n_ptiles = r.n_ptiles;
+  h->n_live = r.n_live;
+  h->status |= r.status & 0xffffu;
+  if (((size_t)r.n_tiles + h->halo_margin) * 3 / 2 > h->tile_cap) {  // grow ahead of need: an overflow cannot be redone once messages are out
+    CK(cudaStreamSynchronize(s));
+    if (int rc = ensure_tile_capacity(h, ((size_t)r.n_tiles + h->halo_margin) * 3)) return rc;
+  }
+  h->have_grid = true;
+  h->time += (double)dt;
+  ++h->substeps;
+  return 0;
+}
+
 int read_status(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
@@ -658,10 +759,12 @@ void svb_destroy(SvbHandle* h) {
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
                    &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e,
-                   &h->comm_counts, &h->halo_send[0], &h->halo_send[1], &h->halo_recv[0], &h->halo_recv[1], &h->mig_send[0], &h->mig_send[1], &h->mig_recv[0], &h->mig_recv[1]};
+                   &h->comm_counts, &h->mailbox, &h->halo_send[0], &h->halo_send[1], &h->halo_recv[0], &h->halo_recv[1], &h->mig_send[0], &h->mig_send[1], &h->mig_recv[0], &h->mig_recv[1]};
   for (DevBuf* b : all) b->release();
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->ev_front) cudaEventDestroy(h->ev_front);
+  for (void* pm : h->peer_mailbox)
+    if (pm) cudaIpcCloseMemHandle(pm);
   if (h->comm) ncclCommDestroy(h->comm);
   if (h->h_counts) cudaFreeHost(h->h_counts);
   for (auto& e : h->ev)
@@ -780,6 +883,9 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
   CK(cudaEventRecord(h->ev_adv[0], h->stream));
+  if (h->p2p && (size_t)h->n + 2 * h->mb_mig_cap > h->cap) {  // room for two substeps of worst-case inflow; the loop itself never resizes
+    if (int rc = resize_particles(h, ((size_t)h->n + 2 * h->mb_mig_cap) * 5 / 4)) return rc;
+  }
   while (h->time < target_time) {
     if (cancel && *cancel) return fail(h, SVB_CANCELED, "The computation was canceled");
     if (int rc = substep(h, adaptive_time_steps != 0)) return rc;
@@ -788,6 +894,11 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   }
   CK(cudaEventRecord(h->ev_adv[1], h->stream));
   if (int rc = read_status(h)) return rc;
+  if (h->p2p) {  // the row count lived on the device during the loop
+    CK(cudaMemcpy(&h->n, h->n_dev, 4, cudaMemcpyDeviceToHost));
+    if (h->h_scalars->status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))
+      return fail(h, SVB_COMM_ERROR, h->h_scalars->status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
+  }
   CK(cudaEventElapsedTime(&h->last_advance_ms, h->ev_adv[0], h->ev_adv[1]));
   if (h->status) {
     if (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED) fail(h, 0, "Failed to compute the elastic energy of a particle (EnergyError::PositionGradientNonPositive)");
@@ -1132,6 +1243,62 @@ int migrate(SvbHandle* h) {
   return 0;
 }
 
+
+// Peer-memory mailboxes: every rank allocates one buffer, shares it with CUDA IPC (handles travel through an NCCL
+// all-gather), and maps every other rank's.  All ranks agree (all-reduce) on whether the mapping worked; if not,
+// the NCCL send/recv path above carries the exchanges.  SVB_SLAB_NCCL=1 forces that path.
+int setup_peer_mailboxes(SvbHandle* h) {
+  const char* force = std::getenv("SVB_SLAB_NCCL");
+  int ok = (force && force[0] == '1') || h->n_ranks > SLAB_MAX_RANKS ? 0 : 1;
+  cudaStream_t s = h->stream;
+  uint32_t* d = h->comm_counts.as<uint32_t>();
+  // capacities from the largest slab, so that every mailbox has the same layout
+  h->h_counts[0] = h->n;
+  CK(cudaMemcpyAsync(d, h->h_counts, 4, cudaMemcpyHostToDevice, s));
+  NCK(ncclAllReduce(d, d, 1, ncclUint32, ncclMax, h->comm, s));
+  CK(cudaMemcpyAsync(h->h_counts, d, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const size_t n_max = h->h_counts[0];
+  h->mb_halo_cap = n_max / 128 + 4096;
+  h->mb_mig_cap = n_max / 16 + 65536;
+  size_t off = 4096;  // header
+  for (int k = 0; k < 2; ++k) { h->mb_halo_off[k] = off; off += h->mb_halo_cap * sizeof(HaloEntry); }
+  for (int k = 0; k < 2; ++k) { h->mb_mig_off[k] = off; off += ((h->mb_mig_cap * MIG_WORDS * 4 + 255) & ~(size_t)255); }
+  CK(h->mailbox.ensure(off));
+  CK(cudaMemsetAsync(h->mailbox.p, 0, 4096, s));
+  DevBuf handles;
+  CK(handles.ensure((size_t)h->n_ranks * sizeof(cudaIpcMemHandle_t)));
+  cudaIpcMemHandle_t mine;
+  if (ok && cudaIpcGetMemHandle(&mine, h->mailbox.p) != cudaSuccess) { cudaGetLastError(); ok = 0; std::memset(&mine, 0, sizeof mine); }
+  CK(cudaMemcpyAsync(handles.as<unsigned char>() + (size_t)h->rank * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
+  NCK(ncclAllGather(handles.as<unsigned char>() + (size_t)h->rank * sizeof mine, handles.p, sizeof mine, ncclUint8, h->comm, s));
+  std::vector<cudaIpcMemHandle_t> all(h->n_ranks);
+  CK(cudaMemcpyAsync(all.data(), handles.p, all.size() * sizeof mine, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int r = 0; r < h->n_ranks && ok; ++r)
+    if (r != h->rank && cudaIpcOpenMemHandle(&h->peer_mailbox[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      h->peer_mailbox[r] = nullptr;
+      ok = 0;
+    }
+  // unanimous or not at all (this all-reduce also orders every rank's mailbox memset before the first message)
+  h->h_counts[0] = (uint32_t)ok;
+  CK(cudaMemcpyAsync(d, h->h_counts, 4, cudaMemcpyHostToDevice, s));
+  NCK(ncclAllReduce(d, d, 1, ncclUint32, ncclMin, h->comm, s));
+  CK(cudaMemcpyAsync(h->h_counts, d, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  handles.release();
+  h->p2p = h->h_counts[0] != 0;
+  if (!h->p2p) return 0;
+  h->p2p_local = d + 32;   // comm_counts holds 64 + 8 * n_ranks bytes... the scratch needs 12 words: see svb_comm_init
+  h->n_dev = d + 48;
+  CK(cudaMemsetAsync(h->p2p_local, 0, 16 * 4, s));
+  CK(cudaMemcpyAsync(h->n_dev, &h->n, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  h->slab_seq = 0;
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1155,7 +1322,7 @@ int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, 
   h->slab_lo = slab_lo_block_x;
   h->slab_hi = slab_hi_block_x;
   // every rank learns every slab: a particle may only travel into the adjacent slab within one substep
-  CK(h->comm_counts.ensure(64 + (size_t)n_ranks * 8));
+  CK(h->comm_counts.ensure(256 + 64 + (size_t)n_ranks * 8));   // words 0..15 counts, 16.. slab table (2 per rank, after word 64), 32..47 p2p scratch, 48 row count
   CK(cudaMallocHost(&h->h_counts, 64 + (size_t)n_ranks * 8));
   int32_t* d_all = reinterpret_cast<int32_t*>(h->comm_counts.as<uint32_t>() + 16);
   int32_t mine[2] = {slab_lo_block_x, slab_hi_block_x};
@@ -1187,7 +1354,7 @@ int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, 
   if (int rc = ensure_tile_capacity(h, h->tile_cap * 2 + 8192)) return rc;
   CK(cudaStreamSynchronize(h->stream));
   h->slabs = true;
-  return 0;
+  return setup_peer_mailboxes(h);
 }
 
 int32_t svb_set_original_indices(SvbHandle* h, const uint32_t* original_index, uint64_t n) {

@@ -88,7 +88,9 @@ struct TileTable {
 // ---- per-substep scalars that kernels read from HBM (so launches do not depend on host values)
 constexpr uint32_t ST_KEY_RANGE = 0x80000000u;   // a live particle lies outside the +-2^18-cell key range
 constexpr uint32_t ST_TILE_OVERFLOW = 0x40000000u;  // tile capacity exceeded: the host grows it and redoes the binning
-constexpr uint32_t ST_ABORT_MASK = ST_KEY_RANGE | ST_TILE_OVERFLOW;
+constexpr uint32_t ST_COMM_TIMEOUT = 0x20000000u;   // slab ranks: a neighbour's message did not arrive
+constexpr uint32_t ST_COMM_OVERFLOW = 0x10000000u;  // slab ranks: a mailbox or the particle buffer ran out of room
+constexpr uint32_t ST_ABORT_MASK = ST_KEY_RANGE | ST_TILE_OVERFLOW | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW;
 struct StepScalars {
   uint32_t n;          // resident particles (incl. tombstoned)
   uint32_t n_live;     // particles with a bin (not tombstoned)

@@ -326,7 +326,7 @@ struct BinArrays {
 // initialise this substep's scalars.  `prev` / `cur` are the two halves of a double buffer, so no thread
 // of this launch reads what another one writes.
 __global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ prev, StepScalars* __restrict__ cur, TileTable T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_touch,
-                                               unsigned long long* __restrict__ layer_slots, uint32_t n, int tables_fresh) {
+                                               unsigned long long* __restrict__ layer_slots, uint32_t n, const uint32_t* __restrict__ n_dev, int tables_fresh) {
   // tables_fresh: the host has just (re)allocated and memset the tables, tile_slot holds nothing to undo
   const uint32_t n_tiles = tables_fresh ? 0u : min(prev->n_tiles, T.tile_cap), n_ptiles = tables_fresh ? 0u : min(prev->n_ptiles, T.tile_cap);
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ p
     for (uint32_t q = gtid; q < LAYER_SLOTS; q += gsz) layer_slots[q] = 0ull;
   if (gtid == 0) {
     StepScalars z{};
-    z.n = n;
+    z.n = n_dev ? min(*n_dev, n) : n;   // slab ranks: the row count lives on the device (migration changes it without the host)
     z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
     z.sticky = prev->sticky;
     *cur = z;
@@ -350,6 +350,7 @@ template <bool HAS_MESH, bool APPLY_FORCE>
 __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, GoalDev G, TileTable T, BinArrays B, uint32_t n, float dt, float gx, float gy,
                                              float gz, float factor_b) {
   if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is (every later kernel no-ops too)
+  n = min(n, S->n);       // the launch covers an upper bound of the row count
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31;
   bool live = false, tomb = false, gone = false;
@@ -523,7 +524,7 @@ __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S
     return;
   }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= min(n, S->n)) return;
   const uint32_t ci = pcell[i];
   uint32_t j;
   if (ci >= 0xfffffffdu) {
@@ -1031,6 +1032,109 @@ __global__ void __launch_bounds__(256) k_unpack_add(StepScalars* S, TileTable T,
     }
   }
 }
+// ---- the same exchanges over peer memory (NVLink loads/stores into the neighbour's HBM, no NCCL call and no
+// host round trip on the data path).  Every rank owns a mailbox that its neighbours map with CUDA IPC:
+//   header | halo entries from the left | from the right | migrating rows from the left | from the right
+// A sender writes its payload straight into the neighbour's mailbox; the last block of the sending kernel
+// publishes the count and then the substep sequence number with system-scope fences.  The receiving kernel
+// spins (bounded) on the sequence number in its own HBM.  Buffers are reused safely because a rank can only
+// send message k+1 after it has consumed the neighbour's message k of the other kind.
+constexpr int SLAB_MAX_RANKS = 16;
+constexpr uint32_t SLAB_OVERFLOW = 0x80000000u;   // count word: the sender ran out of mailbox capacity
+struct SlabHeader {
+  uint32_t halo_seq[2], halo_count[2];   // [0] written by the left neighbour, [1] by the right one
+  uint32_t mig_seq[2], mig_count[2];
+  uint32_t err_seq[SLAB_MAX_RANKS], err_val[SLAB_MAX_RANKS];  // every rank posts its sticky error word to every rank
+};
+__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// true when *p reached `seq`; gives up after ~2 s so a lost neighbour cannot hang the GPU
+__device__ __forceinline__ bool wait_seq(const uint32_t* p, uint32_t seq) {
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    if ((int32_t)(ld_sys(p) - seq) >= 0) return true;
+    __nanosleep(spin < 64 ? 32 : 400);
+  }
+  return false;
+}
+
+// halo, sending side: like k_pack_column, but the entries go straight into the neighbour's mailbox
+__global__ void __launch_bounds__(256) k_halo_send(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid, int column,
+                                                   HaloEntry* __restrict__ peer_entries, uint32_t* peer_count, uint32_t* peer_seq, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local /*[0] slots, [1] blocks done*/) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  if (!SVB_ABORTED(S)) {
+    const uint32_t n_tiles = min(S->n_tiles, T.tile_cap);
+    for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps) {
+      const unsigned long long k = T.tile_key[t];
+      int bx, by, bz;
+      uint32_t layer;
+      tile_key_unpack(k, bx, by, bz, layer);
+      if (bx != column) continue;
+      uint32_t slot = 0;
+      if (lane == 0) slot = atomicAdd(&local[0], 1u);
+      slot = __shfl_sync(SVB_FULL, slot, 0);
+      if (slot >= cap) continue;
+      HaloEntry* e = peer_entries + slot;
+      if (lane == 0) {
+        e->block_key = k & ~(unsigned long long)((1u << LAYER_BITS) - 1u);
+        e->bits = layer_bits_of(layer_slots, layer);
+        e->pad = 0;
+      }
+      e->node[lane] = grid[(size_t)t * 64 + lane];
+      e->node[lane + 32] = grid[(size_t)t * 64 + lane + 32];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&local[1], 1u) == gridDim.x - 1) {
+    const uint32_t c = atomicAdd(&local[0], 0u);
+    st_sys(peer_count, c > cap ? (cap | SLAB_OVERFLOW) : c);
+    st_sys(peer_seq, seq);
+    local[0] = 0; local[1] = 0;
+  }
+}
+// halo, receiving side: wait for the neighbour's message in this rank's mailbox, then add (or create) the tiles
+__global__ void __launch_bounds__(256) k_halo_recv(StepScalars* S, TileTable T, unsigned long long* layer_slots, uint32_t* layer_list, float4* __restrict__ grid,
+                                                   const HaloEntry* __restrict__ in, const uint32_t* count_ptr, const uint32_t* seq_ptr, uint32_t seq) {
+  __shared__ uint32_t s_count;
+  if (threadIdx.x == 0) {
+    uint32_t c = 0;
+    if (wait_seq(seq_ptr, seq)) {
+      c = ld_sys(count_ptr);
+      if (c & SLAB_OVERFLOW) { atomicOr(&S->status, ST_COMM_OVERFLOW); c = 0; }
+    } else atomicOr(&S->status, ST_COMM_TIMEOUT);   // in the abort mask: the rest of the substep no-ops
+    s_count = c;
+  }
+  __syncthreads();
+  const uint32_t count = s_count;
+  if (SVB_ABORTED(S)) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t zeroed = S->n_tiles_zeroed;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < count; q += warps) {
+    const HaloEntry* e = in + q;
+    uint32_t id = TILE_PENDING;
+    if (lane == 0) {
+      const uint32_t layer = layer_find_or_insert(layer_slots, layer_list, e->bits, S);
+      id = tile_find_or_insert(T, e->block_key | layer, S);
+    }
+    id = __shfl_sync(SVB_FULL, id, 0);
+    if (id == TILE_PENDING) continue;
+    float4* dst = grid + (size_t)id * 64;
+    if (id >= zeroed) {  // created by this message: the tile was never zeroed, so store instead of add
+      dst[lane] = e->node[lane];
+      dst[lane + 32] = e->node[lane + 32];
+    } else {
+      red_add_v4(dst + lane, e->node[lane]);
+      red_add_v4(dst + lane + 32, e->node[lane + 32]);
+    }
+  }
+}
+
 constexpr int MIG_WORDS = NFIELDS + 1;  // the 34 state words + the elastic energy
 __global__ void __launch_bounds__(256) k_migrate_pack(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, float h, int lo, int hi, int reach_lo, int reach_hi,
                                                       uint32_t* __restrict__ out_left, uint32_t* __restrict__ out_right, uint32_t* __restrict__ counts, uint32_t cap, uint32_t n) {
@@ -1059,6 +1163,94 @@ __global__ void __launch_bounds__(256) k_migrate_unpack(ParticleBuf P, float* __
 #pragma unroll
   for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
   energy[i] = __uint_as_float(row[NFIELDS]);
+}
+// migration over peer memory.  Sending side: rows that left [lo, hi) go straight into the neighbour's mailbox;
+// the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
+struct SlabPeers {
+  uint32_t* rows[2];                     // neighbour mailbox: migrating rows (left / right neighbour), null at the domain ends
+  uint32_t* count[2]; uint32_t* seq[2];
+  uint32_t* err_seq[SLAB_MAX_RANKS]; uint32_t* err_val[SLAB_MAX_RANKS];   // slot `rank` of every rank's header (null for self)
+  int n_ranks;
+};
+__global__ void __launch_bounds__(256) k_migrate_send(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, float h, int lo, int hi, int reach_lo, int reach_hi, SlabPeers peers,
+                                                      uint32_t cap, uint32_t seq, uint32_t* __restrict__ local /*[0],[1] slots, [2] blocks done*/) {
+  const uint32_t n = S->n_live + S->n_tomb;   // rows after this substep's re-bin
+  if (!SVB_ABORTED(S)) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+      const uint32_t flags = P.u(PFLAGS)[i];
+      if (flags & (F_TOMBSTONED | F_GONE)) continue;
+      const int bx = floor_div4(base_node(P.f(PX)[i], h));
+      if (bx >= lo && bx < hi) continue;
+      if (bx < reach_lo || bx >= reach_hi) { atomicOr(&S->status, ST_KEY_RANGE); continue; }  // crossed more than one slab in a substep
+      const int side = bx < lo ? 0 : 1;
+      const uint32_t slot = atomicAdd(&local[side], 1u);
+      P.u(PFLAGS)[i] = flags | F_GONE;
+      if (slot >= cap || !peers.rows[side]) continue;
+      uint32_t* row = peers.rows[side] + (size_t)slot * MIG_WORDS;
+#pragma unroll
+      for (int f = 0; f < NFIELDS; ++f) row[f] = P.base[(size_t)f * P.cap + i];
+      row[PFLAGS] = flags;  // the row travels without the local F_GONE mark
+      row[NFIELDS] = __float_as_uint(energy[i]);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&local[2], 1u) == gridDim.x - 1) {
+    for (int side = 0; side < 2; ++side) {
+      const uint32_t c = atomicAdd(&local[side], 0u);
+      if (peers.count[side]) {
+        st_sys(peers.count[side], c > cap ? (cap | SLAB_OVERFLOW) : c);
+        st_sys(peers.seq[side], seq);
+      }
+      local[side] = 0;
+    }
+    const uint32_t err = atomicOr(&S->sticky, 0u);
+    for (int r = 0; r < peers.n_ranks; ++r)
+      if (peers.err_val[r]) { st_sys(peers.err_val[r], err); st_sys(peers.err_seq[r], seq); }
+    local[2] = 0;
+  }
+}
+// receiving side: append the neighbours' rows behind this rank's rows, publish the new row count on the device,
+// and fold every rank's error word into this rank's (a FAILED particle anywhere stops every rank after this substep)
+__global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __restrict__ energy, StepScalars* S, const SlabHeader* __restrict__ hdr, const uint32_t* __restrict__ rows_left,
+                                                      const uint32_t* __restrict__ rows_right, int has_left, int has_right, int rank, int n_ranks, uint32_t seq, uint32_t* __restrict__ n_dev) {
+  __shared__ uint32_t s_c[2];
+  if (threadIdx.x == 0) {
+    uint32_t c[2] = {0, 0};
+    const int has[2] = {has_left, has_right};
+    for (int side = 0; side < 2; ++side)
+      if (has[side]) {
+        if (wait_seq(&hdr->mig_seq[side], seq)) {
+          c[side] = ld_sys(&hdr->mig_count[side]);
+          if (c[side] & SLAB_OVERFLOW) { atomicOr(&S->status, ST_COMM_OVERFLOW); c[side] &= ~SLAB_OVERFLOW; }
+        } else atomicOr(&S->status, ST_COMM_TIMEOUT);
+      }
+    s_c[0] = c[0]; s_c[1] = c[1];
+    if (blockIdx.x == 0) {
+      uint32_t err = 0;
+      for (int r = 0; r < n_ranks; ++r)
+        if (r != rank) {
+          if (wait_seq(&hdr->err_seq[r], seq)) err |= ld_sys(&hdr->err_val[r]);
+          else atomicOr(&S->status, ST_COMM_TIMEOUT);
+        }
+      if (err) atomicOr(&S->sticky, err);
+    }
+  }
+  __syncthreads();
+  const uint32_t cl = s_c[0], cr = s_c[1];
+  const uint32_t base = S->n_live + S->n_tomb;
+  const uint32_t room = (uint32_t)P.cap > base ? (uint32_t)P.cap - base : 0u;
+  if (cl + cr > room) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_OVERFLOW); }
+  const uint32_t total = min(cl + cr, room);
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+    const uint32_t* row = q < cl ? rows_left + (size_t)q * MIG_WORDS : rows_right + (size_t)(q - cl) * MIG_WORDS;
+    const uint32_t i = base + q;
+#pragma unroll
+    for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
+    energy[i] = __uint_as_float(row[NFIELDS]);
+  }
+  // a substep that was a no-op on every rank (an earlier substep failed: k_bin returned at once) keeps the row count
+  if (blockIdx.x == 0 && threadIdx.x == 0 && S->bin_blocks_done != 0) *n_dev = base + total;
 }
 __global__ void k_add_u32(uint32_t* a, uint32_t n, uint32_t add) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
