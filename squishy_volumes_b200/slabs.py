@@ -121,22 +121,42 @@ class SlabState:
             raise FatalError(rc, L.svb_last_error(inner._h).decode())
         return cls(inner, plan, rank, world, io_state.particles.n)
 
+    def upload(self, local: IoState, idx: np.ndarray) -> None:
+        """Replace this rank's rows by `local` (rows `idx` of the global particle order, e.g. from `split_state`
+        with this state's plan); communicator, mailboxes and allocations are kept.  Collective: every rank calls it."""
+        from . import abi
+        L = abi.load()
+        n_global = self.n_global
+        self.inner.upload(local)
+        self.inner.n = n_global
+        idx32 = np.ascontiguousarray(idx, dtype=np.uint32)
+        if idx32.size:
+            rc = L.svb_set_original_indices(self.inner._h, cs.uptr(idx32), idx32.size)
+            if rc != 0:
+                raise FatalError(rc, L.svb_last_error(self.inner._h).decode())
+
     def advance(self, harness, frame_input: FrameInput, params: RunParameters) -> Optional[SimulationError]:
         return self.inner.advance(harness, frame_input, params)
 
-    def resident(self) -> Tuple[np.ndarray, Particles]:
-        """(global original indices, rows) of the particles currently on this rank."""
+    def resident(self, out: Optional[Particles] = None) -> Tuple[np.ndarray, Particles]:
+        """(global original indices, rows) of the particles currently on this rank.  `out` (optional) are
+        caller-owned result arrays (e.g. page-locked, reused across frames) with room for every resident row;
+        the returned rows are then views into them."""
         from . import abi
         L = abi.load()
         cap = int(L.svb_particle_count(self.inner._h))
-        out = Particles.empty(max(cap, 1))
+        if out is None:
+            out = Particles.empty(max(cap, 1))
+        elif out.n < cap:
+            raise ValueError(f"resident(): out holds {out.n} rows, {cap} are resident")
         s = cs.particles_struct(out)
         orig = np.zeros(max(cap, 1), dtype=np.uint64)
         rc = L.svb_download_resident(self.inner._h, C.byref(s), orig.ctypes.data_as(C.POINTER(C.c_uint64)))
         if rc != 0:
             raise FatalError(rc, L.svb_last_error(self.inner._h).decode())
         m = int(s.n)
-        return orig[:m].astype(np.int64), out.select(np.arange(m))
+        rows = Particles(**{f.name: getattr(out, f.name)[:m] for f in dataclasses.fields(Particles)})
+        return orig[:m].astype(np.int64), rows
 
     @property
     def time(self) -> float:

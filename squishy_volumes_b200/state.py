@@ -67,6 +67,18 @@ class B200State:
             raise FatalError(rc, L.svb_last_error(h).decode())
         return self
 
+    def upload(self, io_state: IoState) -> None:
+        """`from_io_state` into this (session-lived) handle: H2D of a new state, clock and step history restart;
+        constants, colliders and device allocations are kept (include/svb200.h: svb_upload)."""
+        L = abi.load()
+        p = io_state.particles.normalized()
+        ps = cs.particles_struct(p)
+        rc = L.svb_upload(self._h, C.byref(ps), C.c_double(io_state.time))
+        if rc != 0:
+            raise FatalError(rc, L.svb_last_error(self._h).decode())
+        self.n = p.n
+        self._loaded = None   # keyframe particle arrays are sized by the particle count
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             abi.load().svb_destroy(self._h)

@@ -209,6 +209,38 @@ def test_snapshot_restore_is_deterministic_in_integers():
     assert np.allclose(a.particles.positions, b.particles.positions, atol=1e-6)   # float atomics may reorder sums
 
 
+def test_upload_restarts_a_session_handle():
+    """svb_upload = from_io_state into an existing handle: a different state (other particle count, other buffer
+    parity) goes in, the clock and the error words restart, and the run equals the one of a fresh handle / the oracle."""
+    first = scenes.elastic_cube(side=10, h=0.1)
+    scene = scenes.elastic_cube(side=14, h=0.1)       # more particles than the first state; same collider topology (ground plane)
+    g = B200State().from_io_state(first.io_state, first.frame_input)
+    g.produce_next_state(None, first.frame_input, RunParameters(2.5e-3, 1e-3))    # odd substep count: the live buffer is the second one
+    g.upload(scene.io_state)
+    assert g.substeps == 0 and g.time == scene.io_state.time
+    params = RunParameters(4.5e-3, 1e-3)
+    got, err = g.produce_next_state(None, scene.frame_input, params)
+    assert err is None and g.substeps == 5
+    fresh = B200State().from_io_state(scene.io_state, scene.frame_input)
+    want, _ = fresh.produce_next_state(None, scene.frame_input, params)
+    assert np.array_equal(got.particles.flags, want.particles.flags)
+    assert np.array_equal(got.particles.collider_bits, want.particles.collider_bits)
+    parity.compare_states(got, want, rtol=parity.RTOL_STEP, h=h_of(scene))
+    import oracle.oracle as orc
+    ro, _ = orc.OracleState.from_io_state(scene.io_state, scene.frame_input).produce_next_state(None, scene.frame_input, params)
+    parity.compare_states(got, ro, rtol=parity.RTOL_RUN, h=h_of(scene))
+    # a failed run does not poison the next upload
+    bad = scenes.elastic_cube(side=8, h=0.1)
+    bad.io_state.particles.position_gradients[0] = -np.eye(3, dtype=np.float32)
+    g.upload(bad.io_state)
+    _, err = g.produce_next_state(None, bad.frame_input, RunParameters(1.5e-3, 1e-3))
+    assert err is not None and err.status & 8
+    g.upload(scene.io_state)
+    again, err2 = g.produce_next_state(None, scene.frame_input, params)
+    assert err2 is None
+    parity.compare_states(again, want, rtol=parity.RTOL_STEP, h=h_of(scene))
+
+
 def test_million_particle_properties():
     """BASELINE configs[1] at full size (1.02 M particles): size-independent properties instead of the oracle —
     sort_map is a permutation, the resident order is sorted by bin key, mass is conserved on the grid,
