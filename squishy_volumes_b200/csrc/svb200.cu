@@ -192,7 +192,7 @@ int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
   CK(h->tile_slot.ensure(c * 4));
   CK(h->tile_touch.ensure(c * 4));
   CK(h->cell_count.ensure(c * 64 * 4));
-  CK(h->tile_start.ensure((c + 1) * 4));
+  CK(h->tile_start.ensure((c + 1) * 8));
   CK(h->nbr.ensure(c * 8 * 4));
   CK(h->grid.ensure(c * 64 * 16));
   CK(h->node_mask.ensure(c * 8));
@@ -258,9 +258,7 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   stage_end(h);
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
-  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
-  LAUNCH_CHECK();
-  k_scan_tiles<<<1, 1024, 0, s>>>(h->tile_start.as<uint32_t>(), &S->n_ptiles, 0, &S->n_live);
+  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->cell_count.as<uint32_t>(), h->tile_start.as<uint2>(), h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(h->ev_front, s));
@@ -275,12 +273,12 @@ int enqueue_rebin(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   stage_begin(h, ST_PERMUTE);
   const uint32_t invert_blocks = blocks_for(n, 256);
-  k_invert_zero<<<invert_blocks + 148 * 2, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->src_of.as<uint32_t>(), n, invert_blocks,
+  k_invert_zero<<<invert_blocks + 148 * 2, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint2>(), h->src_of.as<uint32_t>(), n, invert_blocks,
                                                         h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
   LAUNCH_CHECK();
   h->masks_valid = false;
   if (h->store_grid) {
-    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
+    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint2>(), h->nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
     LAUNCH_CHECK();
     h->masks_valid = true;
   }
@@ -330,7 +328,7 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
   }
   const ParticleBuf P = h->Pc(), D = h->P(h->cur ^ 1);
   const uint32_t* src_of = h->src_of.as<uint32_t>();
-  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint2* tile_start = h->tile_start.as<uint2>();
   float* en = h->energy.as<float>();
   const int* nb = h->nbr.as<int>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
@@ -395,9 +393,9 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   //    them in the pre-bin order is equivalent to the reference's Sort -> Collide -> Force.
   if (int rc = enqueue_front(h, in, /*apply_force=*/true, h->adaptive.allowed())) return rc;
   const TileTable T = tile_table(h);
-  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint2* tile_start = h->tile_start.as<uint2>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
   const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
 
   if (!adaptive_steps) {
@@ -417,7 +415,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     if (rc == 1) {  // the binning was redone with a larger tile capacity: queue the back half again
       const TileTable T2 = tile_table(h);
       if (int rc2 = enqueue_rebin(h)) return rc2;
-      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint32_t>(), h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
+      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint2>(), h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
       LAUNCH_CHECK();
       if (int rc2 = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc2;
     }
@@ -435,7 +433,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   }
   if (int rc = enqueue_rebin(h)) return rc;
   const TileTable T2 = tile_table(h);
-  tile_start = h->tile_start.as<uint32_t>();
+  tile_start = h->tile_start.as<uint2>();
   // -- LimitTimeStepBeforeForce (limit_time_step.rs:25-33)
   stage_begin(h, ST_LIMIT);
   k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), cur_scalars(h), hh, n);
@@ -511,9 +509,9 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   const uint32_t n_after = h->h_scalars->n_live + h->h_scalars->n_tomb;  // rows of migrated particles are dropped by the re-bin
   if (int rc = enqueue_rebin(h)) return rc;
   const TileTable T = tile_table(h);
-  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint2* tile_start = h->tile_start.as<uint2>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
   const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
   stage_begin(h, ST_P2G);
   k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
@@ -552,9 +550,9 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   if (int rc = enqueue_rebin(h)) return rc;
   StepScalars* S = cur_scalars(h);
   const TileTable T = tile_table(h);
-  const uint32_t* tile_start = h->tile_start.as<uint32_t>();
+  const uint2* tile_start = h->tile_start.as<uint2>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 6));
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
   stage_begin(h, ST_P2G);
   k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
   LAUNCH_CHECK();

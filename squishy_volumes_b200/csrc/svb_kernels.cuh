@@ -429,10 +429,10 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   }
 }
 
-// per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile total,
-// and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
+// per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile's slot range
+// [first, end) in the binned order (S->n_live ends up as the number of binned particles), and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
 // (update_grid_nodes.rs:102-108)
-__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_total, const uint32_t* __restrict__ tile_touch,
+__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, const uint32_t* __restrict__ tile_touch,
                                                  int* __restrict__ nbr) {
   if (SVB_ABORTED(S)) return;
   const uint32_t lane = threadIdx.x & 31;
@@ -456,7 +456,12 @@ __global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, ui
     }
     const uint32_t ex = inc - mine;
     *reinterpret_cast<uint2*>(cell_count + (size_t)t * 64 + 2 * lane) = make_uint2(ex, ex + c.x);
-    if (lane == 31) tile_total[t] = inc;
+    // the tile's run in the binned order: claimed from a cursor, so the runs are dense but in no particular tile order
+    // (any order is a valid binning; this replaces a single-CTA scan over the tile totals and its launch)
+    if (lane == 31) {
+      const uint32_t first = atomicAdd(&S->n_live, inc);
+      tile_range[t] = make_uint2(first, first + inc);
+    }
     if (lane < 8) nbr[(size_t)t * 8 + lane] = r;
   }
 }
@@ -503,14 +508,14 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* a, const uint32_t
 }
 
 // re-bin (sort.rs:91-101).  Slot of particle i in the binned order:
-//   j = tile_start[tile] + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
+//   j = tile_range[tile].x + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
 // Only the inverse map src_of[j] = i is materialised here (4 B per particle).  P2G gathers its inputs
 // through it and G2P writes its results — and the fields it merely carries — to slot j of the other
 // buffer, so the physical permutation of the 136-byte state costs no pass of its own: consecutive
 // slots come from (nearly) consecutive rows of the previous order, the gathers stay coalesced.
 // The same launch also clears the grid tiles of this substep (blocks beyond the particle range).
 __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank, const uint32_t* __restrict__ cell_offset,
-                                                     const uint32_t* __restrict__ tile_start, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
+                                                     const uint2* __restrict__ tile_range, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
                                                      unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
   if (SVB_ABORTED(S)) return;
   if (blockIdx.x >= invert_blocks) {
@@ -530,22 +535,25 @@ __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S
   if (ci >= 0xfffffffdu) {
     if (ci != 0xffffffffu) return;  // migrated away (or unbinned after an abort): no slot
     j = S->n_live + prank[i];
-  } else j = tile_start[ci >> 6] + cell_offset[ci] + prank[i];
+  } else j = tile_range[ci >> 6].x + cell_offset[ci] + prank[i];
   src_of[j] = i;
 }
 // ------------------------------------------------------------------------------------------------
 // P2G (scatter_momentum.rs:22-93).  One CTA per (block, layer) run of particles, claimed from a
 // work counter.  Each warp takes 32 consecutive particles: every lane evaluates ITS particle once
-// (weights, affine momentum matrix A = m C - s V0 P F^T - s J V0 sigma, so the stress is computed
-// once per particle, not 27 times) and parks the 32 numbers a node needs in shared memory; then the
-// warp walks the 32 particles together with lane = one of the 27 stencil nodes, accumulating in
-// registers while consecutive particles share a cell (they do: the run is sorted by cell) — the
-// warp-aggregated form of the scatter.  A cell change flushes 27 float4 into the warp's private
-// 6x6x6 tile (plain read-modify-write, no shared atomics: fp32 shared atomics are CAS loops).  (A variant
-// with lane = z-column of the stencil and three particles per warp iteration was measured slower: its
-// serialised flushes cost more than the 27-lane walk's 23.5 instructions per particle.)  At
-// the end the warps' tiles are summed and every non-zero tile node goes to HBM with one
-// red.global.add.v4.f32.
+// (affine momentum matrix A = m C - s V0 P F^T - s J V0 sigma, so the stress is computed once per
+// particle, not 27 times) and parks 16 numbers in shared memory: the fractional position x/h - base,
+// the mass, m v and A.  Then the warp walks the 32 particles together with lane = one of the 27 stencil
+// nodes: four warp-uniform LDS.128 per particle, the lane's own weight and offset derived in registers
+// (packed fp32), accumulating in registers while consecutive particles share a cell (they do: the run is
+// sorted by cell) — the warp-aggregated form of the scatter.  A cell change flushes 27 float4 into the
+// warp's private 6x6x6 tile (plain read-modify-write, no shared atomics: fp32 shared atomics are CAS
+// loops).  The walk is bound by shared-memory bandwidth; measured on B200 (scratch/lds_bench.cu) a
+// warp-uniform LDS.128 costs 2.2 cycles, a 3-address LDS.64 2 cycles and a 3-address LDS.128 4 cycles,
+// which is why the earlier layout (per-axis (w, d) pairs + 13 uniform floats = 13.6 cycles per particle)
+// lost to this one (8.8 cycles): 95 -> 80 us at 1 M particles.  (Also measured slower: lane = z-column of
+// the stencil with three interleaved particles per warp iteration — serialised flushes.)  At the end the
+// warps' tiles are summed and every non-zero tile node goes to HBM with one red.global.add.v4.f32.
 // Stencil weights from the base node: `shifted` = x/h - base in [1/2, 3/2).  Branch-free forms of
 // kernel_quadratic(shifted - a), a = 0,1,2 (cpu/src/kernels.rs:17-26 evaluated on the branch each a falls in;
 // both branches agree at the hand-over points).
@@ -555,9 +563,13 @@ __device__ __forceinline__ void quad_weights(float shifted, float* w) {
   w[1] = 0.75f - a1 * a1;
   w[2] = 0.5f * a2 * a2;
 }
+#ifndef SVB_P2G_CTAS_PER_SM
+#define SVB_P2G_CTAS_PER_SM 7   // 71 registers, 24 KB of shared memory per CTA; measured: 6 -> 81 us, 7 -> 79 us, 8 (spills) -> 88 us at 1 M
+#endif
 constexpr int P2G_WARPS = 4;
+constexpr int P2G_CTAS_PER_SM = SVB_P2G_CTAS_PER_SM;
 constexpr int TILE_NODES = 216;
-constexpr int STAGE_STRIDE = 36;  // floats per staged particle: 16-byte aligned rows, conflict-free float4 stores
+constexpr int STAGE_STRIDE = 20;  // floats per staged particle (16 used + the cell id): 16-byte aligned rows, conflict-free float4 stores
 constexpr int P2G_SMEM = P2G_WARPS * TILE_NODES * 16 + P2G_WARPS * 32 * STAGE_STRIDE * 4;
 
 // Blackwell packed fp32: one FFMA2 / FADD2 issue slot does two lanes of work (SASS `FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO`
@@ -575,6 +587,17 @@ __device__ __forceinline__ float2 fmul2(float2 a, float s) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
   return *reinterpret_cast<float2*>(&d);
 }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   unsigned long long d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
@@ -584,7 +607,7 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint2* __restrict__ group_range, const int* __restrict__ nbr,
                                                            StepScalars* S, float4* __restrict__ grid, float h, float dt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
@@ -599,11 +622,18 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
   const int li = node_lane ? lane / 9 : 0, lj = node_lane ? (lane / 3) % 3 : 0, lk = node_lane ? lane % 3 : 0;
-  // staged row (floats): [0..17] (w,d) pairs x0 x1 x2 y0 y1 y2 z0 z1 z2 | 18 cell | 20..23 m*v, mass | 24..35 the columns of A, each padded
-  // with a zero: (column, 0) pairs up with (m*v, mass) so that the whole node update is packed-fp32 work
-  const float* lane_x = stage + 2 * li;
-  const float* lane_y = stage + 6 + 2 * lj;
-  const float* lane_z = stage + 12 + 2 * lk;
+  // staged row (floats): 0..3 shifted x/h - base (3), mass | 4..7 m*v.x, m*v.y, A0, A1 | 8..11 A3, A4, A6, A7 | 12..15 m*v.z, A2, A5, A8 | 16 cell
+  // Every walk load is a warp-uniform LDS.128 (2.2 cycles of shared-memory bandwidth per 16 bytes, measured; a 3-address
+  // LDS.64 costs 2 cycles per 8 bytes): the walk is bound by shared-memory bandwidth, so each lane derives the weight and the
+  // offset of ITS node from the particle's fractional position instead of loading staged per-axis (w, d) pairs.
+  //   kernel_quadratic on the branch node a falls in (cpu/src/kernels.rs:17-26): w_a(t) = g_a (t - c_a)^2 + e_a,  t in [1/2, 3/2)
+  //   a = 0: 1/2 (t - 3/2)^2      a = 1: 3/4 - (t - 1)^2      a = 2: 1/2 (t - 1/2)^2          offset d_a = (a - t) h
+  const float2 kc_xy = make_float2(-(1.5f - 0.5f * (float)li), -(1.5f - 0.5f * (float)lj));
+  const float2 kg_xy = make_float2(li == 1 ? -1.f : 0.5f, lj == 1 ? -1.f : 0.5f);
+  const float2 ke_xy = make_float2(li == 1 ? 0.75f : 0.f, lj == 1 ? 0.75f : 0.f);
+  const float2 ka_xy = make_float2((float)li * h, (float)lj * h);
+  const float kc_z = -(1.5f - 0.5f * (float)lk), kg_z = lk == 1 ? -1.f : 0.5f, ke_z = lk == 1 ? 0.75f : 0.f, ka_z = (float)lk * h;
+  const float2 neg_h2 = make_float2(-h, -h);
   const int lane_tile_off = (li * 6 + lj) * 6 + lk;
 
   for (;;) {
@@ -612,14 +642,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
     __syncthreads();
     const uint32_t g = s_group;
     if (g >= n_groups) break;
-    const uint32_t start = group_start[g];
-    const uint32_t end = group_start[g + 1];
+    const uint2 range = group_range[g];
+    const uint32_t start = range.x, end = range.y;
     for (int q = threadIdx.x; q < P2G_WARPS * TILE_NODES; q += blockDim.x) tiles[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     for (uint32_t chunk = start + warp * 32; chunk < end; chunk += P2G_WARPS * 32) {
       // ---- per-particle evaluation by the owning lane
-      float4 st[9];
+      float4 st[4];
       int cell = -1;
       if (chunk + lane < end) {
         const uint32_t i = src_of[chunk + lane];  // row of this particle in the pre-bin order
@@ -627,18 +657,6 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
         const float n0 = __fdiv_rn(x0, h), n1 = __fdiv_rn(x1, h), n2 = __fdiv_rn(x2, h);
         const int s0 = (int)floorf(__fsub_rn(n0, 0.5f)), s1 = (int)floorf(__fsub_rn(n1, 0.5f)), s2 = (int)floorf(__fsub_rn(n2, 0.5f));
         cell = ((s0 & 3) << 4) | ((s1 & 3) << 2) | (s2 & 3);
-        float w[9], d[9];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const float dn0 = (float)(s0 + a) - n0, dn1 = (float)(s1 + a) - n1, dn2 = (float)(s2 + a) - n2;
-          d[a] = dn0 * h; d[3 + a] = dn1 * h; d[6 + a] = dn2 * h;
-          // kernel_quadratic(dn) on the branch stencil node a falls in: |dn| in [1/2, 3/2] for a = 0, 2 and <= 1/2 for a = 1
-          if (a == 1) { w[1] = 0.75f - dn0 * dn0; w[4] = 0.75f - dn1 * dn1; w[7] = 0.75f - dn2 * dn2; }
-          else {
-            const float e0 = fmaxf(1.5f - fabsf(dn0), 0.f), e1 = fmaxf(1.5f - fabsf(dn1), 0.f), e2 = fmaxf(1.5f - fabsf(dn2), 0.f);
-            w[a] = 0.5f * e0 * e0; w[3 + a] = 0.5f * e1 * e1; w[6 + a] = 0.5f * e2 * e2;
-          }
-        }
         M3 C, F;
 #pragma unroll
         for (int q = 0; q < 9; ++q) { C.m[q] = P.f(PC + q)[i]; F.m[q] = P.f(PF + q)[i]; }
@@ -657,18 +675,13 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
           for (int q = 0; q < 9; ++q) A.m[q] -= sj * cauchy.m[q];
         }
         const float mv0 = mass * P.f(PV)[i], mv1 = mass * P.f(PV + 1)[i], mv2 = mass * P.f(PV + 2)[i];
-        st[0] = make_float4(w[0], d[0], w[1], d[1]);
-        st[1] = make_float4(w[2], d[2], w[3], d[3]);
-        st[2] = make_float4(w[4], d[4], w[5], d[5]);
-        st[3] = make_float4(w[6], d[6], w[7], d[7]);
-        st[4] = make_float4(w[8], d[8], __int_as_float(cell), 0.f);
-        st[5] = make_float4(mv0, mv1, mv2, mass);
-        st[6] = make_float4(A.m[0], A.m[1], A.m[2], 0.f);
-        st[7] = make_float4(A.m[3], A.m[4], A.m[5], 0.f);
-        st[8] = make_float4(A.m[6], A.m[7], A.m[8], 0.f);
+        st[0] = make_float4(n0 - (float)s0, n1 - (float)s1, n2 - (float)s2, mass);
+        st[1] = make_float4(mv0, mv1, A.m[0], A.m[1]);
+        st[2] = make_float4(A.m[3], A.m[4], A.m[6], A.m[7]);
+        st[3] = make_float4(mv2, A.m[2], A.m[5], A.m[8]);
       } else {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) st[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 4; ++q) st[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       // runs of equal cells inside this chunk (the run is sorted by cell): heads as a warp-uniform mask
       const int prev_cell = __shfl_up_sync(SVB_FULL, cell, 1);
@@ -677,7 +690,8 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
       __syncwarp();
       float4* row = reinterpret_cast<float4*>(stage + lane * STAGE_STRIDE);
 #pragma unroll
-      for (int q = 0; q < 9; ++q) row[q] = st[q];
+      for (int q = 0; q < 4; ++q) row[q] = st[q];
+      stage[lane * STAGE_STRIDE + 16] = __int_as_float(cell);
       __syncwarp();
 
       // ---- cooperative walk: lane = stencil node, one register accumulator per run of equal cells
@@ -686,35 +700,34 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, 6) k_p2g(ParticleBuf P, const 
         const int first = __ffs(heads) - 1;
         heads &= heads - 1;
         const int last = heads ? __ffs(heads) - 1 : count;
-        float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);   // (px, py), (pz, mass)
-        const int off = first * STAGE_STRIDE;
-        const float* px = lane_x + off;
-        const float* py = lane_y + off;
-        const float* pz = lane_z + off;
-        const float* sp = stage + off;
+        float2 acc_xy = make_float2(0.f, 0.f);
+        float acc_z = 0.f, acc_m = 0.f;
+        const float4* sp = reinterpret_cast<const float4*>(stage + first * STAGE_STRIDE);
 #pragma unroll 4
         for (int p = first; p < last; ++p) {
-          const float2 wx = *reinterpret_cast<const float2*>(px);
-          const float2 wy = *reinterpret_cast<const float2*>(py);
-          const float2 wz = *reinterpret_cast<const float2*>(pz);
-          const float4 mv = *reinterpret_cast<const float4*>(sp + 20);   // m*v, mass
-          const float4 c0 = *reinterpret_cast<const float4*>(sp + 24);   // A column 0, 0
-          const float4 c1 = *reinterpret_cast<const float4*>(sp + 28);
-          const float4 c2 = *reinterpret_cast<const float4*>(sp + 32);
-          const float wgt = wx.x * wy.x * wz.x;
-          // (m*v + A delta, mass): the zero in every column's fourth slot carries the mass through
-          const float2 ma = ffma2(make_float2(c2.x, c2.y), wz.y, ffma2(make_float2(c1.x, c1.y), wy.y, ffma2(make_float2(c0.x, c0.y), wx.y, make_float2(mv.x, mv.y))));
-          const float2 mb = ffma2(make_float2(c2.z, c2.w), wz.y, ffma2(make_float2(c1.z, c1.w), wy.y, ffma2(make_float2(c0.z, c0.w), wx.y, make_float2(mv.z, mv.w))));
-          acc_a = ffma2(ma, wgt, acc_a);
-          acc_b = ffma2(mb, wgt, acc_b);
-          px += STAGE_STRIDE; py += STAGE_STRIDE; pz += STAGE_STRIDE; sp += STAGE_STRIDE;
+          const float4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3];
+          const float2 t_xy = make_float2(q0.x, q0.y);
+          const float2 u_xy = fadd2(t_xy, kc_xy);
+          const float2 w_xy = ffma2(fmul2(kg_xy, u_xy), u_xy, ke_xy);
+          const float2 d_xy = ffma2(t_xy, neg_h2, ka_xy);
+          const float u_z = q0.z + kc_z;
+          const float w_z = fmaf(kg_z * u_z, u_z, ke_z);
+          const float d_z = fmaf(-h, q0.z, ka_z);
+          const float wgt = w_xy.x * w_xy.y * w_z;
+          // m*v + A delta
+          const float2 m_xy = ffma2(make_float2(q2.z, q2.w), d_z, ffma2(make_float2(q2.x, q2.y), d_xy.y, ffma2(make_float2(q1.z, q1.w), d_xy.x, make_float2(q1.x, q1.y))));
+          const float m_z = fmaf(q3.w, d_z, fmaf(q3.z, d_xy.y, fmaf(q3.y, d_xy.x, q3.x)));
+          acc_xy = ffma2(m_xy, wgt, acc_xy);
+          acc_z = fmaf(wgt, m_z, acc_z);
+          acc_m = fmaf(wgt, q0.w, acc_m);
+          sp += STAGE_STRIDE / 4;
         }
         if (node_lane) {
-          const int c = __float_as_int(stage[first * STAGE_STRIDE + 18]);
+          const int c = __float_as_int(stage[first * STAGE_STRIDE + 16]);
           const int t = ((c >> 4) * 6 + ((c >> 2) & 3)) * 6 + (c & 3) + lane_tile_off;
-          const float4 o = my_tile[t];
-          const float2 oa = fadd2(make_float2(o.x, o.y), acc_a), ob = fadd2(make_float2(o.z, o.w), acc_b);
-          my_tile[t] = make_float4(oa.x, oa.y, ob.x, ob.y);
+          float4 o = my_tile[t];
+          o.x += acc_xy.x; o.y += acc_xy.y; o.z += acc_z; o.w += acc_m;
+          my_tile[t] = o;
         }
       }
       __syncwarp();
@@ -805,7 +818,7 @@ constexpr int G2P_THREADS = 128;
 // `D` (this is where the physical re-bin happens).
 template <bool FUSE, bool REDUCE, bool MELDED>
 __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
-                                                        const uint32_t* __restrict__ group_start, const int* __restrict__ nbr, StepScalars* S,
+                                                        const uint2* __restrict__ group_range, const int* __restrict__ nbr, StepScalars* S,
                                                         const float4* __restrict__ grid, SimConsts K, float dt) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
@@ -826,8 +839,8 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     __syncthreads();
     const uint32_t g = s_group;
     if (g >= n_groups) break;
-    const uint32_t start = group_start[g];
-    const uint32_t end = group_start[g + 1];
+    const uint2 range = group_range[g];
+    const uint32_t start = range.x, end = range.y;
     for (int t = threadIdx.x; t < TILE_NODES; t += blockDim.x) {
       const int ti = t / 36, tj = (t / 6) % 6, tk = t % 6;
       const int nb = s_nbr[(ti >> 2) | ((tj >> 2) << 1) | ((tk >> 2) << 2)];
@@ -1308,15 +1321,15 @@ __global__ void k_rows_to_wire(const float* __restrict__ src, size_t cap, const 
 
 // ------------------------------------------------------------------------------------------------
 // grid download helpers: which nodes of an active tile have >= 1 contributor
-__global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint32_t* __restrict__ group_start, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(256) k_touch_nodes(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint2* __restrict__ group_range, const int* __restrict__ nbr,
                                                      const StepScalars* __restrict__ S, float h, unsigned long long* __restrict__ node_mask) {
   if (SVB_ABORTED(S)) return;
   const uint32_t n_groups = S->n_ptiles;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
-    const uint32_t start = group_start[g];
-    const uint32_t end = group_start[g + 1];
+    const uint2 range = group_range[g];
+    const uint32_t start = range.x, end = range.y;
     for (uint32_t j = start + lane; j < end; j += 32) {
       const uint32_t i = src_of[j];
       const int s0 = base_node(P.f(PX)[i], h) & 3, s1 = base_node(P.f(PX + 1)[i], h) & 3, s2 = base_node(P.f(PX + 2)[i], h) & 3;
