@@ -357,14 +357,16 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   unsigned long long key = TILE_EMPTY;
   uint32_t cell = 0, touch = 0;
   if (i < n) {
+    // every load of the row is issued before the flags are looked at: one memory latency instead of two in the chain
     const uint32_t flags = P.u(PFLAGS)[i];
+    const V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+    V3 v = V3{0.f, 0.f, 0.f};
+    if (APPLY_FORCE) v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+    uint32_t bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
     gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
     tomb = !gone && (flags & F_TOMBSTONED) != 0;
     if (!tomb && !gone) {
-      const V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-      uint32_t bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
       if (APPLY_FORCE) {
-        V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
         if (HAS_MESH) bits = collide_particle(M, K, dt, x, v, bits);
         P.u(PBITS)[i] = bits;
         bool goal = false;
@@ -622,18 +624,19 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
   const int li = node_lane ? lane / 9 : 0, lj = node_lane ? (lane / 3) % 3 : 0, lk = node_lane ? lane % 3 : 0;
-  // staged row (floats): 0..3 shifted x/h - base (3), mass | 4..7 m*v.x, m*v.y, A0, A1 | 8..11 A3, A4, A6, A7 | 12..15 m*v.z, A2, A5, A8 | 16 cell
+  // staged row (floats): 0..3 t = x/h - base (3), mass | 4..7 b.x, b.y, B0, B1 | 8..11 B3, B4, B6, B7 | 12..15 b.z, B2, B5, B8 | 16 cell
+  // with B = A h and b = m v - B t, so that the momentum a particle sends to the node at stencil offset a in {0,1,2}^3 is
+  //   w (m v + A (a - t) h) = w (b + B a):   the lane's offset a is a constant, no per-particle distance has to be formed.
   // Every walk load is a warp-uniform LDS.128 (2.2 cycles of shared-memory bandwidth per 16 bytes, measured; a 3-address
-  // LDS.64 costs 2 cycles per 8 bytes): the walk is bound by shared-memory bandwidth, so each lane derives the weight and the
-  // offset of ITS node from the particle's fractional position instead of loading staged per-axis (w, d) pairs.
-  //   kernel_quadratic on the branch node a falls in (cpu/src/kernels.rs:17-26): w_a(t) = g_a (t - c_a)^2 + e_a,  t in [1/2, 3/2)
-  //   a = 0: 1/2 (t - 3/2)^2      a = 1: 3/4 - (t - 1)^2      a = 2: 1/2 (t - 1/2)^2          offset d_a = (a - t) h
-  const float2 kc_xy = make_float2(-(1.5f - 0.5f * (float)li), -(1.5f - 0.5f * (float)lj));
-  const float2 kg_xy = make_float2(li == 1 ? -1.f : 0.5f, lj == 1 ? -1.f : 0.5f);
-  const float2 ke_xy = make_float2(li == 1 ? 0.75f : 0.f, lj == 1 ? 0.75f : 0.f);
-  const float2 ka_xy = make_float2((float)li * h, (float)lj * h);
-  const float kc_z = -(1.5f - 0.5f * (float)lk), kg_z = lk == 1 ? -1.f : 0.5f, ke_z = lk == 1 ? 0.75f : 0.f, ka_z = (float)lk * h;
-  const float2 neg_h2 = make_float2(-h, -h);
+  // LDS.64 costs 2 cycles per 8 bytes): the walk was bound by shared-memory bandwidth with staged per-axis (w, d) pairs, so
+  // each lane derives the weight of ITS node from t with per-lane polynomial coefficients instead:
+  //   kernel_quadratic on the branch node a falls in (cpu/src/kernels.rs:17-26), t in [1/2, 3/2):
+  //   a = 0: 1/2 (3/2 - t)^2 = t^2/2 - 3t/2 + 9/8     a = 1: 3/4 - (t - 1)^2 = -t^2 + 2t - 1/4     a = 2: 1/2 (t - 1/2)^2 = t^2/2 - t/2 + 1/8
+  const float2 kp2_xy = make_float2(li == 1 ? -1.f : 0.5f, lj == 1 ? -1.f : 0.5f);
+  const float2 kp1_xy = make_float2(li == 0 ? -1.5f : li == 1 ? 2.f : -0.5f, lj == 0 ? -1.5f : lj == 1 ? 2.f : -0.5f);
+  const float2 kp0_xy = make_float2(li == 0 ? 1.125f : li == 1 ? -0.25f : 0.125f, lj == 0 ? 1.125f : lj == 1 ? -0.25f : 0.125f);
+  const float kp2_z = lk == 1 ? -1.f : 0.5f, kp1_z = lk == 0 ? -1.5f : lk == 1 ? 2.f : -0.5f, kp0_z = lk == 0 ? 1.125f : lk == 1 ? -0.25f : 0.125f;
+  const float fli = (float)li, flj = (float)lj, flk = (float)lk;
   const int lane_tile_off = (li * 6 + lj) * 6 + lk;
 
   for (;;) {
@@ -675,10 +678,16 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
           for (int q = 0; q < 9; ++q) A.m[q] -= sj * cauchy.m[q];
         }
         const float mv0 = mass * P.f(PV)[i], mv1 = mass * P.f(PV + 1)[i], mv2 = mass * P.f(PV + 2)[i];
-        st[0] = make_float4(n0 - (float)s0, n1 - (float)s1, n2 - (float)s2, mass);
-        st[1] = make_float4(mv0, mv1, A.m[0], A.m[1]);
+        const float t0 = n0 - (float)s0, t1 = n1 - (float)s1, t2 = n2 - (float)s2;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) A.m[q] *= h;
+        const float b0 = mv0 - (A.m[0] * t0 + A.m[3] * t1 + A.m[6] * t2);
+        const float b1 = mv1 - (A.m[1] * t0 + A.m[4] * t1 + A.m[7] * t2);
+        const float b2 = mv2 - (A.m[2] * t0 + A.m[5] * t1 + A.m[8] * t2);
+        st[0] = make_float4(t0, t1, t2, mass);
+        st[1] = make_float4(b0, b1, A.m[0], A.m[1]);
         st[2] = make_float4(A.m[3], A.m[4], A.m[6], A.m[7]);
-        st[3] = make_float4(mv2, A.m[2], A.m[5], A.m[8]);
+        st[3] = make_float4(b2, A.m[2], A.m[5], A.m[8]);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) st[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -703,23 +712,26 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
         float2 acc_xy = make_float2(0.f, 0.f);
         float acc_z = 0.f, acc_m = 0.f;
         const float4* sp = reinterpret_cast<const float4*>(stage + first * STAGE_STRIDE);
-#pragma unroll 4
-        for (int p = first; p < last; ++p) {
-          const float4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3];
+        auto node_update = [&](const float4* row) {
+          const float4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
           const float2 t_xy = make_float2(q0.x, q0.y);
-          const float2 u_xy = fadd2(t_xy, kc_xy);
-          const float2 w_xy = ffma2(fmul2(kg_xy, u_xy), u_xy, ke_xy);
-          const float2 d_xy = ffma2(t_xy, neg_h2, ka_xy);
-          const float u_z = q0.z + kc_z;
-          const float w_z = fmaf(kg_z * u_z, u_z, ke_z);
-          const float d_z = fmaf(-h, q0.z, ka_z);
+          const float2 w_xy = ffma2(ffma2(kp2_xy, t_xy, kp1_xy), t_xy, kp0_xy);
+          const float w_z = fmaf(fmaf(kp2_z, q0.z, kp1_z), q0.z, kp0_z);
           const float wgt = w_xy.x * w_xy.y * w_z;
-          // m*v + A delta
-          const float2 m_xy = ffma2(make_float2(q2.z, q2.w), d_z, ffma2(make_float2(q2.x, q2.y), d_xy.y, ffma2(make_float2(q1.z, q1.w), d_xy.x, make_float2(q1.x, q1.y))));
-          const float m_z = fmaf(q3.w, d_z, fmaf(q3.z, d_xy.y, fmaf(q3.y, d_xy.x, q3.x)));
+          const float2 m_xy = ffma2(make_float2(q2.z, q2.w), flk, ffma2(make_float2(q2.x, q2.y), flj, ffma2(make_float2(q1.z, q1.w), fli, make_float2(q1.x, q1.y))));
+          const float m_z = fmaf(q3.w, flk, fmaf(q3.z, flj, fmaf(q3.y, fli, q3.x)));
           acc_xy = ffma2(m_xy, wgt, acc_xy);
           acc_z = fmaf(wgt, m_z, acc_z);
           acc_m = fmaf(wgt, q0.w, acc_m);
+        };
+        int p = first;
+        for (; p + 4 <= last; p += 4) {   // whole groups of four without a trip test in between
+#pragma unroll
+          for (int u = 0; u < 4; ++u) node_update(sp + u * (STAGE_STRIDE / 4));
+          sp += 4 * (STAGE_STRIDE / 4);
+        }
+        for (; p < last; ++p) {
+          node_update(sp);
           sp += STAGE_STRIDE / 4;
         }
         if (node_lane) {
