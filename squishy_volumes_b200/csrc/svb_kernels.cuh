@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     }
     __syncthreads();
     for (uint32_t i = start + threadIdx.x; i < end; i += blockDim.x) {
-      const uint32_t si = src_of[i];
+      const uint32_t si = src_of[i];   // (fetching the next iteration's row index one iteration ahead: measured neutral, r1n)
       V3 x = V3{P.f(PX)[si], P.f(PX + 1)[si], P.f(PX + 2)[si]};
       // issue the loads of everything this thread carries / updates before the gather needs them
       uint32_t flags = P.u(PFLAGS)[si];
