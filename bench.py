@@ -298,6 +298,11 @@ def main():
     state.advance(None, fi, run_params(state, steps))
     stages = {k: v / steps for k, v in inner.stage_times().items()}
     inner.enable_stage_timing(False)
+    stages_by_rank = None
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {k: round(v, 5) for k, v in stages.items() if v})
+        stages_by_rank = gathered
     peak, peak_kind = measured_peak()
     n_local = scene.n / world
     dom = max(("p2g", "g2p"), key=lambda s: stages.get(s, 0.0))
@@ -309,6 +314,8 @@ def main():
                 "frac": achieved / peak, "traffic": TRAFFIC.get(dom), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
                 "whole_substep": {"algorithmic_bytes": scene.n * (A_NOSORT + A_SORT_EXTRA), "achieved": whole, "frac": whole / (peak * world)},
                 "stage_ms_per_substep": stages, "stage_note": "rank 0, instrumented pass (one event pair and a sync per stage)"}
+    if stages_by_rank is not None:
+        roofline["stage_ms_per_substep_by_rank"] = stages_by_rank   # exchange stages include the wait for the neighbour
     state.close()
 
     # ---------------- end to end through the public API with host buffers (page-locked, as the contract asks)

@@ -101,6 +101,7 @@ struct SvbHandle {
   uint64_t halo_tiles_sent = 0, migrated_out = 0;
   // peer-memory exchange (CUDA IPC mailboxes; the NCCL path above stays as the fallback when IPC is unavailable)
   bool p2p = false;
+  DevBuf mig_list;                      // slots k_g2p found leaving the slab (left list, right list)
   DevBuf mailbox;                       // this rank's mailbox: SlabHeader | halo in (left, right) | rows in (left, right)
   void* peer_mailbox[16] = {};          // every rank's mailbox mapped into this process (null for self)
   size_t mb_halo_cap = 0, mb_mig_cap = 0, mb_halo_off[2] = {0, 0}, mb_mig_off[2] = {0, 0};
@@ -316,7 +317,7 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
 
 // MeldGrid + CollectVelocity (+ Advance + Cull when fused).  Collider scenes first meld the sibling layers
 // into a velocity grid; without colliders G2P divides by the mass while it stages a tile.
-int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
+int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, const MigrateCut* cut = nullptr) {
   cudaStream_t s = h->stream;
   StepScalars* S = cur_scalars(h);
   const float4* src = h->grid.as<float4>();
@@ -333,9 +334,11 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt) {
   const int* nb = h->nbr.as<int>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
   const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
-#define SVB_G2P(F, R, M) k_g2p<F, R, M><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt)
-  if (fuse) { if (has_mesh) SVB_G2P(true, false, true); else SVB_G2P(true, false, false); }
-  else { if (has_mesh) SVB_G2P(false, true, true); else SVB_G2P(false, true, false); }
+  const MigrateCut mc = cut ? *cut : MigrateCut{};
+#define SVB_G2P(F, R, M, SL) k_g2p<F, R, M, SL><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc)
+  if (fuse && cut) { if (has_mesh) SVB_G2P(true, false, true, true); else SVB_G2P(true, false, false, true); }
+  else if (fuse) { if (has_mesh) SVB_G2P(true, false, true, false); else SVB_G2P(true, false, false, false); }
+  else { if (has_mesh) SVB_G2P(false, true, true, false); else SVB_G2P(false, true, false, false); }
 #undef SVB_G2P
   LAUNCH_CHECK();
   h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
@@ -561,26 +564,30 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   SlabHeader* my_hdr = h->mailbox.as<SlabHeader>();
   unsigned char* my_mb = h->mailbox.as<unsigned char>();
   const bool has[2] = {h->rank > 0, h->rank + 1 < h->n_ranks};
-  for (int side = 0; side < 2; ++side)
-    if (has[side]) {
-      // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right; the message lands in
-      // the neighbour's slot for "from the right" (side 0) / "from the left" (side 1)
-      unsigned char* peer = static_cast<unsigned char*>(h->peer_mailbox[h->rank + (side ? 1 : -1)]);
-      SlabHeader* ph = reinterpret_cast<SlabHeader*>(peer);
-      const int their = side ? 0 : 1;
-      k_halo_send<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), side ? h->slab_hi : h->slab_lo, reinterpret_cast<HaloEntry*>(peer + h->mb_halo_off[their]),
-                                      &ph->halo_count[their], &ph->halo_seq[their], (uint32_t)h->mb_halo_cap, seq, h->p2p_local + 4 * side);
-      LAUNCH_CHECK();
-    }
-  for (int side = 0; side < 2; ++side)
-    if (has[side]) {
-      k_halo_recv<<<148 * 2, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(), h->grid.as<float4>(),
-                                          reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[side]), &my_hdr->halo_count[side], &my_hdr->halo_seq[side], seq);
-      LAUNCH_CHECK();
-    }
+  if (has[0] || has[1]) {
+    // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right; a message lands in the
+    // neighbour's slot for "from the right" (when I am its right neighbour) / "from the left"
+    HaloPeers hp{};
+    for (int side = 0; side < 2; ++side)
+      if (has[side]) {
+        unsigned char* peer = static_cast<unsigned char*>(h->peer_mailbox[h->rank + (side ? 1 : -1)]);
+        SlabHeader* ph = reinterpret_cast<SlabHeader*>(peer);
+        const int their = side ? 0 : 1;
+        hp.entries[side] = reinterpret_cast<HaloEntry*>(peer + h->mb_halo_off[their]);
+        hp.count[side] = &ph->halo_count[their];
+        hp.seq[side] = &ph->halo_seq[their];
+      }
+    k_halo_send2<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local);
+    LAUNCH_CHECK();
+    k_halo_recv2<<<148 * 2, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(), h->grid.as<float4>(), reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[0]),
+                                        reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[1]), my_hdr, has[0] ? 1 : 0, has[1] ? 1 : 0, seq);
+    LAUNCH_CHECK();
+  }
   stage_end(h);
   stage_begin(h, ST_G2P);
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc;
+  CK(h->mig_list.ensure(2 * h->mb_mig_cap * 4));
+  const MigrateCut cut{h->slab_lo, h->slab_hi, h->reach_lo, h->reach_hi, 4.f * (float)h->slab_lo, 4.f * (float)h->slab_hi, h->mig_list.as<uint32_t>(), h->p2p_local + 8, (uint32_t)h->mb_mig_cap};
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, &cut)) return rc;
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
   SlabPeers peers{};
@@ -600,7 +607,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       peers.err_seq[r] = &ph->err_seq[h->rank];
       peers.err_val[r] = &ph->err_val[h->rank];
     }
-  k_migrate_send<<<148 * 4, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, hh, h->slab_lo, h->slab_hi, h->reach_lo, h->reach_hi, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 8);
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev);
@@ -759,7 +766,7 @@ void svb_destroy(SvbHandle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_slots, &h->tile_key, &h->tile_slot, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
-                   &h->grid, &h->melded, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
+                   &h->grid, &h->melded, &h->mig_list, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
                    &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e,

@@ -828,10 +828,19 @@ __global__ void __launch_bounds__(256) k_meld(const StepScalars* __restrict__ S,
 constexpr int G2P_THREADS = 128;
 // Reads the particle through src_of from the pre-bin buffer `P`, writes every field of it to slot i of
 // `D` (this is where the physical re-bin happens).
-template <bool FUSE, bool REDUCE, bool MELDED>
+// slab ranks: a particle whose advanced position left the block columns [lo, hi) is noted in a per-side list of binned
+// slots while G2P still holds its new position (no pass over all rows to find the few that migrate)
+struct MigrateCut {
+  int lo, hi, reach_lo, reach_hi;
+  float node_lo, node_hi;   // 4 * lo, 4 * hi as floats
+  uint32_t* list;     // [2 * cap]: slots leaving to the left, then to the right
+  uint32_t* counts;   // [2]
+  uint32_t cap;
+};
+template <bool FUSE, bool REDUCE, bool MELDED, bool SLAB>
 __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
                                                         const uint2* __restrict__ group_range, const int* __restrict__ nbr, StepScalars* S,
-                                                        const float4* __restrict__ grid, SimConsts K, float dt) {
+                                                        const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
   __shared__ int s_nbr[8];
@@ -935,6 +944,20 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
         else { flags |= F_FAILED; failed = 1; }
         const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
         if (!within) flags |= F_TOMBSTONED;
+        // cheap filter first (x * (1/h) is within a small fraction of a cell of the exact x / h): only particles within half a
+        // cell of a cut evaluate the bit-exact base node
+        const float approx_node = x.x * inv_h - 0.5f;
+        if (SLAB && within && (approx_node < mc.node_lo + 0.5f || approx_node > mc.node_hi - 0.5f)) {
+          const int bx = floor_div4(base_node(x.x, h));
+          if (bx < mc.lo || bx >= mc.hi) {
+            if (bx < mc.reach_lo || bx >= mc.reach_hi) atomicOr(&S->status, ST_KEY_RANGE);   // crossed more than one slab in a substep
+            else {
+              const int side = bx < mc.lo ? 0 : 1;
+              const uint32_t slot = atomicAdd(&mc.counts[side], 1u);
+              if (slot < mc.cap) mc.list[(size_t)side * mc.cap + slot] = i;
+            }
+          }
+        }
       }
       D.f(PX)[i] = x.x; D.f(PX + 1)[i] = x.y; D.f(PX + 2)[i] = x.z;
       D.f(PV)[i] = v.x; D.f(PV + 1)[i] = v.y; D.f(PV + 2)[i] = v.z;
@@ -1117,9 +1140,14 @@ __device__ __forceinline__ bool wait_seq(const uint32_t* p, uint32_t seq) {
   return false;
 }
 
-// halo, sending side: like k_pack_column, but the entries go straight into the neighbour's mailbox
-__global__ void __launch_bounds__(256) k_halo_send(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid, int column,
-                                                   HaloEntry* __restrict__ peer_entries, uint32_t* peer_count, uint32_t* peer_seq, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local /*[0] slots, [1] blocks done*/) {
+// both directions in one launch: tiles of my first column go to the left neighbour, tiles of my halo column (== hi) to the
+// right one; `local` = [0], [1] slot counters, [2] blocks done
+struct HaloPeers {
+  HaloEntry* entries[2];                 // the neighbours' mailbox regions for my messages (null at the domain ends)
+  uint32_t* count[2]; uint32_t* seq[2];
+};
+__global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid, int lo, int hi,
+                                                    HaloPeers peers, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   if (!SVB_ABORTED(S)) {
@@ -1129,12 +1157,15 @@ __global__ void __launch_bounds__(256) k_halo_send(const StepScalars* __restrict
       int bx, by, bz;
       uint32_t layer;
       tile_key_unpack(k, bx, by, bz, layer);
-      if (bx != column) continue;
+      int side;
+      if (bx == lo && peers.entries[0]) side = 0;
+      else if (bx == hi && peers.entries[1]) side = 1;
+      else continue;
       uint32_t slot = 0;
-      if (lane == 0) slot = atomicAdd(&local[0], 1u);
+      if (lane == 0) slot = atomicAdd(&local[side], 1u);
       slot = __shfl_sync(SVB_FULL, slot, 0);
       if (slot >= cap) continue;
-      HaloEntry* e = peer_entries + slot;
+      HaloEntry* e = peers.entries[side] + slot;
       if (lane == 0) {
         e->block_key = k & ~(unsigned long long)((1u << LAYER_BITS) - 1u);
         e->bits = layer_bits_of(layer_slots, layer);
@@ -1144,35 +1175,46 @@ __global__ void __launch_bounds__(256) k_halo_send(const StepScalars* __restrict
       e->node[lane + 32] = grid[(size_t)t * 64 + lane + 32];
     }
   }
-  __threadfence_system();
+  // the block's peer-memory writes are ordered before its "done" tick by the barrier plus one system-scope fence of the
+  // ticking thread (fence cumulativity), not by a fence per thread
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(&local[1], 1u) == gridDim.x - 1) {
-    const uint32_t c = atomicAdd(&local[0], 0u);
-    st_sys(peer_count, c > cap ? (cap | SLAB_OVERFLOW) : c);
-    st_sys(peer_seq, seq);
-    local[0] = 0; local[1] = 0;
+  if (threadIdx.x == 0) __threadfence_system();
+  if (threadIdx.x == 0 && atomicAdd(&local[2], 1u) == gridDim.x - 1) {
+    for (int side = 0; side < 2; ++side) {
+      const uint32_t c = atomicAdd(&local[side], 0u);
+      if (peers.count[side]) {
+        st_sys(peers.count[side], c > cap ? (cap | SLAB_OVERFLOW) : c);
+        st_sys(peers.seq[side], seq);
+      }
+      local[side] = 0;
+    }
+    local[2] = 0;
   }
 }
-// halo, receiving side: wait for the neighbour's message in this rank's mailbox, then add (or create) the tiles
-__global__ void __launch_bounds__(256) k_halo_recv(StepScalars* S, TileTable T, unsigned long long* layer_slots, uint32_t* layer_list, float4* __restrict__ grid,
-                                                   const HaloEntry* __restrict__ in, const uint32_t* count_ptr, const uint32_t* seq_ptr, uint32_t seq) {
-  __shared__ uint32_t s_count;
+__global__ void __launch_bounds__(256) k_halo_recv2(StepScalars* S, TileTable T, unsigned long long* layer_slots, uint32_t* layer_list, float4* __restrict__ grid, const HaloEntry* __restrict__ in_left,
+                                                    const HaloEntry* __restrict__ in_right, const SlabHeader* __restrict__ hdr, int has_left, int has_right, uint32_t seq) {
+  __shared__ uint32_t s_count[2];
   if (threadIdx.x == 0) {
-    uint32_t c = 0;
-    if (wait_seq(seq_ptr, seq)) {
-      c = ld_sys(count_ptr);
-      if (c & SLAB_OVERFLOW) { atomicOr(&S->status, ST_COMM_OVERFLOW); c = 0; }
-    } else atomicOr(&S->status, ST_COMM_TIMEOUT);   // in the abort mask: the rest of the substep no-ops
-    s_count = c;
+    const int has[2] = {has_left, has_right};
+    for (int side = 0; side < 2; ++side) {
+      uint32_t c = 0;
+      if (has[side]) {
+        if (wait_seq(&hdr->halo_seq[side], seq)) {
+          c = ld_sys(&hdr->halo_count[side]);
+          if (c & SLAB_OVERFLOW) { atomicOr(&S->status, ST_COMM_OVERFLOW); c = 0; }
+        } else atomicOr(&S->status, ST_COMM_TIMEOUT);   // in the abort mask: the rest of the substep no-ops
+      }
+      s_count[side] = c;
+    }
   }
   __syncthreads();
-  const uint32_t count = s_count;
+  const uint32_t cl = s_count[0], total = cl + s_count[1];
   if (SVB_ABORTED(S)) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t zeroed = S->n_tiles_zeroed;
-  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < count; q += warps) {
-    const HaloEntry* e = in + q;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < total; q += warps) {
+    const HaloEntry* e = q < cl ? in_left + q : in_right + (q - cl);
     uint32_t id = TILE_PENDING;
     if (lane == 0) {
       const uint32_t layer = layer_find_or_insert(layer_slots, layer_list, e->bits, S);
@@ -1228,20 +1270,23 @@ struct SlabPeers {
   uint32_t* err_seq[SLAB_MAX_RANKS]; uint32_t* err_val[SLAB_MAX_RANKS];   // slot `rank` of every rank's header (null for self)
   int n_ranks;
 };
-__global__ void __launch_bounds__(256) k_migrate_send(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, float h, int lo, int hi, int reach_lo, int reach_hi, SlabPeers peers,
-                                                      uint32_t cap, uint32_t seq, uint32_t* __restrict__ local /*[0],[1] slots, [2] blocks done*/) {
-  const uint32_t n = S->n_live + S->n_tomb;   // rows after this substep's re-bin
+// Sending side, driven by the lists k_g2p<SLAB> filled (slots whose advanced position left the slab): one thread per
+// migrating row; the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
+__global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, MigrateCut mc, SlabPeers peers, uint32_t cap, uint32_t seq,
+                                                           uint32_t* __restrict__ blocks_done) {
+  __shared__ uint32_t s_c[2];
+  if (threadIdx.x < 2) s_c[threadIdx.x] = atomicAdd(&mc.counts[threadIdx.x], 0u);
+  __syncthreads();
+  const uint32_t c0 = s_c[0], c1 = s_c[1];
+  const uint32_t l0 = min(c0, min(mc.cap, cap)), l1 = min(c1, min(mc.cap, cap));
   if (!SVB_ABORTED(S)) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < l0 + l1; q += gridDim.x * blockDim.x) {
+      const int side = q < l0 ? 0 : 1;
+      const uint32_t slot = side ? q - l0 : q;
+      const uint32_t i = mc.list[(size_t)side * mc.cap + slot];
       const uint32_t flags = P.u(PFLAGS)[i];
-      if (flags & (F_TOMBSTONED | F_GONE)) continue;
-      const int bx = floor_div4(base_node(P.f(PX)[i], h));
-      if (bx >= lo && bx < hi) continue;
-      if (bx < reach_lo || bx >= reach_hi) { atomicOr(&S->status, ST_KEY_RANGE); continue; }  // crossed more than one slab in a substep
-      const int side = bx < lo ? 0 : 1;
-      const uint32_t slot = atomicAdd(&local[side], 1u);
       P.u(PFLAGS)[i] = flags | F_GONE;
-      if (slot >= cap || !peers.rows[side]) continue;
+      if (!peers.rows[side]) continue;
       uint32_t* row = peers.rows[side] + (size_t)slot * MIG_WORDS;
 #pragma unroll
       for (int f = 0; f < NFIELDS; ++f) row[f] = P.base[(size_t)f * P.cap + i];
@@ -1249,21 +1294,21 @@ __global__ void __launch_bounds__(256) k_migrate_send(ParticleBuf P, const float
       row[NFIELDS] = __float_as_uint(energy[i]);
     }
   }
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0 && atomicAdd(&local[2], 1u) == gridDim.x - 1) {
+  if (threadIdx.x == 0) __threadfence_system();
+  if (threadIdx.x == 0 && atomicAdd(blocks_done, 1u) == gridDim.x - 1) {
+    const uint32_t c[2] = {c0, c1};
     for (int side = 0; side < 2; ++side) {
-      const uint32_t c = atomicAdd(&local[side], 0u);
       if (peers.count[side]) {
-        st_sys(peers.count[side], c > cap ? (cap | SLAB_OVERFLOW) : c);
+        st_sys(peers.count[side], c[side] > min(mc.cap, cap) ? (min(mc.cap, cap) | SLAB_OVERFLOW) : c[side]);
         st_sys(peers.seq[side], seq);
       }
-      local[side] = 0;
+      mc.counts[side] = 0;
     }
     const uint32_t err = atomicOr(&S->sticky, 0u);
     for (int r = 0; r < peers.n_ranks; ++r)
       if (peers.err_val[r]) { st_sys(peers.err_val[r], err); st_sys(peers.err_seq[r], seq); }
-    local[2] = 0;
+    *blocks_done = 0;
   }
 }
 // receiving side: append the neighbours' rows behind this rank's rows, publish the new row count on the device,
