@@ -15,6 +15,7 @@ from . import cstructs as cs
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SVB200_LIB") or os.path.join(_HERE, "lib", "libsvb200.so")  # SVB200_LIB: developer override for A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svb200.h")
+FILES_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svb_files.h")
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -22,7 +23,7 @@ _lib = None
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [HEADER_PATH]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".cpp"))] + [HEADER_PATH, FILES_HEADER_PATH]
 
 
 def build(force: bool = False) -> str:
@@ -31,16 +32,19 @@ def build(force: bool = False) -> str:
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in sources())
     if stale:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "svb200.cu"), "-lnccl"]
+        cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "svb200.cu"), os.path.join(CSRC, "svb_files.cpp"), "-lnccl"]
         subprocess.run(cmd, check=True, cwd=CSRC)
     return LIB_PATH
 
 
 def declared_symbols():
-    """Every function name include/svb200.h declares."""
-    text = open(HEADER_PATH).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", text)))
+    """Every function name include/svb200.h and include/svb_files.h declare."""
+    names = set()
+    for path in (HEADER_PATH, FILES_HEADER_PATH):
+        text = open(path).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(svbf?_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 class LibraryMissing(RuntimeError):
