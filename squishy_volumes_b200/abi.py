@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("SVB200_LIB") or os.path.join(_HERE, "lib", "libsvb200
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svb200.h")
 FILES_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "svb_files.h")
 CSRC = os.path.join(_HERE, "csrc")
+REPLAY_PATH = os.path.join(_HERE, "lib", "svb_replay")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 _lib = None
@@ -34,6 +35,10 @@ def build(force: bool = False) -> str:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "svb200.cu"), os.path.join(CSRC, "svb_files.cpp"), "-lnccl"]
         subprocess.run(cmd, check=True, cwd=CSRC)
+        # the compute thread's frame loop over the two C ABIs (csrc/svb_replay.cpp), linked against the library next to it
+        gxx = os.environ.get("CXX", "g++")
+        subprocess.run([gxx, "-O2", "-std=c++17", os.path.join(CSRC, "svb_replay.cpp"), "-o", REPLAY_PATH, "-L" + os.path.dirname(LIB_PATH), "-lsvb200",
+                        "-Wl,-rpath,$ORIGIN"], check=True, cwd=CSRC)
     return LIB_PATH
 
 
