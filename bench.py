@@ -51,8 +51,8 @@ A_GRID = 8.0
 A_NOSORT = 280.0
 A_SORT_EXTRA = 272.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
-# committed `ncu --set full` capture (profiles/r1b_top_kernels_jelly1M.txt)
-TRAFFIC = {"p2g": 125.8e6 + 5.0e6, "g2p": 97.7e6 + 95.9e6}
+# committed `ncu --set full` capture (profiles/r1p_top_kernels_jelly1M.txt)
+TRAFFIC = {"p2g": 125.9e6 + 3.8e6, "g2p": 100.2e6 + 94.2e6}
 
 
 def make_scene(name: str, scale: float, length: int = 1):
