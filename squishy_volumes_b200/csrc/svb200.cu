@@ -83,7 +83,7 @@ struct SvbHandle {
   float gravity_a[3] = {0, 0, 0}, gravity_b[3] = {0, 0, 0};
   bool has_b = false, has_goals = false;
   DevBuf d_tri, d_opp, d_tri_collider, d_fan_offsets, d_fan_tris;
-  DevBuf d_va, d_vb, d_vvel, d_fric_a, d_fric_b, d_damp_a, d_damp_b, d_vpos, d_vnormal, d_tnormal, d_tfric, d_tdamp;
+  DevBuf d_va, d_vb, d_vvel, d_fric_a, d_fric_b, d_damp_a, d_damp_b, d_vpos, d_vnormal, d_tnormal, d_tbox, d_tfric, d_tdamp;
   DevBuf d_node_min, d_node_max, d_node_first, d_node_count, d_children, d_tri_indices;
   DevBuf d_flags_a, d_flags_b, d_goal_a, d_goal_b;
   svbh::FlatBvh bvh;
@@ -251,6 +251,15 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   const BinArrays B{h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(),
                     h->layer_list.as<uint32_t>()};
   const uint32_t blocks = std::max<uint32_t>(blocks_for(n, 256), 1);
+  if (in.has_mesh && apply_force) {  // collide.rs:21-206, before the external force like phase/mod.rs:27-41
+    uint32_t* candidates = h->prank.as<uint32_t>();   // free until k_bin writes the ranks
+    k_collide_query<<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, n);
+    LAUNCH_CHECK();
+    k_collide_small<<<148 * 8, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, dt_force);
+    LAUNCH_CHECK();
+    k_collide_big<<<148 * 8, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, dt_force);
+    LAUNCH_CHECK();
+  }
 #define SVB_BIN(MESH, FORCE) k_bin<MESH, FORCE><<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, T, B, n, dt_force, in.g[0], in.g[1], in.g[2], in.factor_b)
   if (in.has_mesh) { if (apply_force) SVB_BIN(true, true); else SVB_BIN(true, false); }
   else { if (apply_force) SVB_BIN(false, true); else SVB_BIN(false, false); }
@@ -768,7 +777,7 @@ void svb_destroy(SvbHandle* h) {
   DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_slots, &h->tile_key, &h->tile_slot, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
                    &h->grid, &h->melded, &h->mig_list, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
-                   &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
+                   &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tbox, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
                    &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e,
                    &h->comm_counts, &h->mailbox, &h->halo_send[0], &h->halo_send[1], &h->halo_recv[0], &h->halo_recv[1], &h->mig_send[0], &h->mig_send[1], &h->mig_recv[0], &h->mig_recv[1]};
   for (DevBuf* b : all) b->release();
@@ -838,6 +847,7 @@ int32_t svb_set_topology(SvbHandle* h, uint32_t n_colliders, const uint32_t* num
   CK(h->d_vpos.ensure((size_t)T.n_vertices * 12 + 4));
   CK(h->d_vnormal.ensure((size_t)T.n_vertices * 12 + 4));
   CK(h->d_tnormal.ensure((size_t)T.n_triangles * 12 + 4));
+  CK(h->d_tbox.ensure((size_t)T.n_triangles * 24 + 4));
   CK(h->d_tfric.ensure((size_t)T.n_triangles * 4 + 4));
   CK(h->d_tdamp.ensure((size_t)T.n_triangles * 4 + 4));
   CK(cudaStreamSynchronize(h->stream));
@@ -903,7 +913,7 @@ int32_t svb_set_keyframes(SvbHandle* h, uint64_t frame, const SvbKeyframe* a, co
     M.fan_offsets = h->d_fan_offsets.as<uint32_t>(); M.fan_tris = h->d_fan_tris.as<uint32_t>();
     M.va = h->d_va.as<float>(); M.vb = h->d_vb.as<float>(); M.vvel = h->d_vvel.as<float>();
     M.fric_a = h->d_fric_a.as<float>(); M.fric_b = h->d_fric_b.as<float>(); M.damp_a = h->d_damp_a.as<float>(); M.damp_b = h->d_damp_b.as<float>();
-    M.vpos = h->d_vpos.as<float>(); M.vnormal = h->d_vnormal.as<float>(); M.tnormal = h->d_tnormal.as<float>(); M.tfric = h->d_tfric.as<float>(); M.tdamp = h->d_tdamp.as<float>();
+    M.vpos = h->d_vpos.as<float>(); M.vnormal = h->d_vnormal.as<float>(); M.tnormal = h->d_tnormal.as<float>(); M.tbox = h->d_tbox.as<float>(); M.tfric = h->d_tfric.as<float>(); M.tdamp = h->d_tdamp.as<float>();
     M.bvh_level = B.level; M.bvh_nodes = (int32_t)B.node_count.size();
     M.node_min = h->d_node_min.as<int32_t>(); M.node_max = h->d_node_max.as<int32_t>(); M.node_first = h->d_node_first.as<int32_t>(); M.node_count = h->d_node_count.as<int32_t>();
     M.children = h->d_children.as<int32_t>(); M.tri_indices = h->d_tri_indices.as<uint32_t>();

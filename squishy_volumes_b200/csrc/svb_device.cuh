@@ -102,6 +102,8 @@ struct StepScalars {
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
+  uint32_t n_candidates;     // particles whose BVH leaf holds a few triangles (k_collide_query -> k_collide_small)
+  uint32_t n_candidates_big; // ... many triangles (-> k_collide_big, one warp each)
   // adaptive time step reductions (f32::total_cmp keys)
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;
@@ -123,6 +125,7 @@ struct MeshDev {
   const float* damp_a; const float* damp_b;
   // interpolated per substep
   float* vpos; float* vnormal; float* tnormal; float* tfric; float* tdamp;
+  float* tbox;                  // 6 per triangle: bounding box (min, max) of the interpolated triangle, a cheap reject before the exact distance
   // BVH
   int32_t bvh_level;
   int32_t bvh_nodes;

@@ -67,6 +67,18 @@ __global__ void k_mesh_tri_normals(MeshDev M) {
   const V3 a = ld3(M.vpos, M.tri[3 * t]), b = ld3(M.vpos, M.tri[3 * t + 1]), c = ld3(M.vpos, M.tri[3 * t + 2]);
   const V3 n = normalize_or_zero(cross(b - a, c - a), SVB_NORMALIZATION_EPS);
   M.tnormal[3 * t] = n.x; M.tnormal[3 * t + 1] = n.y; M.tnormal[3 * t + 2] = n.z;
+  float* box = M.tbox + 6 * t;
+  box[0] = fminf(a.x, fminf(b.x, c.x)); box[1] = fminf(a.y, fminf(b.y, c.y)); box[2] = fminf(a.z, fminf(b.z, c.z));
+  box[3] = fmaxf(a.x, fmaxf(b.x, c.x)); box[4] = fmaxf(a.y, fmaxf(b.y, c.y)); box[5] = fmaxf(a.z, fmaxf(b.z, c.z));
+}
+// true when the triangle's bounding box is farther from p than `reach`: its exact distance is then >= reach as well, so
+// skipping it cannot change which triangle is closest within the forget distance (reach carries a 0.1 % rounding margin)
+__device__ __forceinline__ bool triangle_out_of_reach(const MeshDev& M, uint32_t t, V3 p, float reach) {
+  const float* box = M.tbox + 6 * t;
+  const float dx = fmaxf(fmaxf(box[0] - p.x, p.x - box[3]), 0.f);
+  const float dy = fmaxf(fmaxf(box[1] - p.y, p.y - box[4]), 0.f);
+  const float dz = fmaxf(fmaxf(box[2] - p.z, p.z - box[5]), 0.f);
+  return dx * dx + dy * dy + dz * dz > reach * reach;
 }
 __global__ void k_mesh_vertex_normals(MeshDev M) {
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -143,25 +155,9 @@ __device__ __forceinline__ void bvh_query(const MeshDev& M, int qx, int qy, int 
   }
 }
 
-// collide.rs:45-204 for one particle.  Returns the new collider bits; edits `vel`.
-__device__ __noinline__ uint32_t collide_particle(const MeshDev& M, const SimConsts& K, float dt, V3 p, V3& vel, uint32_t bits) {
-  const int lx = (int)floorf(p.x / K.leaf_size), ly = (int)floorf(p.y / K.leaf_size), lz = (int)floorf(p.z / K.leaf_size);
-  int first, count;
-  bvh_query(M, lx, ly, lz, first, count);
-  if (count == 0) return 0u;
-  uint32_t closest[16];
-  float min_dist[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { closest[c] = 0xffffffffu; min_dist[c] = 3.402823466e+38f; }
-  for (int q = 0; q < count; ++q) {
-    const uint32_t t = M.tri_indices[first + q];
-    const V3 n = ld3(M.tnormal, t);
-    if (is_zero(n)) continue;
-    const float d = triangle_distance(p, ld3(M.vpos, M.tri[3 * t]), ld3(M.vpos, M.tri[3 * t + 1]), ld3(M.vpos, M.tri[3 * t + 2]), n);
-    if (d >= K.forget_distance) continue;
-    const uint32_t c = M.tri_collider[t] & 15u;
-    if (d < min_dist[c]) { min_dist[c] = d; closest[c] = t; }
-  }
+// collide.rs:128-204 for one particle, given the closest triangle per collider (0xffffffff = none within the forget
+// distance): feature classification, side bits, friction / damping / push-out.  Returns the new collider bits; edits `vel`.
+__device__ __forceinline__ uint32_t collide_respond(const MeshDev& M, const SimConsts& K, float dt, V3 p, V3& vel, uint32_t bits, const uint32_t* closest) {
   for (unsigned collider = 0; collider < 16; ++collider) {
     const uint32_t ct = closest[collider];
     if (ct == 0xffffffffu) { bits = bits_set(bits, collider, -1); continue; }
@@ -214,6 +210,134 @@ __device__ __noinline__ uint32_t collide_particle(const MeshDev& M, const SimCon
     vel = vel - res.to_p / dt;
   }
   return bits;
+}
+
+// Collide (collide.rs:21-206) in passes over compacted lists, so that the triangle loops of the particles near a collider do
+// not stall the warps of the many that are not:
+//   k_collide_query   one thread per particle: BVH point query of its leaf cell; an empty leaf clears the collider bits
+//                     (collide.rs:57-61); a leaf with triangles puts the particle on the "small" list (front of the scratch
+//                     array) or, beyond COLLIDE_SMALL_MAX triangles, on the "big" list (back of the array);
+//   k_collide_small   one thread per small candidate: the reference's sequential scan (collide.rs:63-88);
+//   k_collide_big     one WARP per big candidate: the lanes share the leaf's triangle run, the closest triangle per collider
+//                     comes from a warp reduction on (distance, position in the run) — the same "first minimum" the
+//                     sequential scan keeps — and lane 0 finishes the particle.
+constexpr int COLLIDE_SMALL_MAX = 24;
+__global__ void __launch_bounds__(256) k_collide_query(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, uint32_t* __restrict__ candidates, uint32_t cap, uint32_t n) {
+  if (S->sticky) return;
+  n = min(n, S->n);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  int kind = 0;   // 1 small, 2 big
+  if (i < n) {
+    const uint32_t flags = P.u(PFLAGS)[i];
+    const float x0 = P.f(PX)[i], x1 = P.f(PX + 1)[i], x2 = P.f(PX + 2)[i];
+    if (!(flags & (F_TOMBSTONED | F_GONE))) {
+      int first, count;
+      bvh_query(M, (int)floorf(x0 / K.leaf_size), (int)floorf(x1 / K.leaf_size), (int)floorf(x2 / K.leaf_size), first, count);
+      if (count > COLLIDE_SMALL_MAX) kind = 2;
+      else {
+        // a leaf with few triangles (a coarse mesh: the whole box collider of a dam break is ONE leaf) — look for any triangle
+        // whose bounding box is within reach; with none, every collider ends "not near": the same bits as an empty leaf
+        const V3 p = V3{x0, x1, x2};
+        const float reach = K.forget_distance * 1.001f;
+        for (int r = 0; r < count && kind == 0; ++r)
+          if (!triangle_out_of_reach(M, M.tri_indices[first + r], p, reach)) kind = 1;
+      }
+      if (kind == 0) P.u(PBITS)[i] = 0u;
+    }
+  }
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned ms = __ballot_sync(SVB_FULL, kind == 1), mb = __ballot_sync(SVB_FULL, kind == 2);
+  uint32_t base_s = 0, base_b = 0;
+  if (lane == 0) {
+    if (ms) base_s = atomicAdd(&S->n_candidates, (uint32_t)__popc(ms));
+    if (mb) base_b = atomicAdd(&S->n_candidates_big, (uint32_t)__popc(mb));
+  }
+  base_s = __shfl_sync(SVB_FULL, base_s, 0);
+  base_b = __shfl_sync(SVB_FULL, base_b, 0);
+  const unsigned below = (1u << lane) - 1u;
+  if (kind == 1) candidates[base_s + __popc(ms & below)] = i;                    // the two lists cannot meet: together they hold <= n <= cap entries
+  if (kind == 2) candidates[cap - 1 - (base_b + __popc(mb & below))] = i;
+}
+__global__ void __launch_bounds__(128) k_collide_small(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, float dt) {
+  if (S->sticky) return;
+  const uint32_t n_cand = S->n_candidates;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
+    const uint32_t i = candidates[q];
+    const V3 p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+    int first, count;
+    bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
+    uint32_t closest[16];
+    float min_dist[16];
+    const float reach = K.forget_distance * 1.001f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { closest[c] = 0xffffffffu; min_dist[c] = 3.402823466e+38f; }
+    for (int r = 0; r < count; ++r) {
+      const uint32_t t = M.tri_indices[first + r];
+      if (triangle_out_of_reach(M, t, p, reach)) continue;
+      const V3 n = ld3(M.tnormal, t);
+      if (is_zero(n)) continue;
+      const float d = triangle_distance(p, ld3(M.vpos, M.tri[3 * t]), ld3(M.vpos, M.tri[3 * t + 1]), ld3(M.vpos, M.tri[3 * t + 2]), n);
+      if (d >= K.forget_distance) continue;
+      const uint32_t c = M.tri_collider[t] & 15u;
+      if (d < min_dist[c]) { min_dist[c] = d; closest[c] = t; }
+    }
+    V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+    const uint32_t bits = collide_respond(M, K, dt, p, vel, P.u(PBITS)[i], closest);
+    P.u(PBITS)[i] = bits;
+    P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
+  }
+}
+__global__ void __launch_bounds__(256) k_collide_big(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, uint32_t cap, float dt) {
+  if (S->sticky) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_cand = S->n_candidates_big;
+  const uint32_t n_colliders = min(M.n_colliders, 16u);
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_cand; q += warps) {
+    const uint32_t i = candidates[cap - 1 - q];
+    const V3 p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+    int first, count;
+    bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
+    // per lane: closest triangle per collider among the run entries lane, lane + 32, ... as (distance bits << 32 | run position):
+    // distances are >= 0, so the unsigned order of the bits is the numeric order and ties go to the earlier entry
+    unsigned long long best[16];
+    const float reach = K.forget_distance * 1.001f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) best[c] = ~0ull;
+    for (int r = (int)lane; r < count; r += 32) {
+      const uint32_t t = M.tri_indices[first + r];
+      if (triangle_out_of_reach(M, t, p, reach)) continue;
+      const V3 n = ld3(M.tnormal, t);
+      if (is_zero(n)) continue;
+      const float d = triangle_distance(p, ld3(M.vpos, M.tri[3 * t]), ld3(M.vpos, M.tri[3 * t + 1]), ld3(M.vpos, M.tri[3 * t + 2]), n);
+      if (!(d < K.forget_distance)) continue;   // (also drops a NaN distance, which the reference's `d < min` never selects)
+      const uint32_t c = M.tri_collider[t] & 15u;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)r;
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if ((uint32_t)k == c && key < best[k]) best[k] = key;
+    }
+    uint32_t closest[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      closest[c] = 0xffffffffu;
+      if ((uint32_t)c < n_colliders) {   // warp-uniform: scenes with one or two colliders reduce one or two keys
+        unsigned long long b = best[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(SVB_FULL, b, o);
+          b = other < b ? other : b;
+        }
+        if (b != ~0ull) closest[c] = M.tri_indices[first + (uint32_t)b];
+      }
+    }
+    if (lane == 0) {
+      V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+      const uint32_t bits = collide_respond(M, K, dt, p, vel, P.u(PBITS)[i], closest);
+      P.u(PBITS)[i] = bits;
+      P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -302,8 +426,8 @@ __device__ __forceinline__ int tile_find(const TileTable& T, unsigned long long 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_bin — collide + external force + binning, one thread per particle in the CURRENT order.
-//   * collide.rs / external_force.rs edit v and the collider bits in place (skipped on a re-bin redo);
+// k_bin — external force + binning, one thread per particle in the CURRENT order.
+//   * external_force.rs edits v in place (skipped on a re-bin redo), after the collide pass of the same substep;
 //   * the particle's tile (block of its base node, layer of its collider bits) is found or created in
 //     the tile table, warp-aggregated: lanes with equal keys elect one lane to touch the table;
 //   * the particle takes a slot in its cell: rank = atomicAdd(cell_count[tile*64 + cell]) (again one
@@ -366,9 +490,7 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
     gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
     tomb = !gone && (flags & F_TOMBSTONED) != 0;
     if (!tomb && !gone) {
-      if (APPLY_FORCE) {
-        if (HAS_MESH) bits = collide_particle(M, K, dt, x, v, bits);
-        P.u(PBITS)[i] = bits;
+      if (APPLY_FORCE) {   // (collide has already edited v and the bits of this substep: k_collide_query / k_collide_candidates)
         bool goal = false;
         if (G.flags_a) {
           const uint32_t o = P.u(PORIG)[i];
