@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S
 // (packed fp32), accumulating in registers while consecutive particles share a cell (they do: the run is
 // sorted by cell) — the warp-aggregated form of the scatter.  A cell change flushes 27 float4 into the
 // warp's private 6x6x6 tile (plain read-modify-write, no shared atomics: fp32 shared atomics are CAS
-// loops).  The walk is bound by shared-memory bandwidth; measured on B200 (scratch/lds_bench.cu) a
+// loops).  The walk is bound by shared-memory bandwidth; measured on B200 (profiles/lds_bench.cu) a
 // warp-uniform LDS.128 costs 2.2 cycles, a 3-address LDS.64 2 cycles and a 3-address LDS.128 4 cycles,
 // which is why the earlier layout (per-axis (w, d) pairs + 13 uniform floats = 13.6 cycles per particle)
 // lost to this one (8.8 cycles): 95 -> 80 us at 1 M particles.  (Also measured slower: lane = z-column of
