@@ -179,6 +179,14 @@ uint64_t svb_particle_count(const SvbHandle* h);      /* particles currently res
 int32_t svb_set_original_indices(SvbHandle* h, const uint32_t* original_index, uint64_t n);
 /* Download in resident order together with the global original index of each row. */
 int32_t svb_download_resident(SvbHandle* h, SvbParticles* out, uint64_t* original_index);
+/* Live particles per block column on this rank: counts[0] = columns below first_col, counts[1 + k] = column first_col + k,
+ * counts[n_cols + 1] = columns above (n_cols + 2 entries).  The planning input of a rebalance. */
+int32_t svb_slab_histogram(SvbHandle* h, int32_t first_col, uint32_t n_cols, uint64_t* counts);
+/* Collective, between two svb_advance calls (peer-memory path): this rank's block columns become [new_lo, new_hi).  The new
+ * slabs must be contiguous, keep the outer ends, and every cut must stay strictly inside the two old slabs it separates, so
+ * that rows only move to an adjacent rank; rows outside the new range are handed over at once ("rebalanced by
+ * particle count every K substeps"). */
+int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo_block_x, int32_t new_hi_block_x);
 
 #ifdef __cplusplus
 }

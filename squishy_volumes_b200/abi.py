@@ -123,6 +123,10 @@ def load():
     L.svb_comm_init.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
     L.svb_set_original_indices.restype = C.c_int32
     L.svb_set_original_indices.argtypes = [vp, cs.c_u32p, C.c_uint64]
+    L.svb_slab_histogram.restype = C.c_int32
+    L.svb_slab_histogram.argtypes = [vp, C.c_int32, C.c_uint32, C.POINTER(C.c_uint64)]
+    L.svb_slab_rebalance.restype = C.c_int32
+    L.svb_slab_rebalance.argtypes = [vp, C.c_int32, C.c_int32]
     L.svb_download_resident.restype = C.c_int32
     L.svb_download_resident.argtypes = [vp, C.POINTER(cs.SvbParticles), C.POINTER(C.c_uint64)]
     _lib = L

@@ -619,7 +619,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
-                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev);
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0);
   LAUNCH_CHECK();
   stage_end(h);
   // ---- the host catches up with the front half of this substep (the back half keeps the GPU busy meanwhile)
@@ -1315,7 +1315,7 @@ int setup_peer_mailboxes(SvbHandle* h) {
   CK(cudaStreamSynchronize(s));
   const size_t n_max = h->h_counts[0];
   h->mb_halo_cap = n_max / 128 + 4096;
-  h->mb_mig_cap = n_max / 16 + 65536;
+  h->mb_mig_cap = n_max / 4 + 65536;   // room for the columns a rebalance hands over at once, not just the per-substep trickle
   size_t off = 4096;  // header
   for (int k = 0; k < 2; ++k) { h->mb_halo_off[k] = off; off += h->mb_halo_cap * sizeof(HaloEntry); }
   for (int k = 0; k < 2; ++k) { h->mb_mig_off[k] = off; off += ((h->mb_mig_cap * MIG_WORDS * 4 + 255) & ~(size_t)255); }
@@ -1349,6 +1349,7 @@ int setup_peer_mailboxes(SvbHandle* h) {
   h->n_dev = d + 48;
   CK(cudaMemsetAsync(h->p2p_local, 0, 16 * 4, s));
   CK(cudaMemcpyAsync(h->n_dev, &h->n, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(h->n_dev + 1, 0, 4, s));   // blocks-done tick of the rebalance receive
   CK(cudaStreamSynchronize(s));
   h->slab_seq = 0;
   return 0;
@@ -1410,6 +1411,89 @@ int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, 
   CK(cudaStreamSynchronize(h->stream));
   h->slabs = true;
   return setup_peer_mailboxes(h);
+}
+
+int32_t svb_slab_histogram(SvbHandle* h, int32_t first_col, uint32_t n_cols, uint64_t* counts) {
+  if (!h || !counts) return SVB_BAD_ARGUMENT;
+  if (int rc = set_device(h)) return rc;
+  cudaStream_t s = h->stream;
+  CK(cudaStreamSynchronize(s));
+  if (h->p2p) CK(cudaMemcpy(&h->n, h->n_dev, 4, cudaMemcpyDeviceToHost));
+  const size_t bytes = ((size_t)n_cols + 2) * 8;
+  CK(h->node_offset.ensure(bytes));   // free between substeps
+  CK(cudaMemsetAsync(h->node_offset.p, 0, bytes, s));
+  if (h->n) {
+    k_column_histogram<<<148 * 4, 256, 0, s>>>(h->Pc(), h->K.h, h->n, first_col, n_cols, h->node_offset.as<unsigned long long>());
+    LAUNCH_CHECK();
+  }
+  CK(cudaMemcpyAsync(counts, h->node_offset.p, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
+  if (!h || new_lo >= new_hi) return SVB_BAD_ARGUMENT;
+  if (!h->slabs || !h->p2p) return fail(h, SVB_COMM_ERROR, "svb_slab_rebalance needs a slab rank on the peer-memory path");
+  if (int rc = set_device(h)) return rc;
+  cudaStream_t s = h->stream;
+  // every rank learns every old and new slab; the all-gather also orders this rebalance after every rank's last substep
+  CK(h->scratch.ensure((size_t)h->n_ranks * 16 + 64));
+  int32_t* d_tab = h->scratch.as<int32_t>();
+  const int32_t mine[4] = {h->slab_lo, h->slab_hi, new_lo, new_hi};
+  CK(cudaMemcpyAsync(d_tab + 4 * h->rank, mine, 16, cudaMemcpyHostToDevice, s));
+  NCK(ncclAllGather(d_tab + 4 * h->rank, d_tab, 4, ncclInt32, h->comm, s));
+  std::vector<int32_t> all(4 * (size_t)h->n_ranks);
+  CK(cudaMemcpyAsync(all.data(), d_tab, all.size() * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int r = 0; r + 1 < h->n_ranks; ++r) {
+    if (all[4 * r + 3] != all[4 * (r + 1) + 2]) return fail(h, SVB_BAD_ARGUMENT, "new slabs are not contiguous between ranks %d and %d", r, r + 1);
+    // what a rank holds may only go to an adjacent rank: the new cut stays strictly inside the two old slabs it separates
+    if (all[4 * r + 3] <= all[4 * r] || all[4 * r + 3] >= all[4 * (r + 1) + 1]) return fail(h, SVB_BAD_ARGUMENT, "the cut between ranks %d and %d moves beyond an adjacent slab", r, r + 1);
+  }
+  if (all[2] != all[0] || all[4 * (h->n_ranks - 1) + 3] != all[4 * (h->n_ranks - 1) + 1]) return fail(h, SVB_BAD_ARGUMENT, "the outer slab ends must stay where they are");
+  const int reach_lo = h->rank > 0 ? all[4 * (h->rank - 1) + 2] : new_lo;
+  const int reach_hi = h->rank + 1 < h->n_ranks ? all[4 * (h->rank + 1) + 3] : new_hi;
+  StepScalars* S = cur_scalars(h);
+  CK(h->mig_list.ensure(2 * h->mb_mig_cap * 4));
+  const MigrateCut cut{new_lo, new_hi, reach_lo, reach_hi, 4.f * (float)new_lo, 4.f * (float)new_hi, h->mig_list.as<uint32_t>(), h->p2p_local + 8, (uint32_t)h->mb_mig_cap};
+  const uint32_t seq = ++h->slab_seq;
+  k_note_outside<<<148 * 4, 256, 0, s>>>(h->Pc(), S, h->K.h, cut, h->n_dev);
+  LAUNCH_CHECK();
+  SlabHeader* my_hdr = h->mailbox.as<SlabHeader>();
+  unsigned char* my_mb = h->mailbox.as<unsigned char>();
+  const bool has[2] = {h->rank > 0, h->rank + 1 < h->n_ranks};
+  SlabPeers peers{};
+  peers.n_ranks = h->n_ranks;
+  for (int side = 0; side < 2; ++side)
+    if (has[side]) {
+      unsigned char* peer = static_cast<unsigned char*>(h->peer_mailbox[h->rank + (side ? 1 : -1)]);
+      SlabHeader* ph = reinterpret_cast<SlabHeader*>(peer);
+      const int their = side ? 0 : 1;
+      peers.rows[side] = reinterpret_cast<uint32_t*>(peer + h->mb_mig_off[their]);
+      peers.count[side] = &ph->mig_count[their];
+      peers.seq[side] = &ph->mig_seq[their];
+    }
+  for (int r = 0; r < h->n_ranks; ++r)
+    if (r != h->rank) {
+      SlabHeader* ph = reinterpret_cast<SlabHeader*>(h->peer_mailbox[r]);
+      peers.err_seq[r] = &ph->err_seq[h->rank];
+      peers.err_val[r] = &ph->err_val[h->rank];
+    }
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
+  LAUNCH_CHECK();
+  k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1);
+  LAUNCH_CHECK();
+  if (int rc = read_status(h)) return rc;
+  if (h->h_scalars->status & ST_COMM_OVERFLOW) return fail(h, SVB_COMM_ERROR, "rebalance: more particles change rank than the mailboxes (%zu rows) or the particle buffer hold", h->mb_mig_cap);
+  if (h->h_scalars->status & ST_COMM_TIMEOUT) return fail(h, SVB_COMM_ERROR, "rebalance: a neighbour did not answer");
+  if (h->h_scalars->status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "rebalance: a particle would have to cross more than one slab");
+  CK(cudaMemcpy(&h->n, h->n_dev, 4, cudaMemcpyDeviceToHost));
+  h->slab_lo = new_lo;
+  h->slab_hi = new_hi;
+  h->reach_lo = reach_lo;
+  h->reach_hi = reach_hi;
+  return 0;
 }
 
 int32_t svb_set_original_indices(SvbHandle* h, const uint32_t* original_index, uint64_t n) {

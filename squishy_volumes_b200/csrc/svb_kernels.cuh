@@ -1436,7 +1436,8 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
 // receiving side: append the neighbours' rows behind this rank's rows, publish the new row count on the device,
 // and fold every rank's error word into this rank's (a FAILED particle anywhere stops every rank after this substep)
 __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __restrict__ energy, StepScalars* S, const SlabHeader* __restrict__ hdr, const uint32_t* __restrict__ rows_left,
-                                                      const uint32_t* __restrict__ rows_right, int has_left, int has_right, int rank, int n_ranks, uint32_t seq, uint32_t* __restrict__ n_dev) {
+                                                      const uint32_t* __restrict__ rows_right, int has_left, int has_right, int rank, int n_ranks, uint32_t seq, uint32_t* __restrict__ n_dev,
+                                                      int between_substeps) {
   __shared__ uint32_t s_c[2];
   if (threadIdx.x == 0) {
     uint32_t c[2] = {0, 0};
@@ -1461,7 +1462,8 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
   }
   __syncthreads();
   const uint32_t cl = s_c[0], cr = s_c[1];
-  const uint32_t base = S->n_live + S->n_tomb;
+  // after a substep the rows are the re-binned ones; a rebalance between substeps appends behind whatever is resident
+  const uint32_t base = between_substeps ? *n_dev : S->n_live + S->n_tomb;
   const uint32_t room = (uint32_t)P.cap > base ? (uint32_t)P.cap - base : 0u;
   if (cl + cr > room) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_OVERFLOW); }
   const uint32_t total = min(cl + cr, room);
@@ -1473,7 +1475,41 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
     energy[i] = __uint_as_float(row[NFIELDS]);
   }
   // a substep that was a no-op on every rank (an earlier substep failed: k_bin returned at once) keeps the row count
-  if (blockIdx.x == 0 && threadIdx.x == 0 && S->bin_blocks_done != 0) *n_dev = base + total;
+  if (between_substeps) {
+    // every block reads *n_dev as its base: publish the new count only after all of them did (last block, like the senders)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      uint32_t* done = n_dev + 1;   // scratch word next to the row count
+      if (atomicAdd(done, 1u) == gridDim.x - 1) { *n_dev = base + total; *done = 0; }
+    }
+  } else if (blockIdx.x == 0 && threadIdx.x == 0 && S->bin_blocks_done != 0) *n_dev = base + total;
+}
+// rebalance (between substeps): every resident live row whose block column lies outside the rank's NEW range goes on the
+// per-side list k_migrate_send_list consumes (the per-substep path fills that list from k_g2p<SLAB> instead)
+__global__ void __launch_bounds__(256) k_note_outside(ParticleBuf P, StepScalars* S, float h, MigrateCut mc, const uint32_t* __restrict__ n_dev) {
+  const uint32_t n = *n_dev;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t flags = P.u(PFLAGS)[i];
+    if (flags & (F_TOMBSTONED | F_GONE)) continue;
+    const int bx = floor_div4(base_node(P.f(PX)[i], h));
+    if (bx >= mc.lo && bx < mc.hi) continue;
+    if (bx < mc.reach_lo || bx >= mc.reach_hi) { atomicOr(&S->status, ST_KEY_RANGE); continue; }
+    const int side = bx < mc.lo ? 0 : 1;
+    const uint32_t slot = atomicAdd(&mc.counts[side], 1u);
+    if (slot < mc.cap) mc.list[(size_t)side * mc.cap + slot] = i;
+  }
+}
+// live particles per block column: counts[0] = below first_col, counts[1 + k] = column first_col + k, counts[n_cols + 1] = above
+__global__ void __launch_bounds__(256) k_column_histogram(ParticleBuf P, float h, uint32_t n, int first_col, uint32_t n_cols, unsigned long long* __restrict__ counts) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (P.u(PFLAGS)[i] & (F_TOMBSTONED | F_GONE)) continue;
+    const long long k = (long long)floor_div4(base_node(P.f(PX)[i], h)) - first_col;
+    const uint32_t bin = k < 0 ? 0u : (k >= (long long)n_cols ? n_cols + 1u : (uint32_t)k + 1u);
+    // consecutive rows share a column (the state is binned): one atomic per distinct bin per warp
+    const unsigned peers = __match_any_sync(__activemask(), bin);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[bin], (unsigned long long)__popc(peers));
+  }
 }
 __global__ void k_add_u32(uint32_t* a, uint32_t n, uint32_t add) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

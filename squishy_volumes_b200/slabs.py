@@ -56,6 +56,39 @@ def plan_slabs(positions: np.ndarray, h: float, n_ranks: int) -> List[Tuple[int,
     return [(bounds[r], bounds[r + 1]) for r in range(n_ranks)]
 
 
+def replan_slabs(plan: Sequence[Tuple[int, int]], first_col: int, hist: np.ndarray, max_move: int) -> List[Tuple[int, int]]:
+    """New cuts that balance the particle count, given the GLOBAL column histogram of a running simulation
+    (`hist[0]` = columns below `first_col`, `hist[1 + k]` = column `first_col + k`, `hist[-1]` = columns above) under the
+    constraints of `svb_slab_rebalance`: the outer ends stay, every cut stays strictly inside the two old slabs it separates
+    (rows only ever move to an adjacent rank), cuts stay inside the histogram window, and no cut shift hands over more than
+    `max_move` particles at once (mailbox capacity).  Pure integer planning: every rank computes the same answer."""
+    n = len(plan)
+    if n < 2:
+        return [tuple(p) for p in plan]
+    hist = np.asarray(hist, dtype=np.int64)
+    cols = hist.shape[0] - 2
+    below = np.cumsum(hist)[:cols + 1]           # below[j] = particles in columns < first_col + j
+    total = int(hist.sum())
+    old = [int(p[0]) for p in plan[1:]]
+    new: List[int] = []
+    for k, cut in enumerate(old, start=1):
+        if not (first_col <= cut <= first_col + cols):
+            raise ValueError(f"cut {cut} lies outside the histogram window [{first_col}, {first_col + cols}]")
+        target = total * k / n
+        ideal = first_col + int(np.searchsorted(below, target, side="left"))
+        lo_bound = (old[k - 2] if k >= 2 else int(plan[0][0])) + 1
+        hi_bound = (old[k] if k < n - 1 else int(plan[-1][1])) - 1
+        if new:
+            lo_bound = max(lo_bound, new[-1] + 1)
+        c = min(max(ideal, lo_bound, first_col), hi_bound, first_col + cols)
+        step = 1 if c < cut else -1
+        while c != cut and abs(int(below[c - first_col]) - int(below[cut - first_col])) > max_move:
+            c += step                              # walk back towards the old cut until the hand-over fits
+        new.append(c)
+    bounds = [int(plan[0][0])] + new + [int(plan[-1][1])]
+    return [(bounds[r], bounds[r + 1]) for r in range(n)]
+
+
 def slab_of(positions: np.ndarray, h: float, plan: Sequence[Tuple[int, int]]) -> np.ndarray:
     bx = block_x(positions, h)
     cuts = np.array([hi for _, hi in plan[:-1]], dtype=np.int64)
@@ -134,6 +167,43 @@ class SlabState:
             rc = L.svb_set_original_indices(self.inner._h, cs.uptr(idx32), idx32.size)
             if rc != 0:
                 raise FatalError(rc, L.svb_last_error(self.inner._h).decode())
+
+    def column_histogram(self, first_col: int, n_cols: int) -> np.ndarray:
+        """Live particles per block column on this rank (n_cols + 2 entries, see include/svb200.h: svb_slab_histogram)."""
+        from . import abi
+        L = abi.load()
+        out = np.zeros(n_cols + 2, dtype=np.uint64)
+        rc = L.svb_slab_histogram(self.inner._h, int(first_col), int(n_cols), out.ctypes.data_as(C.POINTER(C.c_uint64)))
+        if rc != 0:
+            raise FatalError(rc, L.svb_last_error(self.inner._h).decode())
+        return out
+
+    def rebalance(self, dist, margin: int = 64, max_move: Optional[int] = None) -> bool:
+        """Collective, between two `advance` calls: move the cuts so that the ranks hold equal particle counts again
+        (SURVEY.md §8e).  `dist` is an initialised torch.distributed module (gloo or nccl) used to add up the column
+        histograms.  Returns True when the plan changed."""
+        from . import abi
+        cuts = [p[0] for p in self.plan[1:]]
+        if not cuts:
+            return False
+        first = min(cuts) - margin
+        n_cols = max(cuts) - min(cuts) + 2 * margin
+        local = self.column_histogram(first, n_cols).astype(np.int64)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, local)
+        hist = np.sum(gathered, axis=0)
+        if max_move is None:
+            max_move = int(0.8 * (self.n_global // self.world // 4 + 65536))   # 80 % of a mailbox (svb_comm_init: n_max / 4 + 65536 rows)
+        new_plan = replan_slabs(self.plan, first, hist, max_move)
+        if [tuple(p) for p in new_plan] == [tuple(p) for p in self.plan]:
+            return False
+        L = abi.load()
+        lo, hi = new_plan[self.rank]
+        rc = L.svb_slab_rebalance(self.inner._h, int(lo), int(hi))
+        if rc != 0:
+            raise FatalError(rc, L.svb_last_error(self.inner._h).decode())
+        self.plan = list(new_plan)
+        return True
 
     def advance(self, harness, frame_input: FrameInput, params: RunParameters) -> Optional[SimulationError]:
         return self.inner.advance(harness, frame_input, params)

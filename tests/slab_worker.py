@@ -20,7 +20,7 @@ from tests import golden_scenes, parity  # noqa: E402
 
 
 def build_scene(name):
-    if name == "jelly":
+    if name in ("jelly", "jelly_rebalance"):
         sc = scenes.jelly_collision(side=16)
         sc.io_state.particles.velocities[:, 0] *= 6.0          # fast approach: many particles cross the cut
         return sc
@@ -53,8 +53,31 @@ def main():
         assert L.svb_comm_unique_id(buf) == 0
         box[0] = bytes(buf)
     dist.broadcast_object_list(box, src=0)
-    st = slabs.SlabState.from_io_state(sc.io_state, sc.frame_input, rank, world, local, box[0])
+    plan = None
+    if name == "jelly_rebalance":
+        # start from cuts that are off balance by a block column each, run half the substeps, rebalance, run the rest
+        h0 = sc.frame_input.consts.scaled_grid_node_size()
+        good = slabs.plan_slabs(sc.io_state.particles.positions, h0, world)
+        cuts = [p[0] + (1 if k % 2 == 0 else -1) for k, p in enumerate(good[1:])]
+        for k in range(1, len(cuts)):
+            cuts[k] = max(cuts[k], cuts[k - 1] + 1)
+        bounds = [good[0][0]] + cuts + [good[-1][1]]
+        plan = [(bounds[r], bounds[r + 1]) for r in range(world)]
+    st = slabs.SlabState.from_io_state(sc.io_state, sc.frame_input, rank, world, local, box[0], plan=plan)
     params = RunParameters(target_time=(steps - 0.5) * sc.time_step, max_time_step=sc.time_step)
+    if name == "jelly_rebalance":
+        half = RunParameters(target_time=(steps // 2 - 0.5) * sc.time_step, max_time_step=sc.time_step)
+        err = st.advance(None, sc.frame_input, half)
+        assert err is None and st.substeps == steps // 2
+        before = [tuple(p) for p in st.plan]
+        n_before = len(st.resident()[0])
+        changed = st.rebalance(dist, margin=8)
+        counts = [None] * world
+        dist.all_gather_object(counts, (n_before, len(st.resident()[0])))
+        if rank == 0:
+            print(f"[{name}] plan {before} -> {[tuple(p) for p in st.plan]} changed={changed}; resident before/after {counts}", flush=True)
+            assert changed and sum(c[1] for c in counts) == sc.n
+            assert max(c[1] for c in counts) - min(c[1] for c in counts) <= max(c[0] for c in counts) - min(c[0] for c in counts)
     err = st.advance(None, sc.frame_input, params)
     idx, rows = st.resident()
     gathered = [None] * world

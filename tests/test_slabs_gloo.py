@@ -93,3 +93,43 @@ def test_two_rank_gloo_roundtrip():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in results)
     assert sum(n for _, _, n in results) == scenes.jelly_collision(side=12).n
+
+
+def _hist(bx, first, n_cols):
+    k = bx - first
+    bins = np.where(k < 0, 0, np.where(k >= n_cols, n_cols + 1, k + 1))
+    return np.bincount(bins, minlength=n_cols + 2)
+
+
+def test_replan_moves_cuts_towards_balance_within_its_constraints():
+    """replan_slabs: the planning half of svb_slab_rebalance (rebalanced by particle count)."""
+    rng = np.random.Generator(np.random.Philox(9))
+    bx = np.concatenate([rng.integers(0, 40, 30000), rng.integers(40, 48, 30000)])      # dense material on the right
+    plan = [(-slabs.FAR, 10), (10, 20), (20, 30), (30, slabs.FAR)]
+    first, n_cols = -10, 80
+    hist = _hist(bx, first, n_cols)
+    new = slabs.replan_slabs(plan, first, hist, max_move=10 ** 9)
+    assert new[0][0] == -slabs.FAR and new[-1][1] == slabs.FAR
+    assert all(new[r][1] == new[r + 1][0] and new[r][0] < new[r][1] for r in range(3))
+    for k in range(1, 4):                                   # every cut strictly inside the two old slabs it separates
+        assert plan[k - 1][0] < new[k][0] < plan[k][1]
+
+    def spread(p):
+        cuts = np.array([q[0] for q in p[1:]])
+        c = np.bincount(np.searchsorted(cuts, bx, side="right"), minlength=4)
+        return c.max() - c.min()
+    assert spread(new) < spread(plan)
+    again = new
+    for _ in range(8):                                      # repeated rebalancing converges to near-equal counts
+        again = slabs.replan_slabs(again, first, hist, max_move=10 ** 9)
+    assert spread(again) <= 2 * hist.max()
+    assert slabs.replan_slabs(again, first, hist, max_move=10 ** 9) == again
+    # a tight mailbox limits how many particles one step hands over
+    limited = slabs.replan_slabs(plan, first, hist, max_move=2000)
+    below = np.cumsum(hist)
+    for k in range(1, 4):
+        assert abs(int(below[limited[k][0] - first]) - int(below[plan[k][0] - first])) <= 2000
+    assert slabs.replan_slabs(plan, first, hist, max_move=0) == plan
+    with pytest.raises(ValueError):
+        slabs.replan_slabs([(-slabs.FAR, 500), (500, slabs.FAR)], first, hist, max_move=10)
+    assert slabs.replan_slabs([(-slabs.FAR, slabs.FAR)], first, hist, 10) == [(-slabs.FAR, slabs.FAR)]
