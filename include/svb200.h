@@ -156,8 +156,8 @@ int32_t svb_active_blocks(SvbHandle* h, int32_t* block_ids /* n*3 */, uint32_t* 
  * gpu/src/profiler_output.rs:93-192).  Returns the number of stages; names are static strings. */
 int32_t svb_stage_times(SvbHandle* h, const char** names, float* ms, int32_t cap);
 void svb_enable_stage_timing(SvbHandle* h, int32_t on);
-/* Re-bin cadence: particles are re-keyed and radix-sorted every substep; the physical permutation
- * of the SoA state happens every `every` substeps (1 = every substep, the reference's behaviour). */
+/* Options by name: "store_grid" (CpuRunParameters::store_grid: exact contributor masks for svb_download_grid),
+ * "global_particles" (slab ranks: size of the original-order keyframe arrays). */
 void svb_set_option(SvbHandle* h, const char* name, double value);
 
 /* ---- device-resident entry points (bench: inputs already in HBM) ---- */

@@ -2,9 +2,10 @@
 //
 // Particles: struct of arrays in HBM, every field a contiguous run of `cap` 4-byte words, fields
 // back to back in one allocation (field f of particle i = base[f*cap + i]).  Two such buffers
-// ping-pong across the physical re-bin (gather by the radix-sorted index).
+// ping-pong across the physical re-bin (G2P reads a row through the inverse map of the counting sort and
+// writes it to its binned slot in the other buffer).
 // Grid: sparse set of 4x4x4-node blocks, one dense 64-node float4 (px,py,pz,m) tile per active
-// (block, collider-bits layer), addressed through the sorted list of active bin keys.
+// (block, collider-bits layer), found through an open-addressing table of 64-bit tile keys.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -98,7 +99,7 @@ struct StepScalars {
   uint32_t n_tiles;    // active (block, layer) grid tiles
   uint32_t n_ptiles;   // tiles that own particles = ids [0, n_ptiles): the work list of P2G / G2P
   uint32_t n_layers;   // distinct non-zero collider-bit patterns
-  uint32_t n_tiles_zeroed;  // tiles cleared by k_zero_grid (tiles created later by a halo message are stored, not added)
+  uint32_t n_tiles_zeroed;  // tiles cleared by k_invert_zero (tiles created later by a halo message are stored, not added)
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles

@@ -2,15 +2,16 @@
 //
 // Phase map to the reference's CPU back end (/root/reference/rust/crates/cpu/src/phase/*.rs):
 //   k_mesh_*            interpolate_input.rs:18-107      collider mesh lerp, face / vertex normals
-//   k_bin               collide.rs:21-206 + external_force.rs:17-50 + sort.rs:29-33 (cell of floor(x/h - 1/2))
-//                       + update_grid_nodes.rs:31-156 (tile activation): single-pass counting sort on (tile, cell)
-//   k_cell_scan, k_scan_tiles                             cell / tile offsets of the binned order
-//   k_halo              update_grid_nodes.rs:102-108      neighbour tiles reached by each tile's particles
-//   k_permute           sort.rs:91-101                    scatter the SoA state into binned order
+//   k_collide_*         collide.rs:21-206                 BVH query, closest triangle per collider, response (compacted candidate lists)
+//   k_begin, k_bin      external_force.rs:17-50 + sort.rs:29-33 (cell of floor(x/h - 1/2)) + update_grid_nodes.rs:31-156
+//                       (tile activation): single-pass counting sort on (tile, cell)
+//   k_offsets           update_grid_nodes.rs:102-108      cell offsets, tile runs, neighbour tiles reached by each tile's particles
+//   k_invert_zero       sort.rs:91-101                    inverse map of the binned order (the state is permuted by the G2P write) + grid clear
 //   k_p2g               scatter_momentum.rs:22-93         particle -> grid, stress once per particle
 //   k_g2p               meld_grid.rs:16-69 + collect_velocity.rs:19-75 + advance_particles.rs:17-93
 //                       + cull_particles.rs:17-41 (+ limit_time_step.rs:187-223 reductions)
 //   k_limit_force       limit_time_step.rs:25-182
+//   k_halo_*2, k_migrate_*, k_note_outside, k_column_histogram     multi-GPU slabs (no reference counterpart)
 #pragma once
 #include "svb_device.cuh"
 
