@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B on one box: bench each library variant at 1M and 8M.  usage: scripts_ab.sh name1 name2 ...   (names under squishy_volumes_b200/lib/variants/, "cur" = the in-tree build)
+# A/B on one box: bench each library variant at 1M and 8M.  usage: tests/tools/ab.sh name1 name2 ...   (names under squishy_volumes_b200/lib/variants/, "cur" = the in-tree build)
 mkdir -p gpurun_out
 for rep in 1 2; do
 for v in "$@"; do

@@ -1,7 +1,7 @@
 """BASELINE.json configs 3-5 at full size on ONE B200 (run on the GPU box): size-independent properties instead of the oracle,
 plus device-timed substep rates.  Prints one JSON line per config; the summary is committed under profiles/.
 
-    python scripts_big_configs.py sand_torus 1 dam_break 1 mixed 1          # name, scale pairs
+    python tests/tools/big_configs.py sand_torus 1 dam_break 1 mixed 1          # name, scale pairs
 """
 import json
 import sys
@@ -11,7 +11,6 @@ import numpy as np
 
 sys.path.insert(0, ".")
 import bench  # noqa: E402
-import oracle.oracle as orc  # noqa: E402  (test infrastructure: the numpy cell keys only)
 from squishy_volumes_b200.state import B200State  # noqa: E402
 from squishy_volumes_b200.types import ParticleFlags, RunParameters  # noqa: E402
 
@@ -43,9 +42,6 @@ def run(name, scale, steps=10, warm=3):
     assert np.array_equal(np.sort(sm), np.arange(sc.n, dtype=np.uint32))
     live = (p1.flags & ParticleFlags.TOMBSTONED) == 0
     out["tombstoned"] = int((~live).sum())
-    # every live particle's reported cell is the bit-exact base node of the position it was binned at: check through the
-    # active-block set instead (positions have advanced since): every live particle's block, and the blocks its stencil reaches, are active
-    cells_now = orc.shift_quadratic(p1.positions[live], h)
     ids, bits = g.active_blocks()
     assert np.isfinite(p1.positions).all() and np.isfinite(p1.position_gradients).all() and np.isfinite(p1.velocities).all()
     # grid mass = live particle mass (every particle's weights sum to one; tombstoned particles take no part)
@@ -63,7 +59,6 @@ def run(name, scale, steps=10, warm=3):
     out["active_blocks"] = int(ids.shape[0])
     out["collider_layers"] = int(np.unique(bits).shape[0])
     out["max_speed"] = float(np.linalg.norm(p1.velocities[live], axis=1).max())
-    del cells_now
     g.close()
     return out
 
