@@ -64,7 +64,7 @@ struct SvbHandle {
   DevBuf energy;
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
   // binning scratch + tile table (rebuilt every substep)
-  DevBuf pcell, prank, src_of, table_slots, tile_key, tile_slot, tile_touch, cell_count, tile_start, nbr, grid, melded, node_mask, node_offset, scratch;
+  DevBuf pcell, prank, src_of, table_slots, tile_key, tile_slot, tile_touch, cell_count, slot_first, tile_start, nbr, grid, melded, node_mask, node_offset, scratch;
   size_t tile_cap = 0;      // tiles the per-tile arrays can hold
   bool tables_fresh = true; // tables were (re)allocated: memset them once, later substeps undo only what they used
   int s_cur = 0;            // half of the scalars double buffer this substep writes
@@ -191,8 +191,9 @@ int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
   CK(h->table_slots.ensure(slots * 16));
   CK(h->tile_key.ensure(c * 8));
   CK(h->tile_slot.ensure(c * 4));
-  CK(h->tile_touch.ensure(c * 4));
-  CK(h->cell_count.ensure(c * 64 * 4));
+  CK(h->tile_touch.ensure(slots * 4));          // the per-substep particle counters are indexed by table slot (k_bin never waits for a tile id)
+  CK(h->cell_count.ensure(slots * 64 * 4));
+  CK(h->slot_first.ensure(slots * 4));
   CK(h->tile_start.ensure((c + 1) * 8));
   CK(h->nbr.ensure(c * 8 * 4));
   CK(h->grid.ensure(c * 64 * 16));
@@ -233,8 +234,8 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   stage_begin(h, ST_BIN);
   if (h->tables_fresh) {
     CK(cudaMemsetAsync(h->table_slots.p, 0xff, ((size_t)h->table_mask + 1) * 16, s));
-    CK(cudaMemsetAsync(h->cell_count.p, 0, h->tile_cap * 64 * 4, s));
-    CK(cudaMemsetAsync(h->tile_touch.p, 0, h->tile_cap * 4, s));
+    CK(cudaMemsetAsync(h->cell_count.p, 0, ((size_t)h->table_mask + 1) * 64 * 4, s));
+    CK(cudaMemsetAsync(h->tile_touch.p, 0, ((size_t)h->table_mask + 1) * 4, s));
     CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
   }
   k_begin<<<148, 256, 0, s>>>(S_prev, S, tile_table(h), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), n, h->p2p ? h->n_dev : nullptr, h->tables_fresh ? 1 : 0);
@@ -268,7 +269,7 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   stage_end(h);
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
-  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->cell_count.as<uint32_t>(), h->tile_start.as<uint2>(), h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
+  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->cell_count.as<uint32_t>(), h->tile_start.as<uint2>(), h->slot_first.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(h->ev_front, s));
@@ -283,7 +284,7 @@ int enqueue_rebin(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   stage_begin(h, ST_PERMUTE);
   const uint32_t invert_blocks = blocks_for(n, 256);
-  k_invert_zero<<<invert_blocks + 148 * 2, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_start.as<uint2>(), h->src_of.as<uint32_t>(), n, invert_blocks,
+  k_invert_zero<<<invert_blocks + 148 * 2, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n, invert_blocks,
                                                         h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
   LAUNCH_CHECK();
   h->masks_valid = false;
@@ -774,7 +775,7 @@ void svb_destroy(SvbHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_slots, &h->tile_key, &h->tile_slot, &h->tile_touch, &h->cell_count, &h->tile_start, &h->nbr,
+  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_slots, &h->tile_key, &h->tile_slot, &h->tile_touch, &h->cell_count, &h->slot_first, &h->tile_start, &h->nbr,
                    &h->grid, &h->melded, &h->mig_list, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tbox, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,

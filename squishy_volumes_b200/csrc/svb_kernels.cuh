@@ -415,6 +415,36 @@ __device__ __forceinline__ uint32_t tile_find_or_insert(const TileTable& T, unsi
   atomicOr(&S->status, ST_TILE_OVERFLOW);
   return TILE_PENDING;
 }
+// k_bin's variant: returns the TABLE SLOT of the tile (or ~0u when the capacity is exhausted, status bit set).  The particle
+// counters of a substep are indexed by slot, so no thread waits for a tile id: the thread that claims an empty slot takes the next
+// particle-tile id and records (id -> key, slot) and slot -> id for the kernels that follow, nobody spins on it.  Particle tiles
+// count in n_ptiles AND n_tiles, so that n_tiles == n_ptiles when the binning kernel ends without any block having to publish it.
+__device__ __forceinline__ uint32_t tile_slot_find_or_insert(const TileTable& T, unsigned long long key, StepScalars* S) {
+  uint32_t s = tile_hash(key, T.mask);
+  for (uint32_t tries = 0; tries <= T.mask; ++tries) {
+    unsigned long long k = *(volatile unsigned long long*)&T.slots[s].x;
+    if (k == TILE_EMPTY) {
+      k = atomicCAS(&T.slots[s].x, TILE_EMPTY, key);
+      if (k == TILE_EMPTY) {
+        const uint32_t id = atomicAdd(&S->n_ptiles, 1u);
+        atomicAdd(&S->n_tiles, 1u);   // result unused: a fire-and-forget RED
+        if (id < T.tile_cap) {
+          T.tile_key[id] = key;
+          T.tile_slot[id] = s;
+          *(volatile unsigned long long*)&T.slots[s].y = id;
+          return s;
+        }
+        atomicOr(&S->status, ST_TILE_OVERFLOW);
+        *(volatile unsigned long long*)&T.slots[s].y = TILE_PENDING - 1;
+        return ~0u;
+      }
+    }
+    if (k == key) return s;
+    s = (s + 1) & T.mask;
+  }
+  atomicOr(&S->status, ST_TILE_OVERFLOW);
+  return ~0u;
+}
 __device__ __forceinline__ int tile_find(const TileTable& T, unsigned long long key) {
   uint32_t s = tile_hash(key, T.mask);
   for (uint32_t tries = 0; tries <= T.mask; ++tries) {
@@ -439,10 +469,10 @@ struct GoalDev {
   const float* goal_a; const float* goal_b;           // 3 per particle, original order
 };
 struct BinArrays {
-  uint32_t* pcell;        // [n] tile*64 + cell, 0xffffffff for tombstoned
-  uint32_t* prank;        // [n] slot inside the cell (or among the tombstoned)
-  uint32_t* cell_count;   // [tile_cap*64]
-  uint32_t* tile_touch;   // [tile_cap] 8-bit mask over neighbour offsets d
+  uint32_t* pcell;        // [n] table slot * 64 + cell, 0xffffffff for tombstoned
+  uint32_t* prank;        // [n] rank inside the cell (or among the tombstoned)
+  uint32_t* cell_count;   // [table slots * 64]: indexed by the tile's TABLE SLOT, so counting never waits for a tile id
+  uint32_t* tile_touch;   // [table slots] 8-bit mask over neighbour offsets d
   unsigned long long* layer_slots;
   uint32_t* layer_list;
 };
@@ -456,11 +486,12 @@ __global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ p
   const uint32_t n_tiles = tables_fresh ? 0u : min(prev->n_tiles, T.tile_cap), n_ptiles = tables_fresh ? 0u : min(prev->n_ptiles, T.tile_cap);
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   for (uint32_t t = gtid; t < n_tiles; t += gsz) {
-    T.slots[T.tile_slot[t]] = make_ulonglong2(TILE_EMPTY, ~0ull);
-    tile_touch[t] = 0u;
+    const uint32_t slot = T.tile_slot[t];
+    T.slots[slot] = make_ulonglong2(TILE_EMPTY, ~0ull);
+    tile_touch[slot] = 0u;
   }
   uint4* cc = reinterpret_cast<uint4*>(cell_count);
-  for (uint32_t q = gtid; q < n_ptiles * 16u; q += gsz) cc[q] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t q = gtid; q < n_ptiles * 16u; q += gsz) cc[(size_t)T.tile_slot[q >> 4] * 16u + (q & 15u)] = make_uint4(0u, 0u, 0u, 0u);
   if (prev->n_layers && !tables_fresh)
     for (uint32_t q = gtid; q < LAYER_SLOTS; q += gsz) layer_slots[q] = 0ull;
   if (gtid == 0) {
@@ -526,13 +557,13 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   // ---- tile: one table access per distinct key in the warp
   const unsigned peers = __match_any_sync(SVB_FULL, key);
   const int leader = __ffs(peers) - 1;
-  uint32_t tile = TILE_PENDING;
-  if (live && (int)lane == leader) tile = tile_find_or_insert(T, key, S);
+  uint32_t tile = ~0u;   // the tile's table slot
+  if (live && (int)lane == leader) tile = tile_slot_find_or_insert(T, key, S);
   tile = __shfl_sync(SVB_FULL, tile, leader);
   const uint32_t tm = __reduce_or_sync(peers, touch);
-  if (live && (int)lane == leader && tile != TILE_PENDING) atomicOr(&B.tile_touch[tile], tm);  // result unused: a fire-and-forget RED
-  // ---- slot in the cell: one atomic per distinct (tile, cell) in the warp
-  const bool binned = live && tile != TILE_PENDING;
+  if (live && (int)lane == leader && tile != ~0u) atomicOr(&B.tile_touch[tile], tm);  // result unused: a fire-and-forget RED
+  // ---- rank in the cell: one atomic per distinct (tile, cell) in the warp
+  const bool binned = live && tile != ~0u;
   const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : (gone ? 0xfffffffdu : 0xfffffffeu));
   const unsigned cpeers = __match_any_sync(SVB_FULL, ci);
   const int cleader = __ffs(cpeers) - 1;
@@ -546,32 +577,28 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
     B.pcell[i] = ci;
     B.prank[i] = base + __popc(cpeers & ((1u << lane) - 1u));
   }
-  // the last block to finish publishes the number of particle-owning tiles (halo tiles get ids after them)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(&S->bin_blocks_done, 1u) == gridDim.x - 1) S->n_ptiles = min(atomicAdd(&S->n_tiles, 0u), T.tile_cap);
-  }
+  if (i == 0) S->bin_blocks_done = 1u;   // "this substep was binned" (a sticky error makes the kernel return at the top instead)
 }
 
 // per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile's slot range
 // [first, end) in the binned order (S->n_live ends up as the number of binned particles), and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
 // (update_grid_nodes.rs:102-108)
-__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, const uint32_t* __restrict__ tile_touch,
-                                                 int* __restrict__ nbr) {
+__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, uint32_t* __restrict__ slot_first,
+                                                 const uint32_t* __restrict__ tile_touch, int* __restrict__ nbr) {
   if (SVB_ABORTED(S)) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n_ptiles = S->n_ptiles;
+  const uint32_t n_ptiles = min(S->n_ptiles, T.tile_cap);   // final: only k_bin creates particle tiles
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_ptiles; t += warps) {
+    const uint32_t slot = T.tile_slot[t];   // the counters of a particle tile live at its table slot
     // halo first: its table probes overlap the scan below
     int r = -1;
     if (lane == 0) r = (int)t;
-    else if (lane < 8 && ((tile_touch[t] >> lane) & 1u)) {
+    else if (lane < 8 && ((tile_touch[slot] >> lane) & 1u)) {
       const uint32_t id = tile_find_or_insert(T, tile_key_offset(T.tile_key[t], (int)lane), S);
       r = id == TILE_PENDING ? -1 : (int)id;
     }
-    const uint2 c = *reinterpret_cast<const uint2*>(cell_count + (size_t)t * 64 + 2 * lane);
+    const uint2 c = *reinterpret_cast<const uint2*>(cell_count + (size_t)slot * 64 + 2 * lane);
     const uint32_t mine = c.x + c.y;
     uint32_t inc = mine;
 #pragma unroll
@@ -580,12 +607,13 @@ __global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, ui
       if (lane >= (uint32_t)o) inc += v;
     }
     const uint32_t ex = inc - mine;
-    *reinterpret_cast<uint2*>(cell_count + (size_t)t * 64 + 2 * lane) = make_uint2(ex, ex + c.x);
+    *reinterpret_cast<uint2*>(cell_count + (size_t)slot * 64 + 2 * lane) = make_uint2(ex, ex + c.x);
     // the tile's run in the binned order: claimed from a cursor, so the runs are dense but in no particular tile order
     // (any order is a valid binning; this replaces a single-CTA scan over the tile totals and its launch)
     if (lane == 31) {
       const uint32_t first = atomicAdd(&S->n_live, inc);
       tile_range[t] = make_uint2(first, first + inc);
+      slot_first[slot] = first;
     }
     if (lane < 8) nbr[(size_t)t * 8 + lane] = r;
   }
@@ -633,14 +661,14 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* a, const uint32_t
 }
 
 // re-bin (sort.rs:91-101).  Slot of particle i in the binned order:
-//   j = tile_range[tile].x + cell_offset[tile*64 + cell] + rank      (tombstoned: n_live + rank)
+//   j = slot_first[slot] + cell_offset[slot*64 + cell] + rank      (slot = the tile's table slot; tombstoned: n_live + rank)
 // Only the inverse map src_of[j] = i is materialised here (4 B per particle).  P2G gathers its inputs
 // through it and G2P writes its results — and the fields it merely carries — to slot j of the other
 // buffer, so the physical permutation of the 136-byte state costs no pass of its own: consecutive
 // slots come from (nearly) consecutive rows of the previous order, the gathers stay coalesced.
 // The same launch also clears the grid tiles of this substep (blocks beyond the particle range).
 __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank, const uint32_t* __restrict__ cell_offset,
-                                                     const uint2* __restrict__ tile_range, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
+                                                     const uint32_t* __restrict__ slot_first, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
                                                      unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
   if (SVB_ABORTED(S)) return;
   if (blockIdx.x >= invert_blocks) {
@@ -660,7 +688,7 @@ __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S
   if (ci >= 0xfffffffdu) {
     if (ci != 0xffffffffu) return;  // migrated away (or unbinned after an abort): no slot
     j = S->n_live + prank[i];
-  } else j = tile_range[ci >> 6].x + cell_offset[ci] + prank[i];
+  } else j = slot_first[ci >> 6] + cell_offset[ci] + prank[i];
   src_of[j] = i;
 }
 // ------------------------------------------------------------------------------------------------
