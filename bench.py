@@ -50,9 +50,10 @@ A_G2P = 56.0 + 96.0
 A_GRID = 8.0
 A_NOSORT = 280.0
 A_SORT_EXTRA = 272.0
+E2E_REPEATS = 3
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
-# committed `ncu --set full` capture (profiles/r1p_top_kernels_jelly1M.txt)
-TRAFFIC = {"p2g": 125.9e6 + 3.8e6, "g2p": 100.2e6 + 94.2e6}
+# committed `ncu --set full` capture (profiles/r1r_top_kernels_jelly1M.txt)
+TRAFFIC = {"p2g": 126.0e6 + 3.9e6, "g2p": 101.0e6 + 93.1e6}
 
 
 def make_scene(name: str, scale: float, length: int = 1):
@@ -339,20 +340,24 @@ def main():
         out_buffers = Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)})
         h2d = sum(getattr(host_state.particles, f).nbytes for f in fields)
         st2 = B200State.from_io_state(host_state, fi, device=local)
-        st2.advance(None, fi, run_params(st2, 2))        # first-use costs (keyframe upload, table allocation) are session setup too
-        barrier(dist, local)
-        te = time.perf_counter()
-        st2.upload(host_state)
-        out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
-        barrier(dist, local)
-        e2e_s = time.perf_counter() - te
-        e2e_done = st2.substeps
+        st2.produce_next_state(None, fi, run_params(st2, 2), out=out_buffers)   # first-use costs (kernel loading, keyframe upload, table allocation) are session setup too
+        e2e_s = float("inf")
+        for _ in range(E2E_REPEATS):
+            barrier(dist, local)
+            te = time.perf_counter()
+            st2.upload(host_state)
+            out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
+            barrier(dist, local)
+            e2e_s = min(e2e_s, time.perf_counter() - te)
+            e2e_done = st2.substeps
         st2.close()
-        what = f"B200State.upload (H2D of the whole state, page-locked) + produce_next_state ({e2e_done} substeps + D2H of the IoState into page-locked arrays), wall clock; handle created beforehand"
+        what = (f"B200State.upload (H2D of the whole state, page-locked) + produce_next_state ({e2e_done} substeps + D2H of the IoState into page-locked arrays), wall clock, "
+                f"best of {E2E_REPEATS} (a shared host now and then stalls one pass by tens of ms); handle created beforehand")
     else:
         from squishy_volumes_b200 import slabs
         st2, inner2 = make_state(scene.io_state)       # session: communicator, mailboxes, allocations
         st2.advance(None, fi, run_params(st2, 2))
+        st2.resident()                                  # first use of the download kernels is session setup too
         hgrid = fi.consts.scaled_grid_node_size()
         local_rows, idx = slabs.split_state(scene.io_state, hgrid, st2.plan, rank)
         host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(local_rows.particles, f.name)) for f in dataclasses.fields(Particles)}))
@@ -361,17 +366,19 @@ def main():
         out_buffers = Particles(**{f.name: pinned(getattr(big, f.name)) for f in dataclasses.fields(Particles)})
         del big
         h2d = all_sum(dist, local, float(sum(getattr(host_state.particles, f).nbytes for f in fields)))   # summed over ranks
-        barrier(dist, local)
-        te = time.perf_counter()
-        st2.upload(host_state, idx)                     # H2D of this rank's slab
-        st2.advance(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
-        idx_out, rows = st2.resident(out=out_buffers)   # D2H of the rows this rank holds now
-        barrier(dist, local)
-        e2e_s = all_max(dist, local, time.perf_counter() - te)
-        e2e_done = st2.substeps
+        e2e_s = float("inf")
+        for _ in range(E2E_REPEATS):
+            barrier(dist, local)
+            te = time.perf_counter()
+            st2.upload(host_state, idx)                     # H2D of this rank's slab
+            st2.advance(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+            idx_out, rows = st2.resident(out=out_buffers)   # D2H of the rows this rank holds now
+            barrier(dist, local)
+            e2e_s = min(e2e_s, all_max(dist, local, time.perf_counter() - te))
+            e2e_done = st2.substeps
         st2.close()
         what = (f"per rank: SlabState.upload (H2D of its slab, page-locked) + {e2e_done} substeps with halo exchange and migration + D2H of the resident rows into "
-                "page-locked arrays; wall clock, max over ranks; communicator / mailboxes / handle created beforehand, host-side split and re-assembly outside")
+                f"page-locked arrays; wall clock, max over ranks, best of {E2E_REPEATS}; communicator / mailboxes / handle created beforehand, host-side split and re-assembly outside")
     d2h = h2d
     e2e = {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": d2h / e2e_done, "what": what}
 
