@@ -133,6 +133,9 @@ def cpu_leg(scene, steps: int, warmup: int, budget_s: float):
     import oracle.oracle as orc
     orc.build()
     L = orc.lib()
+    # all the host threads the box offers, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    L.svo_set_threads(int(usable))
     cores = int(L.svo_max_threads())
     o = orc.OracleState.from_io_state(scene.io_state, scene.frame_input)
     o._sync_keyframes(scene.frame_input)
