@@ -405,7 +405,6 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   // -- Collide + ExternalForce + Sort + UpdateGridNodes.  Collide / force are per particle, so running
   //    them in the pre-bin order is equivalent to the reference's Sort -> Collide -> Force.
   if (int rc = enqueue_front(h, in, /*apply_force=*/true, h->adaptive.allowed())) return rc;
-  const TileTable T = tile_table(h);
   const uint2* tile_start = h->tile_start.as<uint2>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
   const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
@@ -426,7 +425,6 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     if (rc < 0) return rc;
     if (rc == 2) return 0;  // stopped by an earlier simulation-level error; time does not advance
     if (rc == 1) {  // the binning was redone with a larger tile capacity: queue the back half again
-      const TileTable T2 = tile_table(h);
       if (int rc2 = enqueue_rebin(h)) return rc2;
       k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint2>(), h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
       LAUNCH_CHECK();
@@ -445,7 +443,6 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     if (rc == 2) return 0;
   }
   if (int rc = enqueue_rebin(h)) return rc;
-  const TileTable T2 = tile_table(h);
   tile_start = h->tile_start.as<uint2>();
   // -- LimitTimeStepBeforeForce (limit_time_step.rs:25-33)
   stage_begin(h, ST_LIMIT);
@@ -521,7 +518,6 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   }
   const uint32_t n_after = h->h_scalars->n_live + h->h_scalars->n_tomb;  // rows of migrated particles are dropped by the re-bin
   if (int rc = enqueue_rebin(h)) return rc;
-  const TileTable T = tile_table(h);
   const uint2* tile_start = h->tile_start.as<uint2>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
   const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
