@@ -37,7 +37,7 @@ def build(force: bool = False) -> str:
         subprocess.run(cmd, check=True, cwd=CSRC)
         # the compute thread's frame loop over the two C ABIs (csrc/svb_replay.cpp), linked against the library next to it
         gxx = os.environ.get("CXX", "g++")
-        subprocess.run([gxx, "-O2", "-std=c++17", os.path.join(CSRC, "svb_replay.cpp"), "-o", REPLAY_PATH, "-L" + os.path.dirname(LIB_PATH), "-lsvb200",
+        subprocess.run([gxx, "-O2", "-std=c++17", "-pthread", os.path.join(CSRC, "svb_replay.cpp"), "-o", REPLAY_PATH, "-L" + os.path.dirname(LIB_PATH), "-lsvb200",
                         "-Wl,-rpath,$ORIGIN"], check=True, cwd=CSRC)
     return LIB_PATH
 

@@ -7,10 +7,15 @@
 //
 // Exit status: 0 done, 2 simulation-level error (the failing frame is stored first, compute_thread.rs:165-169), 1 fatal.
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/svb200.h"
@@ -56,6 +61,72 @@ struct KeyframeArrays {
     k.triangle_frictions = frictions.data(); k.triangle_dampings = dampings.data();
     return 0;
   }
+};
+
+// The reference hands finished frames to a store thread (rust/crates/cache/src/store_thread.rs) so that serialising and
+// writing ~170 bytes per particle does not stall the simulation; same here: the frame loop downloads into a job, the worker
+// writes it (svbf_frame_write: temp.bin + rename, one writer at a time), at most two frames wait in the queue.
+struct FrameJob {
+  uint64_t frame = 0;
+  double time = 0;
+  uint64_t n = 0, ng = 0;
+  bool has_grid = false;
+  ParticleArrays pa;
+  GridArrays ga;
+};
+class StoreThread {
+ public:
+  explicit StoreThread(std::string dir) : dir_(std::move(dir)), worker_([this] { run(); }) {}
+  ~StoreThread() { finish(); }
+  // blocks while two frames are already waiting (back-pressure instead of unbounded host memory)
+  void push(std::unique_ptr<FrameJob> job) {
+    std::unique_lock<std::mutex> lock(m_);
+    room_.wait(lock, [this] { return queue_.size() < 2; });
+    queue_.push_back(std::move(job));
+    work_.notify_one();
+  }
+  // waits for everything queued; returns false (and the message) when a frame could not be stored
+  bool finish(std::string* message = nullptr) {
+    {
+      std::unique_lock<std::mutex> lock(m_);
+      done_ = true;
+      work_.notify_one();
+    }
+    if (worker_.joinable()) worker_.join();
+    if (message) *message = error_;
+    return error_.empty();
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      std::unique_ptr<FrameJob> job;
+      {
+        std::unique_lock<std::mutex> lock(m_);
+        work_.wait(lock, [this] { return done_ || !queue_.empty(); });
+        if (queue_.empty()) return;
+        job = std::move(queue_.front());
+        queue_.pop_front();
+        room_.notify_one();
+      }
+      char path[4096];
+      svbf_frame_path(dir_.c_str(), job->frame, path, sizeof path);
+      SvbParticles p = job->pa.view(job->n);
+      SvbGrid g = job->ga.view(job->ng);
+      uint64_t bytes = 0;
+      if (svbf_frame_write(path, nullptr, job->time, &p, job->has_grid ? &g : nullptr, &bytes)) {
+        std::lock_guard<std::mutex> lock(m_);
+        if (error_.empty()) error_ = svbf_last_error();
+      } else std::printf("stored frame %llu: %llu bytes\n", (unsigned long long)job->frame, (unsigned long long)bytes);
+    }
+  }
+  std::string dir_;
+  std::mutex m_;
+  std::condition_variable work_, room_;
+  std::deque<std::unique_ptr<FrameJob>> queue_;
+  bool done_ = false;
+  std::string error_;
+  std::thread worker_;
 };
 
 int die(const char* what, const char* detail) {
@@ -125,6 +196,7 @@ int main(int argc, char** argv) {
   KeyframeArrays ka, kb;
   uint64_t loaded_a = ~0ull;
   int status = 0;
+  StoreThread store(cache_dir);
   while (next_frame < number_of_frames) {  // :125-177
     const auto t0 = std::chrono::steady_clock::now();
     const uint64_t frame = next_frame - 1;
@@ -139,21 +211,24 @@ int main(int argc, char** argv) {
     const uint64_t substeps_before = svb_substeps(h);
     const int rc = svb_advance(h, target_time, max_time_step, adaptive, nullptr, nullptr, nullptr);
     if (rc < 0) return die("svb_advance", svb_last_error(h));
-    if (svb_download(h, &particles)) return die("svb_download", svb_last_error(h));
-    GridArrays ga;
-    SvbGrid g{};
+    std::unique_ptr<FrameJob> job(new FrameJob());
+    job->frame = next_frame;
+    job->time = svb_time(h);
+    job->n = n;
+    SvbParticles out = job->pa.view(n);
+    if (svb_download(h, &out)) return die("svb_download", svb_last_error(h));
     if (store_grid) {
       const int64_t count = svb_grid_count(h);
       if (count < 0) return die("svb_grid_count", svb_last_error(h));
-      g = ga.view((uint64_t)count);
+      job->has_grid = true;
+      job->ng = (uint64_t)count;
+      SvbGrid g = job->ga.view(job->ng);
       if (svb_download_grid(h, &g)) return die("svb_download_grid", svb_last_error(h));
     }
-    svbf_frame_path(cache_dir.c_str(), next_frame, path, sizeof path);
-    uint64_t bytes = 0;
-    if (svbf_frame_write(path, nullptr, svb_time(h), &particles, store_grid ? &g : nullptr, &bytes)) return die("store frame", svbf_last_error());  // stored even if the substep loop failed
+    store.push(std::move(job));  // stored even if the substep loop failed (compute_thread.rs:165-169)
     const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    std::printf("frame %llu of %llu: %llu substeps, %.3f s, %llu bytes%s\n", (unsigned long long)next_frame, (unsigned long long)number_of_frames,
-                (unsigned long long)(svb_substeps(h) - substeps_before), seconds, (unsigned long long)bytes, rc > 0 ? " (simulation error)" : "");
+    std::printf("frame %llu of %llu: %llu substeps, %.3f s%s\n", (unsigned long long)next_frame, (unsigned long long)number_of_frames,
+                (unsigned long long)(svb_substeps(h) - substeps_before), seconds, rc > 0 ? " (simulation error)" : "");
     if (rc > 0) {
       std::fprintf(stderr, "svb_replay: simulation-level error %d at frame %llu: %s\n", rc, (unsigned long long)next_frame, svb_last_error(h));
       status = 2;
@@ -161,6 +236,8 @@ int main(int argc, char** argv) {
     }
     ++next_frame;
   }
+  std::string store_error;
+  if (!store.finish(&store_error)) return die("store frame", store_error.c_str());
   svb_destroy(h);
   svbf_input_close(in);
   return status;
