@@ -284,41 +284,42 @@ int32_t svbf_frame_write(const char* path, const char* version, double time, con
   s.vec(p->flags, n, 1);
   s.val<uint64_t>(n);  // parameters: Vec<ParticleParameters> (particles.rs:62-84), variable length per particle
   {
-    std::vector<uint8_t> chunk;
-    chunk.reserve(1 << 20);
-    auto push = [&](const void* src, size_t k) { chunk.insert(chunk.end(), static_cast<const uint8_t*>(src), static_cast<const uint8_t*>(src) + k); };
+    // at most 29 bytes per particle: fill a fixed buffer through a raw pointer (this loop is the serial part of a frame write)
+    constexpr size_t CHUNK = 1 << 20, MAX_RECORD = 32;
+    std::vector<uint8_t> chunk(CHUNK + MAX_RECORD);
+    uint8_t* w = chunk.data();
+    auto push4 = [&w](const void* src) { std::memcpy(w, src, 4); w += 4; };
+    const uint32_t solid = 0, fluid = 1;
     for (uint64_t i = 0; i < n; ++i) {
       const uint32_t fl = p->flags[i];
-      push(&p->mass[i], 4);
-      push(&p->initial_volume[i], 4);
-      const uint8_t visc = (fl & F_USE_VISCOSITY) ? 1 : 0;  // Option<ViscosityParameters>
-      push(&visc, 1);
+      push4(&p->mass[i]);
+      push4(&p->initial_volume[i]);
+      const bool visc = (fl & F_USE_VISCOSITY) != 0;  // Option<ViscosityParameters>
+      *w++ = visc ? 1 : 0;
       if (visc) {
         const float d = p->viscosity_dynamic ? p->viscosity_dynamic[i] : 0.f, b = p->viscosity_bulk ? p->viscosity_bulk[i] : 0.f;
-        push(&d, 4);
-        push(&b, 4);
+        push4(&d);
+        push4(&b);
       }
       if (fl & F_IS_FLUID) {  // SpecificParticleParameters::Fluid { exponent: i32, bulk_modulus: f32 } = variant 1
-        const uint32_t variant = 1;
         const int32_t exponent = (int32_t)p->lambda_or_exponent[i];
-        push(&variant, 4);
-        push(&exponent, 4);
-        push(&p->mu_or_bulk_modulus[i], 4);
+        push4(&fluid);
+        push4(&exponent);
+        push4(&p->mu_or_bulk_modulus[i]);
       } else {  // Solid { mu, lambda, sand_alpha: Option<f32> } = variant 0 (also the Default)
-        const uint32_t variant = 0;
-        push(&variant, 4);
-        push(&p->mu_or_bulk_modulus[i], 4);
-        push(&p->lambda_or_exponent[i], 4);
-        const uint8_t sand = (fl & F_USE_SAND_ALPHA) ? 1 : 0;
-        push(&sand, 1);
+        push4(&solid);
+        push4(&p->mu_or_bulk_modulus[i]);
+        push4(&p->lambda_or_exponent[i]);
+        const bool sand = (fl & F_USE_SAND_ALPHA) != 0;
+        *w++ = sand ? 1 : 0;
         if (sand) {
           const float a = p->sand_alpha ? p->sand_alpha[i] : 0.f;
-          push(&a, 4);
+          push4(&a);
         }
       }
-      if (chunk.size() > (1 << 20) - 64) { s.put(chunk.data(), chunk.size()); chunk.clear(); }
+      if ((size_t)(w - chunk.data()) >= CHUNK) { s.put(chunk.data(), (size_t)(w - chunk.data())); w = chunk.data(); }
     }
-    s.put(chunk.data(), chunk.size());
+    s.put(chunk.data(), (size_t)(w - chunk.data()));
   }
   s.vec(p->elastic_energies, n, 1);
   s.vec(p->collider_bits, n, 1);
