@@ -280,6 +280,8 @@ def main():
     state, inner = make_state(scene.io_state)
     if warmup:
         state.advance(None, fi, run_params(state, warmup))   # contact has begun, buffers have settled
+    if world == 1:
+        inner.snapshot()                                      # device-side copy: the extra passes below repeat exactly the timed one
     launches0 = inner.kernel_launches
     barrier(dist, local)
     with ClockSampler(local) as clocks:
@@ -287,11 +289,16 @@ def main():
         ms = inner.last_advance_ms
         barrier(dist, local)
         gpu_launches = inner.kernel_launches - launches0
-        # keep sampling clocks over a few more identical passes so short runs still get samples
-        extra = 0
-        while len(clocks.samples) < 3 and extra < 20:
+        # the timed pass lasts a few milliseconds, one nvidia-smi query a good part of a second: keep the same load on the GPU
+        # (single GPU: the timed pass itself, restored from the snapshot) until the sampler has seen it a few times
+        extra, t_stop = 0, time.perf_counter() + 6.0
+        while len(clocks.samples) < 3 and (time.perf_counter() < t_stop if world == 1 else extra < 20):
+            if world == 1:
+                inner.restore()
             state.advance(None, fi, run_params(state, steps))
             extra += 1
+    if world == 1:
+        inner.restore()                                       # the stage pass below measures the timed pass's state as well
     done = steps
     ms_max = all_max(dist, local, ms)
     total_particles = float(scene.n)
