@@ -59,3 +59,17 @@ def test_fails_loudly_without_device(lib_path):
     sc = scenes.elastic_cube(side=4, h=0.1)
     with pytest.raises(FatalError):
         B200State.from_io_state(sc.io_state, sc.frame_input)
+
+
+def test_headers_are_plain_c(tmp_path):
+    """include/*.h is the drop-in boundary: plain C (no C++ or torch types), usable from cgo / Rust bindgen / ctypes;
+    the ctypes mirrors of the file-layer structs have the header's sizes."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text(f'#include "{root}/include/svb200.h"\n#include "{root}/include/svb_files.h"\n'
+                   "#include <stdio.h>\nint main(void){printf(\"%zu %zu %zu\\n\", sizeof(SvbfObjectDesc), sizeof(SvbfParticlesInput), sizeof(SvbfColliderInput));return 0;}\n")
+    exe = tmp_path / "hdr"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    from squishy_volumes_b200 import files
+    assert sizes == [C.sizeof(files.SvbfObjectDesc), C.sizeof(files.SvbfParticlesInput), C.sizeof(files.SvbfColliderInput)]
