@@ -58,6 +58,14 @@ struct Cursor {
     out.resize((size_t)n * per_element);
     return take(out.data(), out.size() * sizeof(T));
   }
+  // the same Vec, left where it is: element count and a pointer into the buffer
+  bool vec_view(size_t element_bytes, uint64_t& count, const uint8_t*& data) {
+    count = get<uint64_t>();
+    if (!ok || element_bytes == 0 || count > (uint64_t)(end - p) / element_bytes) { ok = false; count = 0; data = nullptr; return false; }
+    data = p;
+    p += (size_t)count * element_bytes;
+    return true;
+  }
   template <class T> bool opt_vec(bool& present, std::vector<T>& out, size_t per_element) {
     const uint8_t tag = get<uint8_t>();
     if (tag > 1) ok = false;
@@ -205,12 +213,11 @@ bool parse_frame(Cursor& c, InputFrameData& fr) {
 
 struct SvbfFrame {
   double time = 0;
-  std::vector<uint32_t> flags, bits;
-  std::vector<float> mass, volume, p0, p1, alpha, vd, vb, energies, x, F, v, C, x0;
+  std::vector<uint8_t> file;   // the whole frame file: the bulk arrays are used in place, only the parameters are unpacked
+  struct View { uint64_t count = 0; const uint8_t* data = nullptr; };
+  View flags, energies, bits, x, F, v, C, x0, node_ids, node_bits, node_masses, node_velocities;
+  std::vector<float> mass, volume, p0, p1, alpha, vd, vb;
   bool has_grid = false;
-  std::vector<int32_t> node_ids;
-  std::vector<uint32_t> node_bits;
-  std::vector<float> node_masses, node_velocities;
 };
 
 struct SvbfInput {
@@ -354,13 +361,12 @@ int32_t svbf_frame_open(const char* path, const char* version, SvbfFrame** out) 
   if (!f) return fail(SVBF_IO_ERROR, "failed to open %s: %s", path, std::strerror(errno));
   fseeko(f.get(), 0, SEEK_END);
   const uint64_t size = (uint64_t)ftello(f.get());
-  std::vector<uint8_t> buf;
-  if (int rc = read_range(f.get(), 0, size, buf, path)) return rc;
-  Cursor c(buf.data(), buf.size());
-  if (int rc = check_magic_and_version(c, FRAME_MAGIC, version, path)) return rc;
   std::unique_ptr<SvbfFrame> fr(new SvbfFrame());
+  if (int rc = read_range(f.get(), 0, size, fr->file, path)) return rc;
+  Cursor c(fr->file.data(), fr->file.size());
+  if (int rc = check_magic_and_version(c, FRAME_MAGIC, version, path)) return rc;
   fr->time = c.get<double>();
-  c.vec(fr->flags, 1);
+  c.vec_view(4, fr->flags.count, fr->flags.data);
   const uint64_t n = c.get<uint64_t>();
   if (!c.ok || n > (uint64_t)(c.end - c.p) / 17) return fail(SVBF_FORMAT, "%s: truncated or malformed particle parameters", path);
   fr->mass.resize(n); fr->volume.resize(n); fr->p0.assign(n, 0.f); fr->p1.assign(n, 0.f); fr->alpha.assign(n, 0.f); fr->vd.assign(n, 0.f); fr->vb.assign(n, 0.f);
@@ -382,50 +388,51 @@ int32_t svbf_frame_open(const char* path, const char* version, SvbfFrame** out) 
       fr->p0[i] = c.get<float>();
     } else c.ok = false;
   }
-  c.vec(fr->energies, 1);
-  c.vec(fr->bits, 1);
-  c.vec(fr->x, 3);
-  c.vec(fr->F, 9);
-  c.vec(fr->v, 3);
-  c.vec(fr->C, 9);
-  c.vec(fr->x0, 3);
+  c.vec_view(4, fr->energies.count, fr->energies.data);
+  c.vec_view(4, fr->bits.count, fr->bits.data);
+  c.vec_view(12, fr->x.count, fr->x.data);
+  c.vec_view(36, fr->F.count, fr->F.data);
+  c.vec_view(12, fr->v.count, fr->v.data);
+  c.vec_view(36, fr->C.count, fr->C.data);
+  c.vec_view(12, fr->x0.count, fr->x0.data);
   const uint8_t tag = c.get<uint8_t>();
   if (tag > 1) c.ok = false;
   fr->has_grid = tag == 1;
   if (c.ok && fr->has_grid) {
-    c.vec(fr->node_ids, 3);
-    c.vec(fr->node_bits, 1);
-    c.vec(fr->node_masses, 1);
-    c.vec(fr->node_velocities, 3);
+    c.vec_view(12, fr->node_ids.count, fr->node_ids.data);
+    c.vec_view(4, fr->node_bits.count, fr->node_bits.data);
+    c.vec_view(4, fr->node_masses.count, fr->node_masses.data);
+    c.vec_view(12, fr->node_velocities.count, fr->node_velocities.data);
   }
   if (!c.ok) return fail(SVBF_FORMAT, "%s: truncated or malformed frame body", path);
-  const size_t np = fr->flags.size();
-  if (n != np || fr->energies.size() != np || fr->bits.size() != np || fr->x.size() != 3 * np || fr->F.size() != 9 * np || fr->v.size() != 3 * np || fr->C.size() != 9 * np ||
-      fr->x0.size() != 3 * np)
+  const uint64_t np = fr->flags.count;
+  if (n != np || fr->energies.count != np || fr->bits.count != np || fr->x.count != np || fr->F.count != np || fr->v.count != np || fr->C.count != np || fr->x0.count != np)
     return fail(SVBF_FORMAT, "%s: particle arrays of different lengths", path);
   if (fr->has_grid) {
-    const size_t g = fr->node_bits.size();
-    if (fr->node_ids.size() != 3 * g || fr->node_masses.size() != g || fr->node_velocities.size() != 3 * g) return fail(SVBF_FORMAT, "%s: grid arrays of different lengths", path);
+    const uint64_t g = fr->node_bits.count;
+    if (fr->node_ids.count != g || fr->node_masses.count != g || fr->node_velocities.count != g) return fail(SVBF_FORMAT, "%s: grid arrays of different lengths", path);
   }
   *out = fr.release();
   return 0;
 }
 double svbf_frame_time(const SvbfFrame* f) { return f ? f->time : 0.0; }
-uint64_t svbf_frame_particle_count(const SvbfFrame* f) { return f ? f->flags.size() : 0; }
-int64_t svbf_frame_grid_count(const SvbfFrame* f) { return f && f->has_grid ? (int64_t)f->node_bits.size() : -1; }
+uint64_t svbf_frame_particle_count(const SvbfFrame* f) { return f ? f->flags.count : 0; }
+int64_t svbf_frame_grid_count(const SvbfFrame* f) { return f && f->has_grid ? (int64_t)f->node_bits.count : -1; }
 int32_t svbf_frame_copy(const SvbfFrame* f, SvbParticles* p, SvbGrid* grid) {
   if (!f) return fail(SVBF_BAD_ARGUMENT, "svbf_frame_copy: null frame");
-  auto cp = [](auto* dst, const auto& src) { if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(src[0])); };
+  auto view = [](void* dst, const SvbfFrame::View& v, size_t element_bytes) { if (dst && v.count) std::memcpy(dst, v.data, (size_t)v.count * element_bytes); };
+  auto column = [](float* dst, const std::vector<float>& src) { if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * 4); };
   if (p) {
-    p->n = f->flags.size();
-    cp(p->flags, f->flags); cp(p->mass, f->mass); cp(p->initial_volume, f->volume); cp(p->mu_or_bulk_modulus, f->p0); cp(p->lambda_or_exponent, f->p1);
-    cp(p->sand_alpha, f->alpha); cp(p->viscosity_dynamic, f->vd); cp(p->viscosity_bulk, f->vb); cp(p->initial_positions, f->x0); cp(p->positions, f->x);
-    cp(p->position_gradients, f->F); cp(p->velocities, f->v); cp(p->velocity_gradients, f->C); cp(p->elastic_energies, f->energies); cp(p->collider_bits, f->bits);
+    p->n = f->flags.count;
+    view(p->flags, f->flags, 4); view(p->elastic_energies, f->energies, 4); view(p->collider_bits, f->bits, 4); view(p->positions, f->x, 12);
+    view(p->position_gradients, f->F, 36); view(p->velocities, f->v, 12); view(p->velocity_gradients, f->C, 36); view(p->initial_positions, f->x0, 12);
+    column(p->mass, f->mass); column(p->initial_volume, f->volume); column(p->mu_or_bulk_modulus, f->p0); column(p->lambda_or_exponent, f->p1);
+    column(p->sand_alpha, f->alpha); column(p->viscosity_dynamic, f->vd); column(p->viscosity_bulk, f->vb);
   }
   if (grid) {
     if (!f->has_grid) return fail(SVBF_BAD_ARGUMENT, "the frame holds no grid nodes");
-    grid->n = f->node_bits.size();
-    cp(grid->node_ids, f->node_ids); cp(grid->collider_bits, f->node_bits); cp(grid->masses, f->node_masses); cp(grid->velocities, f->node_velocities);
+    grid->n = f->node_bits.count;
+    view(grid->node_ids, f->node_ids, 12); view(grid->collider_bits, f->node_bits, 4); view(grid->masses, f->node_masses, 4); view(grid->velocities, f->node_velocities, 12);
     if (grid->contributor_counts) for (uint64_t i = 0; i < grid->n; ++i) grid->contributor_counts[i] = 1;
   }
   return 0;
