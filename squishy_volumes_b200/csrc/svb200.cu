@@ -935,8 +935,12 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
   CK(cudaEventRecord(h->ev_adv[0], h->stream));
-  if (h->p2p && (size_t)h->n + 2 * h->mb_mig_cap > h->cap) {  // room for two substeps of worst-case inflow; the loop itself never resizes
-    if (int rc = resize_particles(h, ((size_t)h->n + 2 * h->mb_mig_cap) * 5 / 4)) return rc;
+  // room for the per-substep inflow (a trickle: the CFL limit keeps travel below one cell per substep); the loop itself never
+  // resizes, k_migrate_recv reports a full buffer.  Deliberately NOT sized by the mailboxes (those also serve a rebalance, which
+  // makes its own room): slab ranks launch their per-row kernels for the capacity, idle blocks are not free.
+  const size_t inflow = (size_t)h->n / 16 + 65536;
+  if (h->p2p && (size_t)h->n + 2 * inflow > h->cap) {
+    if (int rc = resize_particles(h, ((size_t)h->n + 2 * inflow) * 5 / 4)) return rc;
   }
   while (h->time < target_time) {
     if (cancel && *cancel) return fail(h, SVB_CANCELED, "The computation was canceled");
@@ -1452,6 +1456,8 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
   const int reach_hi = h->rank + 1 < h->n_ranks ? all[4 * (h->rank + 1) + 3] : new_hi;
   StepScalars* S = cur_scalars(h);
   CK(h->mig_list.ensure(2 * h->mb_mig_cap * 4));
+  CK(cudaMemcpy(&h->n, h->n_dev, 4, cudaMemcpyDeviceToHost));
+  if (int rc = resize_particles(h, (size_t)h->n + 2 * h->mb_mig_cap)) return rc;   // a rebalance may hand over whole block columns
   const MigrateCut cut{new_lo, new_hi, reach_lo, reach_hi, 4.f * (float)new_lo, 4.f * (float)new_hi, h->mig_list.as<uint32_t>(), h->p2p_local + 8, (uint32_t)h->mb_mig_cap};
   const uint32_t seq = ++h->slab_seq;
   k_note_outside<<<148 * 4, 256, 0, s>>>(h->Pc(), S, h->K.h, cut, h->n_dev);
