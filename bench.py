@@ -50,25 +50,36 @@ A_G2P = 56.0 + 96.0
 A_GRID = 8.0
 A_NOSORT = 280.0
 A_SORT_EXTRA = 272.0
-E2E_REPEATS = 3
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
-# committed `ncu --set full` capture (profiles/r1r_top_kernels_jelly1M.txt)
-TRAFFIC = {"p2g": 126.0e6 + 3.9e6, "g2p": 101.0e6 + 93.1e6}
+E2E_REPEATS = 5
+
+
+def measured_traffic(scene_name: str, particles_per_gpu: int, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from a committed `ncu --set full` capture of exactly
+    this workload (profiles/traffic.json, filled by profiles/summarize.py), or None: a number from another scene or size is
+    not this run's traffic."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None
+    hit = table.get(f"{scene_name}:{int(particles_per_gpu)}:{kernel}")
+    return float(hit["bytes"]) if hit else None
 
 
 def make_scene(name: str, scale: float, length: int = 1):
+    """The five BASELINE.json configs at `scale` times their named particle count.  The collider scenes start IN CONTACT
+    (scenes.py: `contact=True`) so that a short timed run exercises collide, meld and the return mapping, not free fall."""
     if name == "jelly_collision":
         side = max(4, int(round(80 * scale ** (1.0 / 3.0))))
         return scenes.jelly_collision(side=side, length=length)
     if name == "elastic_cube":
         return scenes.elastic_cube(side=max(4, int(round(46 * scale ** (1.0 / 3.0)))))
     if name == "sand_torus":
-        return scenes.sand_torus(side=max(8, int(round(200 * scale ** (1.0 / 3.0)))))
+        return scenes.sand_torus(side=max(8, int(round(200 * scale ** (1.0 / 3.0)))), contact=True)
     if name == "dam_break":
         s = scale ** (1.0 / 3.0)
-        return scenes.dam_break(nx=max(8, int(400 * s)), ny=max(4, int(200 * s)), nz=max(4, int(200 * s)))
+        return scenes.dam_break(nx=max(8, int(400 * s)), ny=max(4, int(200 * s)), nz=max(4, int(200 * s)), contact=True)
     if name == "mixed":
-        return scenes.mixed(side=max(16, int(round(400 * scale ** (1.0 / 3.0)))))
+        return scenes.mixed(side=max(16, int(round(400 * scale ** (1.0 / 3.0)))), contact=True)
     raise SystemExit(f"unknown scene {name}")
 
 
@@ -153,7 +164,7 @@ def cpu_leg(scene, steps: int, warmup: int, budget_s: float):
         if time.perf_counter() - t0 > budget_s:
             break
     el = time.perf_counter() - t0
-    return {"value": scene.n * done / el, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": 1e3 * el / done,
+    return {"value": scene.n * done / el, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": 1e3 * el / done, "steps_done": done,
             "sample": f"{done} substeps of the same {scene.n}-particle scene after {warmup} warm-up substeps (C++/OpenMP restatement of the reference CPU path; Rust crate not buildable here)"}
 
 
@@ -199,6 +210,48 @@ def barrier(dist, local):
     torch.cuda.synchronize(local)
 
 
+def slab_parity_check(dist, rank, world, local, fresh_unique_id):
+    """Outside the timed region: a small fast-approach jelly collision (8 192 particles, 24 substeps, particles cross every
+    cut) on the SAME `world` slab ranks against the single-GPU run of the same scene on rank 0.  Integer fields (flags,
+    collider bits, cell keys) must agree exactly, floats within the per-substep-compounded tolerance of tests/parity.py.
+    Returns the dict printed as "slab_parity" (driver-side evidence that the multi-GPU path computes the same thing)."""
+    from squishy_volumes_b200 import slabs
+    from squishy_volumes_b200.state import B200State
+    sc = scenes.jelly_collision(side=16)
+    sc.io_state.particles.velocities[:, 0] *= 6.0
+    sc.frame_input.consts.frames_per_second = 1
+    params = RunParameters(target_time=23.5 * sc.time_step, max_time_step=sc.time_step)
+    st = slabs.SlabState.from_io_state(sc.io_state, sc.frame_input, rank, world, local, fresh_unique_id())
+    err = st.advance(None, sc.frame_input, params)
+    idx, rows = st.resident()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (idx, rows, None if err is None else err.status))
+    st.close()
+    out = None
+    if rank == 0:
+        single = B200State.from_io_state(sc.io_state, sc.frame_input, device=local)
+        want, err1 = single.produce_next_state(None, sc.frame_input, params)
+        single.close()
+        got = slabs.assemble(sc.n, [(i, r) for i, r, _ in gathered], sc.io_state.particles)
+        h = sc.frame_input.consts.scaled_grid_node_size()
+        cell = lambda x: np.floor(x / np.float32(h) - np.float32(0.5)).astype(np.int32)
+        rel = {}
+        for f in ("positions", "velocities", "position_gradients", "velocity_gradients"):
+            a, b = getattr(got, f).astype(np.float64), getattr(want.particles, f).astype(np.float64)
+            rel[f] = float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+        start_owner = slabs.slab_of(sc.io_state.particles.positions, h, st.plan)
+        end_owner = np.empty(sc.n, np.int32)
+        for r, (i, _, _) in enumerate(gathered):
+            end_owner[np.asarray(i, np.int64)] = r
+        out = {"scene": f"jelly_collision side=16 ({sc.n} particles), 24 substeps, approach speed x6", "ranks": world,
+               "integer_fields_exact": bool(np.array_equal(got.flags, want.particles.flags) and np.array_equal(got.collider_bits, want.particles.collider_bits)
+                                            and np.array_equal(cell(got.positions), cell(want.particles.positions))),
+               "max_rel_err_vs_single_gpu": rel, "tolerance": 2e-3, "within_tolerance": bool(max(rel.values()) <= 2e-3),
+               "particles_that_changed_rank": int(np.count_nonzero(start_owner != end_owner)),
+               "errors": [e for _, _, e in gathered if e is not None] + ([] if err1 is None else [err1.status])}
+    return out
+
+
 def main():
     # the contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
     sys.stdout.flush()
@@ -207,38 +260,42 @@ def main():
     json_out = os.fdopen(json_fd, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=42)     # one output frame at 24 fps, dt = 1e-3
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)    # ~5 output frames at 24 fps, dt = 1e-3: a timed region of tens of milliseconds
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scene", default="jelly_collision")
     ap.add_argument("--scale", type=float, default=1.0, help="particle-count multiplier of the named scene")
-    ap.add_argument("--adaptive", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N > 1: split ONE scene of the named size over the GPUs (default for every scene but jelly_collision)")
+    ap.add_argument("--adaptive", action="store_true", help="adaptive time steps (the reference's default mode); max_time_step = 4 x the scene's fixed dt")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (development A/B runs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
 
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    if world_env > 1 and args.scene != "jelly_collision":
-        raise SystemExit("multi-GPU bench: only the jelly_collision workload is slab-decomposed here")
-    # N > 1: weak scaling — the blocks grow along x with the GPU count, the slab decomposition cuts them on
-    # block planes, neighbours exchange grid-halo sums after P2G and migrating particles after the advance.
-    scene = make_scene(args.scene, args.scale, length=world_env)
+    # N > 1.  jelly_collision (the default workload): weak scaling — the blocks grow along x with the GPU count, 1.02 M particles
+    # per GPU.  Every other scene, or --strong: ONE scene of the named size is cut into N slabs (BASELINE configs 4 and 5).
+    weak = world_env > 1 and args.scene == "jelly_collision" and not args.strong
+    scene = make_scene(args.scene, args.scale, length=world_env if weak else 1)
     scene.frame_input.consts.frames_per_second = 1  # one long frame: the bench never crosses a keyframe boundary
     dt = scene.time_step
+    max_dt = 4.0 * dt if args.adaptive else dt
+    state_mb = scene.n / max(world_env, 1) * 136 / 1e6
     config = {"workload": f"{args.scene}: {scene.description}", "particles_total": scene.n, "particles_per_gpu": scene.n // max(world_env, 1),
-              "time_step": dt, "adaptive_time_steps": bool(args.adaptive),
+              "time_step": dt, "adaptive_time_steps": bool(args.adaptive), "max_time_step": max_dt,
               "rebin": "every substep (counting sort on (tile, cell); the physical permutation rides on the G2P write)",
-              "l2": "state (>= 136 B/particle * 1.02 M = 139 MB + grid) exceeds the 126 MB L2; no explicit flush",
-              "decomposition": "single GPU" if world_env == 1 else f"{world_env} slabs along x; halo-column sums + particle migration every substep over peer memory (NVLink, CUDA IPC), NCCL fallback"}
+              "l2": f"per-GPU particle state {state_mb:.0f} MB (136 B/particle) + grid vs the 126 MB L2: " + ("larger than L2, no explicit flush" if state_mb > 126 else "NOT larger than L2 - the HBM fractions of this run are partly L2 numbers"),
+              "decomposition": "single GPU" if world_env == 1 else f"{world_env} slabs along x ({'weak: the scene grows with N' if weak else 'strong: one scene split N ways'}); halo-column sums + particle migration every substep over peer memory (NVLink, CUDA IPC), NCCL fallback"}
+    scaling = "weak" if (weak or world_env == 1) else "strong"
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         if rank != 0:
             return 0
-        leg = cpu_leg(scene, steps, min(warmup, 2), budget_s=150.0)
-        line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-                "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        leg = cpu_leg(scene, steps, warmup, budget_s=150.0)
+        line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": leg["steps_done"], "warmup": warmup,
+                "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line), file=json_out, flush=True)
@@ -253,7 +310,8 @@ def main():
     t0 = scene.io_state.time
 
     def run_params(state, k):
-        return RunParameters(target_time=state.time + (k - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive)
+        # fixed dt: exactly k substeps.  adaptive: the same simulated time span, however many substeps the limits make of it
+        return RunParameters(target_time=state.time + ((k - 0.5) * dt if not args.adaptive else k * dt), max_time_step=max_dt, adaptive_time_steps=args.adaptive)
 
     def fresh_unique_id():
         """An NCCL unique id serves one communicator: every slab state gets its own, handed over by rank 0."""
@@ -276,6 +334,8 @@ def main():
         st = slabs.SlabState.from_io_state(io_state, fi, rank, world, local, fresh_unique_id())
         return st, st.inner
 
+    slab_parity = slab_parity_check(dist, rank, world, local, fresh_unique_id) if world > 1 else None
+
     # ---------------- device-resident throughput
     state, inner = make_state(scene.io_state)
     if warmup:
@@ -283,31 +343,34 @@ def main():
     if world == 1:
         inner.snapshot()                                      # device-side copy: the extra passes below repeat exactly the timed one
     launches0 = inner.kernel_launches
+    sub0 = state.substeps
     barrier(dist, local)
     with ClockSampler(local) as clocks:
         state.advance(None, fi, run_params(state, steps))
         ms = inner.last_advance_ms
+        done = state.substeps - sub0
         barrier(dist, local)
         gpu_launches = inner.kernel_launches - launches0
-        # the timed pass lasts a few milliseconds, one nvidia-smi query a good part of a second: keep the same load on the GPU
+        # the timed pass lasts tens of milliseconds, one nvidia-smi query a good part of a second: keep the same load on the GPU
         # (single GPU: the timed pass itself, restored from the snapshot) until the sampler has seen it a few times
         extra, t_stop = 0, time.perf_counter() + 6.0
-        while len(clocks.samples) < 3 and (time.perf_counter() < t_stop if world == 1 else extra < 20):
+        while len(clocks.samples) < 3 and (time.perf_counter() < t_stop if world == 1 else extra < 10):
             if world == 1:
                 inner.restore()
             state.advance(None, fi, run_params(state, steps))
             extra += 1
     if world == 1:
         inner.restore()                                       # the stage pass below measures the timed pass's state as well
-    done = steps
     ms_max = all_max(dist, local, ms)
     total_particles = float(scene.n)
     value = total_particles * done / (ms_max * 1e-3)
 
     # ---------------- per-stage pass (instrumented: one event pair + sync per stage) -> roofline
     inner.enable_stage_timing(True)
+    sub1 = state.substeps
     state.advance(None, fi, run_params(state, steps))
-    stages = {k: v / steps for k, v in inner.stage_times().items()}
+    stage_steps = max(state.substeps - sub1, 1)
+    stages = {k: v / stage_steps for k, v in inner.stage_times().items()}
     inner.enable_stage_timing(False)
     stages_by_rank = None
     if dist is not None:
@@ -320,17 +383,54 @@ def main():
     alg_bytes = n_local * ((A_P2G if dom == "p2g" else A_G2P) + A_GRID / 2)
     dom_ms = max(stages.get(dom, 0.0), 1e-9)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    whole = scene.n * (A_NOSORT + A_SORT_EXTRA) / (ms_max / done * 1e-3) / 1e9
+    sub_s = ms_max / done * 1e-3
+    whole_nosort = scene.n * A_NOSORT / sub_s / 1e9
+    whole_rebin = scene.n * (A_NOSORT + A_SORT_EXTRA) / sub_s / 1e9
+    other = "g2p" if dom == "p2g" else "p2g"
+    other_bytes = n_local * ((A_P2G if other == "p2g" else A_G2P) + A_GRID / 2)
+    other_ms = max(stages.get(other, 0.0), 1e-9)
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": TRAFFIC.get(dom), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
-                "whole_substep": {"algorithmic_bytes": scene.n * (A_NOSORT + A_SORT_EXTRA), "achieved": whole, "frac": whole / (peak * world)},
+                "frac": achieved / peak, "traffic": measured_traffic(args.scene, scene.n // world, "k_" + dom),
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
+                "second_kernel": {"kernel": "k_" + other, "achieved": other_bytes / (other_ms * 1e-3) / 1e9, "frac": other_bytes / (other_ms * 1e-3) / 1e9 / peak,
+                                  "algorithmic_bytes_per_launch": other_bytes, "launch_ms": other_ms, "traffic": measured_traffic(args.scene, scene.n // world, "k_" + other)},
+                "whole_substep": {"algorithmic_bytes_compulsory": scene.n * A_NOSORT, "achieved": whole_nosort, "frac": whole_nosort / (peak * world),
+                                  "note": "A_nosort = 280 B per particle-substep (SURVEY.md 8d); the design performs no separate re-sort pass",
+                                  "with_rebin_credit": {"algorithmic_bytes": scene.n * (A_NOSORT + A_SORT_EXTRA), "achieved": whole_rebin, "frac": whole_rebin / (peak * world),
+                                                        "note": "credits the 272 B a separate physical re-sort every substep would move (SURVEY.md 8d A_sort); shown for comparison only"}},
                 "stage_ms_per_substep": stages, "stage_note": "rank 0, instrumented pass (one event pair and a sync per stage)"}
     if stages_by_rank is not None:
         roofline["stage_ms_per_substep_by_rank"] = stages_by_rank   # exchange stages include the wait for the neighbour
     state.close()
 
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": int(done), "warmup": warmup, "ms_per_step": ms_max / done, "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "roofline": roofline, "gpu_launches": int(gpu_launches),
+            "clocks": clocks.summary()}
+    if slab_parity is not None or world > 1:
+        line["slab_parity"] = slab_parity
+
     # ---------------- end to end through the public API with host buffers (page-locked, as the contract asks)
+    if not args.no_e2e:
+        line["e2e"] = e2e_leg(args, scene, fi, dist, rank, world, local, make_state, run_params, steps, dt, max_dt, t0, total_particles)
+    if rank == 0 and not args.no_cpu:
+        leg = cpu_leg(scene, 1000, 2, budget_s=args.cpu_budget)
+        line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if dist is not None:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), file=json_out, flush=True)
+    return 0
+
+
+def e2e_leg(args, scene, fi, dist, rank, world, local, make_state, run_params, steps, dt, max_dt, t0, total_particles):
+    """Same metric through the public API with HOST buffers: every pass uploads the IoState (H2D from page-locked memory), runs the
+    substeps and downloads the IoState (D2H into page-locked memory).  The handle (device allocations, and for N > 1 the NCCL
+    communicator + CUDA-IPC mailboxes) is session setup, like the CUDA context: it is created before the clock starts.
+    Reported: the MEDIAN of E2E_REPEATS passes (wall clock, max over ranks)."""
     import dataclasses
+    import torch
+    from squishy_volumes_b200.state import B200State
     from squishy_volumes_b200.types import IoState, Particles
     keep = []
 
@@ -342,27 +442,26 @@ def main():
         return v
     fields = ("flags", "mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha", "viscosity_dynamic", "viscosity_bulk", "positions",
               "position_gradients", "velocities", "velocity_gradients", "elastic_energies", "collider_bits")
-    # The handle (device allocations, and for N > 1 the NCCL communicator + CUDA-IPC mailboxes) is session setup, like the
-    # CUDA context: it is created before the clock starts.  Timed, like one output frame of the compute thread:
-    # from_io_state into that handle (H2D of the state from page-locked memory) -> the substeps -> to_io_state (D2H).
+    target = t0 + ((steps - 0.5) * dt if not args.adaptive else steps * dt)
+    params = RunParameters(target_time=target, max_time_step=max_dt, adaptive_time_steps=args.adaptive)
+    times = []
     if world == 1:
         host_state = IoState(scene.io_state.time, Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)}))
         out_buffers = Particles(**{f.name: pinned(getattr(scene.io_state.particles, f.name)) for f in dataclasses.fields(Particles)})
         h2d = sum(getattr(host_state.particles, f).nbytes for f in fields)
         st2 = B200State.from_io_state(host_state, fi, device=local)
         st2.produce_next_state(None, fi, run_params(st2, 2), out=out_buffers)   # first-use costs (kernel loading, keyframe upload, table allocation) are session setup too
-        e2e_s = float("inf")
         for _ in range(E2E_REPEATS):
             barrier(dist, local)
             te = time.perf_counter()
             st2.upload(host_state)
-            out, err = st2.produce_next_state(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive), out=out_buffers)
+            out, err = st2.produce_next_state(None, fi, params, out=out_buffers)
             barrier(dist, local)
-            e2e_s = min(e2e_s, time.perf_counter() - te)
+            times.append(time.perf_counter() - te)
             e2e_done = st2.substeps
         st2.close()
         what = (f"B200State.upload (H2D of the whole state, page-locked) + produce_next_state ({e2e_done} substeps + D2H of the IoState into page-locked arrays), wall clock, "
-                f"best of {E2E_REPEATS} (a shared host now and then stalls one pass by tens of ms); handle created beforehand")
+                f"median of {E2E_REPEATS} passes; handle created beforehand")
     else:
         from squishy_volumes_b200 import slabs
         st2, inner2 = make_state(scene.io_state)       # session: communicator, mailboxes, allocations
@@ -376,34 +475,21 @@ def main():
         out_buffers = Particles(**{f.name: pinned(getattr(big, f.name)) for f in dataclasses.fields(Particles)})
         del big
         h2d = all_sum(dist, local, float(sum(getattr(host_state.particles, f).nbytes for f in fields)))   # summed over ranks
-        e2e_s = float("inf")
         for _ in range(E2E_REPEATS):
             barrier(dist, local)
             te = time.perf_counter()
             st2.upload(host_state, idx)                     # H2D of this rank's slab
-            st2.advance(None, fi, RunParameters(target_time=t0 + (steps - 0.5) * dt, max_time_step=dt, adaptive_time_steps=args.adaptive))
+            st2.advance(None, fi, params)
             idx_out, rows = st2.resident(out=out_buffers)   # D2H of the rows this rank holds now
             barrier(dist, local)
-            e2e_s = min(e2e_s, all_max(dist, local, time.perf_counter() - te))
+            times.append(all_max(dist, local, time.perf_counter() - te))
             e2e_done = st2.substeps
         st2.close()
         what = (f"per rank: SlabState.upload (H2D of its slab, page-locked) + {e2e_done} substeps with halo exchange and migration + D2H of the resident rows into "
-                f"page-locked arrays; wall clock, max over ranks, best of {E2E_REPEATS}; communicator / mailboxes / handle created beforehand, host-side split and re-assembly outside")
-    d2h = h2d
-    e2e = {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": d2h / e2e_done, "what": what}
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": done, "warmup": warmup, "ms_per_step": ms_max / done, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "roofline": roofline, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "clocks": clocks.summary()}
-    if rank == 0 and not args.no_cpu:
-        leg = cpu_leg(scene, 1000, 2, budget_s=args.cpu_budget)
-        line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    if dist is not None:
-        dist.barrier(device_ids=[local])
-        dist.destroy_process_group()
-    if rank == 0:
-        print(json.dumps(line), file=json_out, flush=True)
-    return 0
+                f"page-locked arrays; wall clock, max over ranks, median of {E2E_REPEATS} passes; communicator / mailboxes / handle created beforehand, host-side split and re-assembly outside")
+    e2e_s = float(np.median(times))
+    return {"value": total_particles * e2e_done / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / e2e_done, "d2h_bytes_per_step": h2d / e2e_done, "what": what,
+            "seconds_per_pass": [round(t, 5) for t in times]}
 
 
 if __name__ == "__main__":

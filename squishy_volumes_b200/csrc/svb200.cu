@@ -110,6 +110,8 @@ struct SvbHandle {
   uint32_t* p2p_local = nullptr;        // device scratch of the sending kernels (slot counters, blocks done)
 
   double time = 0;
+  double time_before_last = 0;      // clock before the most recent substep (taken back when that substep turns out to have failed)
+  bool failed_rolled_back = false;
   svbh::AdaptiveTimeStep adaptive;
   uint64_t substeps = 0;
   uint32_t status = 0;
@@ -297,6 +299,16 @@ int enqueue_rebin(SvbHandle* h) {
   return 0;
 }
 
+// The substep that raised a simulation-level error does not count: the reference returns from the failing phase without cycling it
+// or advancing the clock (cpu/src/cpu_state.rs:176-190), so the stored frame carries the time BEFORE that substep.  The device
+// finishes the failing substep (the error is only seen afterwards), hence the host takes its bookkeeping back, once.
+void rollback_failed_substep(SvbHandle* h) {
+  if (h->failed_rolled_back || h->substeps == 0) return;
+  h->time = h->time_before_last;
+  --h->substeps;
+  h->failed_rolled_back = true;
+}
+
 // wait for the front half's scalars; on tile overflow grow the capacity and redo the binning
 // (the state is only rewritten by G2P, and k_invert / P2G / G2P no-op on overflow)
 int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
@@ -304,16 +316,18 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
     CK(cudaEventSynchronize(h->ev_front));
     const StepScalars& r = *h->h_scalars;
     if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys");
+    if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW)) return fail(h, SVB_COMM_ERROR, "slab exchange failed in an earlier substep (status 0x%x)", r.status);
     if (r.sticky) {  // the previous substep failed: this one was a no-op on the device
-      h->status |= r.sticky & 0xffffu;
+      h->status |= (r.sticky | r.accum) & 0xffffu;
       if (back_enqueued) { CK(cudaStreamSynchronize(h->stream)); h->cur ^= 1; }
+      rollback_failed_substep(h);
       return 2;
     }
     if (!(r.status & ST_TILE_OVERFLOW)) {
       h->n_tiles = r.n_tiles;
       h->n_ptiles = r.n_ptiles;
       h->n_live = r.n_live;
-      h->status |= r.status & 0xffffu;
+      h->status |= (r.status | r.accum) & 0xffffu;
       return back_enqueued ? 0 : 1;  // 1: caller still has to enqueue the back half
     }
     if (attempt > 8) return fail(h, SVB_CUDA_ERROR, "tile capacity did not settle");
@@ -397,6 +411,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
     return h->p2p ? substep_slab_p2p(h, in) : substep_slab(h, in);
   }
   if (n == 0) {
+    h->time_before_last = h->time;
     h->time += (double)h->adaptive.allowed();
     ++h->substeps;
     return 0;
@@ -431,6 +446,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
       if (int rc2 = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc2;
     }
     h->have_grid = true;
+    h->time_before_last = h->time;
     h->time += (double)dt;
     ++h->substeps;
     return 0;
@@ -490,6 +506,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   LAUNCH_CHECK();
   stage_end(h);
   h->have_grid = true;
+  h->time_before_last = h->time;
   h->time += (double)h->adaptive.allowed();
   ++h->substeps;
   return 0;
@@ -543,6 +560,7 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   stage_end(h);
   h->status |= h->h_counts[8] & 0xffffu;
   h->have_grid = true;
+  h->time_before_last = h->time;
   h->time += (double)dt;
   ++h->substeps;
   return 0;
@@ -624,19 +642,25 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   const StepScalars& r = *h->h_scalars;
   if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys");
   if (r.status & ST_TILE_OVERFLOW) return fail(h, SVB_COMM_ERROR, "tile capacity exceeded on a slab rank (%u tiles > %zu)", r.n_tiles, h->tile_cap);
-  if (r.sticky) {  // the previous substep failed somewhere: this one was a no-op on every rank
-    h->status |= r.sticky & 0xffffu;
+  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))   // raised by an earlier substep's back half and carried forward by k_begin
+    return fail(h, SVB_COMM_ERROR, r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
+  if (r.sticky) {  // the previous substep failed somewhere: this one was a no-op on every rank (the queued G2P wrote nothing: undo the buffer swap)
+    h->status |= (r.sticky | r.accum) & 0xffffu;
+    CK(cudaStreamSynchronize(s));
+    h->cur ^= 1;
+    rollback_failed_substep(h);
     return 0;
   }
   h->n_tiles = r.n_tiles;
   h->n_ptiles = r.n_ptiles;
   h->n_live = r.n_live;
-  h->status |= r.status & 0xffffu;
+  h->status |= (r.status | r.accum) & 0xffffu;
   if (((size_t)r.n_tiles + h->halo_margin) * 3 / 2 > h->tile_cap) {  // grow ahead of need: an overflow cannot be redone once messages are out
     CK(cudaStreamSynchronize(s));
     if (int rc = ensure_tile_capacity(h, ((size_t)r.n_tiles + h->halo_margin) * 3)) return rc;
   }
   h->have_grid = true;
+  h->time_before_last = h->time;
   h->time += (double)dt;
   ++h->substeps;
   return 0;
@@ -687,7 +711,8 @@ int read_status(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  h->status |= (h->h_scalars->status | h->h_scalars->sticky) & 0xffffu;
+  h->status |= (h->h_scalars->status | h->h_scalars->sticky | h->h_scalars->accum) & 0xffffu;
+  if (h->h_scalars->sticky) rollback_failed_substep(h);   // the failing substep was the last one queued
   return 0;
 }
 
@@ -755,7 +780,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(h->layer_slots.ensure(LAYER_SLOTS * 8));
   CK(h->layer_list.ensure(LAYER_SLOTS * 4));
   CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, h->stream));
-  CK(cudaMemsetAsync(h->pbuf[0].p, 0, h->cap * NFIELDS * 4, h->stream));
+  for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->pbuf[b].p, 0, h->cap * NFIELDS * 4, h->stream));
   CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
   if (int rc = ensure_tile_capacity(h, (size_t)n / 96 + 2048)) return rc;
 
@@ -801,11 +826,13 @@ int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
   const size_t need = h->slabs ? (size_t)n * 3 / 2 + 65536 : (size_t)std::max<uint32_t>(n, 1);
   if (int rc = resize_particles(h, need)) return rc;
   h->n = n;
-  CK(cudaMemsetAsync(h->pbuf[h->cur].p, 0, h->cap * NFIELDS * 4, h->stream));
+  for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->pbuf[b].p, 0, h->cap * NFIELDS * 4, h->stream));
   CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
   if (int rc = load_particles(h, p)) return rc;
   // a new state starts a new run: clock, step history, error words, per-substep tables
   h->time = time;
+  h->time_before_last = time;
+  h->failed_rolled_back = false;
   h->substeps = 0;
   h->status = 0;
   h->adaptive = svbh::AdaptiveTimeStep();
@@ -930,8 +957,9 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   {  // a new advance starts without status bits; the tile bookkeeping of the last substep stays (k_begin undoes it)
     StepScalars* S = cur_scalars(h);
     CK(cudaMemsetAsync(&S->status, 0, 4, h->stream));
-    CK(cudaMemsetAsync(&S->sticky, 0, 4, h->stream));
+    CK(cudaMemsetAsync(&S->sticky, 0, 8, h->stream));   // sticky + accum
   }
+  h->failed_rolled_back = false;
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
   CK(cudaEventRecord(h->ev_adv[0], h->stream));
@@ -966,6 +994,8 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
 
 int32_t svb_download(SvbHandle* h, SvbParticles* out) {
   if (!h || !out) return SVB_BAD_ARGUMENT;
+  // slab ranks hold rows of the GLOBAL particle order (and F_GONE rows): the original-order scatter below would leave its buffers
+  if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_download needs the whole particle set on one device: use svb_download_resident on a slab rank");
   if (int rc = set_device(h)) return rc;
   const uint32_t n = h->n;
   out->n = n;
@@ -1126,6 +1156,7 @@ void svb_set_option(SvbHandle* h, const char* name, double value) {
 
 int32_t svb_snapshot(SvbHandle* h) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points (a slab rank's row count lives on the device)");
   if (int rc = set_device(h)) return rc;
   CK(h->snap_p.ensure(h->cap * NFIELDS * 4));
   CK(h->snap_e.ensure(h->cap * 4));
@@ -1141,6 +1172,7 @@ int32_t svb_snapshot(SvbHandle* h) {
 }
 int32_t svb_restore(SvbHandle* h) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points (a slab rank's row count lives on the device)");
   if (!h->have_snapshot) return fail(h, SVB_BAD_ARGUMENT, "svb_restore without svb_snapshot");
   if (int rc = set_device(h)) return rc;
   CK(cudaMemcpyAsync(h->pbuf[h->cur].p, h->snap_p.p, h->cap * NFIELDS * 4, cudaMemcpyDeviceToDevice, h->stream));

@@ -109,7 +109,12 @@ struct StepScalars {
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;
   uint32_t sticky;     // simulation-level error bits that stop the run (SVB_PARTICLE_CLOSE_TO_INVERTED); survives the per-substep reset
+  uint32_t accum;      // simulation-level bits (SVB_TABLE_*) of the EARLIER substeps of this svb_advance call: k_begin folds the previous
+                       // substep's status word in here, so a bit set in any substep's back half reaches the host at the end of the call
 };
+// abort bits that stay set once raised: every later substep of the call is a no-op and the host reports a fatal error.  (A tile
+// overflow is not carried: the host grows the tables and redoes the binning.)
+constexpr uint32_t ST_CARRY_MASK = ST_KEY_RANGE | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW;
 #define SVB_ABORTED(S) (((S)->status & ST_ABORT_MASK) || (S)->sticky)
 
 struct MeshDev {

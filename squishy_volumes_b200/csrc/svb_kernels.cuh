@@ -499,6 +499,8 @@ __global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ p
     z.n = n_dev ? min(*n_dev, n) : n;   // slab ranks: the row count lives on the device (migration changes it without the host)
     z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
     z.sticky = prev->sticky;
+    z.accum = prev->accum | (prev->status & 0xffffu);
+    z.status = prev->status & ST_CARRY_MASK;
     *cur = z;
   }
 }

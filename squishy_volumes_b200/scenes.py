@@ -197,12 +197,14 @@ def jelly_collision(side: int = 80, h: float = 0.04, n_keyframes: int = 4, lengt
                  f"{p.n}-particle two-block Neo-Hookean collision (E=1e4 / 1e5), h={h}, no collider")
 
 
-def sand_torus(side: int = 200, h: float = 0.04, n_keyframes: int = 4) -> Scene:
-    """Config 3: sand block (Drucker-Prager return mapping) falling onto a torus mesh collider."""
+def sand_torus(side: int = 200, h: float = 0.04, n_keyframes: int = 4, contact: bool = False) -> Scene:
+    """Config 3: sand block (Drucker-Prager return mapping) falling onto a torus mesh collider.
+    `contact`: the block starts half a cell INTO the top of the torus at 8 m/s, so that the first substeps already
+    classify sides, push particles out and yield (the full-size measurements are short runs)."""
     sp = h / 2
     L = side * sp
-    pos = lattice((side,) * 3, sp, (-L / 2, -L / 2, 0.0))
-    p = make_particles(pos, sp, Material("sand", 1600.0, 1e6, 0.3, sand_alpha=0.3), velocity=(0, 0, -1.0))
+    pos = lattice((side,) * 3, sp, (-L / 2, -L / 2, -3.0 * h if contact else 0.0))
+    p = make_particles(pos, sp, Material("sand", 1600.0, 1e6, 0.3, sand_alpha=0.3), velocity=(0, 0, -8.0 if contact else -1.0))
     torus = torus_mesh(0.35 * L, 0.12 * L, 48, 24, center=(0, 0, -0.12 * L - 2.5 * h))
     fi = _frame_input(_consts(h, 100.0), [torus], p.n, (0, 0, -9.8), [0.4], [0.0], n_keyframes)
     return Scene("sand_torus", IoState(0.0, p), fi, 1e-4,
@@ -210,25 +212,28 @@ def sand_torus(side: int = 200, h: float = 0.04, n_keyframes: int = 4) -> Scene:
 
 
 def dam_break(nx: int = 400, ny: int = 200, nz: int = 200, h: float = 0.04, n_keyframes: int = 4,
-              viscous: bool = False) -> Scene:
-    """Config 4: weakly compressible fluid column inside a closed box collider."""
+              viscous: bool = False, contact: bool = False) -> Scene:
+    """Config 4: weakly compressible fluid column inside a closed box collider.
+    `contact`: the box hugs the column (0.1 h instead of 3 h of clearance) and the column moves at (2, 0, -6) m/s, so that
+    the walls are within the collider's accept distance from the first substep and particles cross them within ten."""
     sp = h / 2
     lo = (-nx * sp, -ny * sp / 2, 0.0)
     pos = lattice((nx, ny, nz), sp, lo)
     mat = Material("fluid", 1000.0, bulk_modulus=1000.0, exponent=7, viscosity=(0.5, 0.1) if viscous else None)
-    p = make_particles(pos, sp, mat)
-    m = 3 * h
+    p = make_particles(pos, sp, mat, velocity=(2.0, 0.0, -6.0) if contact else (0.0, 0.0, 0.0))
+    m = (0.1 if contact else 3.0) * h
     box = box_mesh((lo[0] - m, lo[1] - m, lo[2] - m), (lo[0] + 2 * nx * sp + m, lo[1] + ny * sp + m, nz * sp * 1.5), inward=True)
     fi = _frame_input(_consts(h, 100.0), [box], p.n, (0, 0, -9.8), [0.0], [0.0], n_keyframes)
     return Scene("dam_break", IoState(0.0, p), fi, 2e-4,
                  f"{p.n}-particle weakly compressible dam break (K=1000, gamma=7) in a box collider, h={h}")
 
 
-def mixed(side: int = 400, h: float = 0.04, brick: int = 16, n_keyframes: int = 4) -> Scene:
-    """Config 5: interleaved bricks, half Neo-Hookean, quarter sand, quarter fluid; plane + torus colliders."""
+def mixed(side: int = 400, h: float = 0.04, brick: int = 16, n_keyframes: int = 4, contact: bool = False) -> Scene:
+    """Config 5: interleaved bricks, half Neo-Hookean, quarter sand, quarter fluid; plane + torus colliders.
+    `contact`: the block starts 0.1 h above the plane (overlapping the top of the torus) at 4 m/s."""
     sp = h / 2
     L = side * sp
-    pos = lattice((side,) * 3, sp, (-L / 2, -L / 2, 0.0))
+    pos = lattice((side,) * 3, sp, (-L / 2, -L / 2, -3.15 * h if contact else 0.0))
     n = pos.shape[0]
     ii = (np.arange(side) // brick)
     code = (ii[:, None, None] + ii[None, :, None] + ii[None, None, :]).reshape(-1) % 4  # 0,1 solid; 2 sand; 3 fluid
@@ -238,7 +243,7 @@ def mixed(side: int = 400, h: float = 0.04, brick: int = 16, n_keyframes: int = 
                    (2, Material("sand", 1600.0, 1e5, 0.3, sand_alpha=0.3)), (3, Material("fluid", 1000.0, bulk_modulus=1000.0, exponent=7))):
         sel = np.nonzero(code == c)[0]
         order.append(sel)
-        parts.append(make_particles(pos[sel], sp, mat, velocity=(0, 0, -0.5)))
+        parts.append(make_particles(pos[sel], sp, mat, velocity=(0, 0, -4.0 if contact else -0.5)))
     p = Particles.concatenate(parts)
     inv = np.argsort(np.concatenate(order), kind="stable")
     p = p.select(inv)  # back to lattice order so the input is spatially coherent like a Blender capture

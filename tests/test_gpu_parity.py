@@ -124,6 +124,9 @@ def test_golden_runs(name):
         err_abs, scale = parity.field_error(getattr(p, f), gold[f], ok)
         scale = max(scale, scale_floor)
         assert err_abs <= parity.ATOL + parity.RTOL_RUN * scale, (f, err_abs, scale)
+    # every live particle — the few with a flipped side bit included — under the per-particle percentile bounds
+    rep = parity.assert_percentiles(p, gold, hh, parity.PCT_RUN, live, label=name)
+    print(name, "bit mismatches", mism_bits, "percentiles", rep)
     ids, bits = g.active_blocks()
     got_blocks = np.unique(np.concatenate([ids, bits[:, None].astype(np.int32)], axis=1), axis=0)
     if mism_bits == 0:

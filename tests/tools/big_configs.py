@@ -58,6 +58,12 @@ def run(name, scale, steps=10, warm=3):
     assert det.min() > 0
     out["active_blocks"] = int(ids.shape[0])
     out["collider_layers"] = int(np.unique(bits).shape[0])
+    # the scene starts in contact (scenes.py contact=True): colliders are near from the first substep, material deforms / yields
+    out["particles_near_a_collider"] = int(np.count_nonzero(p1.collider_bits))
+    dF = p1.position_gradients.reshape(-1, 9) - np.eye(3, dtype=np.float32).reshape(9)
+    out["particles_deformed"] = int(np.count_nonzero(np.abs(dF).max(axis=1) > 1e-3))
+    if name != "jelly_collision":
+        assert out["collider_layers"] > 1 and out["particles_near_a_collider"] > 0 and out["particles_deformed"] > 0, out
     out["max_speed"] = float(np.linalg.norm(p1.velocities[live], axis=1).max())
     g.close()
     return out
