@@ -63,12 +63,20 @@ struct SvbHandle {
   int cur = 0;
   DevBuf energy;
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
-  // binning scratch + tile table (rebuilt every substep)
-  DevBuf pcell, prank, src_of, table_slots, tile_key, tile_slot, tile_touch, cell_count, slot_first, tile_start, nbr, grid, melded, node_mask, node_offset, scratch;
+  // binning scratch + the two alternating "front sets" of per-substep tile bookkeeping (svb_kernels.cuh: reset_set): substep n runs on
+  // set n % 2 while its G2P already bins the advanced positions into the other one
+  DevBuf pcell, prank, src_of, grid, melded, node_mask, node_offset, scratch;
+  struct FrontBufs {
+    DevBuf table_slots, tile_key, tile_slot, tile_touch, cell_count, slot_first, tile_start, nbr;
+    bool fresh = true;      // (re)allocated: memset once before its next use, later uses undo only what they left
+  } fs[2];
   size_t tile_cap = 0;      // tiles the per-tile arrays can hold
-  bool tables_fresh = true; // tables were (re)allocated: memset them once, later substeps undo only what they used
-  int s_cur = 0;            // half of the scalars double buffer this substep writes
+  int s_cur = 0;            // front set and half of the scalars double buffer of the substep being queued / last completed
+  bool binned_ahead = false;  // the OTHER set holds the bins of the current particle state (filled by the last G2P / advance)
+  bool limits_ahead = false;  // DtState::next_* hold LimitTimeStepBeforeForce's reductions of the current particle state
   uint32_t table_mask = 0;  // open-addressing slots - 1
+  DevBuf dt_state;          // DtState: adaptive time stepping on the device
+  DtState* h_dt = nullptr;  // pinned lagged copy
   DevBuf scalars, layer_slots, layer_list;
   StepScalars* h_scalars = nullptr;  // pinned
   cudaEvent_t ev_front = nullptr;
@@ -112,6 +120,7 @@ struct SvbHandle {
   double time = 0;
   double time_before_last = 0;      // clock before the most recent substep (taken back when that substep turns out to have failed)
   bool failed_rolled_back = false;
+  uint32_t stop_bits = 0;           // sticky word (errors | ST_STOP_*) that ended the last substep loop
   svbh::AdaptiveTimeStep adaptive;
   uint64_t substeps = 0;
   uint32_t status = 0;
@@ -184,26 +193,29 @@ int upload_array(SvbHandle* h, DevBuf& b, const void* src, size_t bytes) {
   return 0;
 }
 
-// tile capacity: per-tile arrays + an open-addressing table at <= 25 % load
+// tile capacity: per-tile arrays + an open-addressing table at <= 25 % load, for both front sets
 int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
   if (tiles <= h->tile_cap) return 0;
   const size_t c = tiles + tiles / 2 + 1024;
   size_t slots = 1024;
   while (slots < 4 * c) slots <<= 1;
-  CK(h->table_slots.ensure(slots * 16));
-  CK(h->tile_key.ensure(c * 8));
-  CK(h->tile_slot.ensure(c * 4));
-  CK(h->tile_touch.ensure(slots * 4));          // the per-substep particle counters are indexed by table slot (k_bin never waits for a tile id)
-  CK(h->cell_count.ensure(slots * 64 * 4));
-  CK(h->slot_first.ensure(slots * 4));
-  CK(h->tile_start.ensure((c + 1) * 8));
-  CK(h->nbr.ensure(c * 8 * 4));
+  for (auto& f : h->fs) {
+    CK(f.table_slots.ensure(slots * 16));
+    CK(f.tile_key.ensure(c * 8));
+    CK(f.tile_slot.ensure(c * 4));
+    CK(f.tile_touch.ensure(slots * 4));          // the per-substep particle counters are indexed by table slot (binning never waits for a tile id)
+    CK(f.cell_count.ensure(slots * 64 * 4));
+    CK(f.slot_first.ensure(slots * 4));
+    CK(f.tile_start.ensure((c + 1) * 8));
+    CK(f.nbr.ensure(c * 8 * 4));
+    f.fresh = true;  // new allocations: the next use memsets them instead of undoing the previous one
+  }
   CK(h->grid.ensure(c * 64 * 16));
   CK(h->node_mask.ensure(c * 8));
   CK(h->node_offset.ensure((c + 1) * 4));
   h->tile_cap = c;
   h->table_mask = (uint32_t)(slots - 1);
-  h->tables_fresh = true;  // new allocations: the next substep memsets them instead of undoing the previous one
+  h->binned_ahead = false;   // whatever was binned ahead went with the old tables
   return 0;
 }
 
@@ -212,66 +224,80 @@ int set_device(SvbHandle* h) {
   return 0;
 }
 
-StepScalars* cur_scalars(SvbHandle* h) { return h->scalars.as<StepScalars>() + h->s_cur; }
+StepScalars* scalars_of(SvbHandle* h, int which) { return h->scalars.as<StepScalars>() + which; }
+StepScalars* cur_scalars(SvbHandle* h) { return scalars_of(h, h->s_cur); }
 
-TileTable tile_table(SvbHandle* h) {
-  return TileTable{h->table_slots.as<ulonglong2>(), h->table_mask, h->tile_key.as<unsigned long long>(), h->tile_slot.as<uint32_t>(), (uint32_t)h->tile_cap};
+TileTable tile_table(SvbHandle* h, int which) {
+  auto& f = h->fs[which];
+  return TileTable{f.table_slots.as<ulonglong2>(), h->table_mask, f.tile_key.as<unsigned long long>(), f.tile_slot.as<uint32_t>(), (uint32_t)h->tile_cap};
+}
+TileTable tile_table(SvbHandle* h) { return tile_table(h, h->s_cur); }
+BinArrays bin_arrays(SvbHandle* h, int which) {
+  auto& f = h->fs[which];
+  return BinArrays{h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), f.cell_count.as<uint32_t>(), f.tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>()};
+}
+int memset_fresh_set(SvbHandle* h, int which) {
+  auto& f = h->fs[which];
+  if (!f.fresh) return 0;
+  cudaStream_t s = h->stream;
+  CK(cudaMemsetAsync(f.table_slots.p, 0xff, ((size_t)h->table_mask + 1) * 16, s));
+  CK(cudaMemsetAsync(f.cell_count.p, 0, ((size_t)h->table_mask + 1) * 64 * 4, s));
+  CK(cudaMemsetAsync(f.tile_touch.p, 0, ((size_t)h->table_mask + 1) * 4, s));
+  return 0;
 }
 MeldInfo meld_info(SvbHandle* h) { return MeldInfo{h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>()}; }
 
 struct StepInputs {
   float factor_b, g[3];
   bool has_mesh;
+  bool adaptive;      // the clock, dt, gravity and the frame factor come from DtState on the device
+  float dt;           // fixed dt
 };
+const DtState* dt_ref(SvbHandle* h, const StepInputs& in) { return in.adaptive ? h->dt_state.as<DtState>() : nullptr; }
 
-// front half of a substep: (collide + force +) binning, cell/tile offsets, halo tiles.  Ends with an
-// async copy of the scalars to pinned memory and an event, so the host can look at the tile count
-// while the back half is already queued behind it.
-int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt_force) {
+// Front half of a substep.  Either the set of this substep was filled ahead of time by the previous substep's G2P / advance
+// (`binned_ahead`: the substep starts at k_offsets), or it bins now: k_begin, (collide,) k_bin.  Then the cell / tile offsets and the
+// halo tiles.  Ends with an async copy of the scalars to pinned memory and an event, so the host can look at the tile count while
+// the back half is already queued behind it.  `redo`: the binning of the same substep again after a tile-capacity overflow.
+int enqueue_front(SvbHandle* h, const StepInputs& in, bool redo) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->p2p ? (uint32_t)h->cap : h->n;   // peer-memory slabs: the exact row count lives on the device, launch for the capacity
-  const StepScalars* S_prev = cur_scalars(h);
-  h->s_cur ^= 1;
+  if (!redo) h->s_cur ^= 1;
   StepScalars* S = cur_scalars(h);
-  stage_begin(h, ST_BIN);
-  if (h->tables_fresh) {
-    CK(cudaMemsetAsync(h->table_slots.p, 0xff, ((size_t)h->table_mask + 1) * 16, s));
-    CK(cudaMemsetAsync(h->cell_count.p, 0, ((size_t)h->table_mask + 1) * 64 * 4, s));
-    CK(cudaMemsetAsync(h->tile_touch.p, 0, ((size_t)h->table_mask + 1) * 4, s));
-    CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
-  }
-  k_begin<<<148, 256, 0, s>>>(S_prev, S, tile_table(h), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), n, h->p2p ? h->n_dev : nullptr, h->tables_fresh ? 1 : 0);
-  LAUNCH_CHECK();
-  h->tables_fresh = false;
-  GoalDev G{nullptr, nullptr, nullptr, nullptr};
-  if (h->has_goals) {
-    G.flags_a = h->d_flags_a.as<uint32_t>();
-    G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : G.flags_a;
-    G.goal_a = h->d_goal_a.as<float>();
-    G.goal_b = h->has_b ? h->d_goal_b.as<float>() : G.goal_a;
-  }
+  const StepScalars* S_prev = scalars_of(h, h->s_cur ^ 1);
+  const bool ahead = !redo && h->binned_ahead;
+  h->binned_ahead = false;
+  auto& F = h->fs[h->s_cur];
   const TileTable T = tile_table(h);
-  const BinArrays B{h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(),
-                    h->layer_list.as<uint32_t>()};
-  const uint32_t blocks = std::max<uint32_t>(blocks_for(n, 256), 1);
-  if (in.has_mesh && apply_force) {  // collide.rs:21-206, before the external force like phase/mod.rs:27-41
-    uint32_t* candidates = h->prank.as<uint32_t>();   // free until k_bin writes the ranks
-    k_collide_query<<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, n);
+  stage_begin(h, ST_BIN);
+  if (!ahead) {
+    if (F.fresh) {
+      if (int rc = memset_fresh_set(h, h->s_cur)) return rc;
+      CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, s));
+    }
+    k_begin<<<148, 256, 0, s>>>(S_prev, S, T, F.cell_count.as<uint32_t>(), F.tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), n, h->p2p ? h->n_dev : nullptr, F.fresh ? 1 : 0);
     LAUNCH_CHECK();
-    k_collide_small<<<148 * 8, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, dt_force);
-    LAUNCH_CHECK();
-    k_collide_big<<<148 * 8, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, dt_force);
+    F.fresh = false;
+    const uint32_t blocks = std::max<uint32_t>(blocks_for(n, 256), 1);
+    if (in.has_mesh && !redo) {  // collide.rs:21-206 (once per substep: it edits v and the bits in place)
+      uint32_t* candidates = h->prank.as<uint32_t>();   // free until k_bin writes the ranks
+      k_collide_query<<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, n);
+      LAUNCH_CHECK();
+      k_collide_small<<<148 * 8, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, in.dt, dt_ref(h, in));
+      LAUNCH_CHECK();
+      k_collide_big<<<148 * 8, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, in.dt, dt_ref(h, in));
+      LAUNCH_CHECK();
+    }
+    const BinArrays B = bin_arrays(h, h->s_cur);
+    if (in.has_mesh) k_bin<true><<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, T, B, n);
+    else k_bin<false><<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, T, B, n);
     LAUNCH_CHECK();
   }
-#define SVB_BIN(MESH, FORCE) k_bin<MESH, FORCE><<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, G, T, B, n, dt_force, in.g[0], in.g[1], in.g[2], in.factor_b)
-  if (in.has_mesh) { if (apply_force) SVB_BIN(true, true); else SVB_BIN(true, false); }
-  else { if (apply_force) SVB_BIN(false, true); else SVB_BIN(false, false); }
-#undef SVB_BIN
-  LAUNCH_CHECK();
   stage_end(h);
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
-  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, T, h->cell_count.as<uint32_t>(), h->tile_start.as<uint2>(), h->slot_first.as<uint32_t>(), h->tile_touch.as<uint32_t>(), h->nbr.as<int>());
+  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, ahead ? S_prev : nullptr, n, h->p2p ? h->n_dev : nullptr, T, F.cell_count.as<uint32_t>(),
+                                                                                                 F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(), F.tile_touch.as<uint32_t>(), F.nbr.as<int>());
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(h->ev_front, s));
@@ -279,24 +305,64 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool apply_force, float dt
   return 0;
 }
 
-// re-bin + grid preparation that follows the front half
-int enqueue_rebin(SvbHandle* h) {
+// re-bin + grid preparation that follows the front half; `prepare_next`: also reset the other front set, which this substep's
+// G2P / advance will fill with the bins of the advanced positions
+int enqueue_rebin(SvbHandle* h, bool prepare_next) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->p2p ? (uint32_t)h->cap : h->n;
   StepScalars* S = cur_scalars(h);
+  auto& F = h->fs[h->s_cur];
   stage_begin(h, ST_PERMUTE);
+  PrepareNext prep{};
+  if (prepare_next) {
+    const int nx = h->s_cur ^ 1;
+    auto& N = h->fs[nx];
+    if (int rc = memset_fresh_set(h, nx)) return rc;
+    prep = PrepareNext{scalars_of(h, nx), tile_table(h, nx), N.cell_count.as<uint32_t>(), N.tile_touch.as<uint32_t>(), n, h->p2p ? h->n_dev : nullptr, N.fresh ? 1 : 0, 74u};
+    N.fresh = false;
+  }
   const uint32_t invert_blocks = blocks_for(n, 256);
-  k_invert_zero<<<invert_blocks + 148 * 2, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), h->cell_count.as<uint32_t>(), h->slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n, invert_blocks,
-                                                        h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap);
+  k_invert_zero<<<invert_blocks + 148 * 2 + prep.blocks, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), F.cell_count.as<uint32_t>(), F.slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n,
+                                                                      invert_blocks, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap, prep);
   LAUNCH_CHECK();
   h->masks_valid = false;
   if (h->store_grid) {
-    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint2>(), h->nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
+    k_touch_nodes<<<148 * 8, 256, 0, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), S, h->K.h, h->node_mask.as<unsigned long long>());
     LAUNCH_CHECK();
     h->masks_valid = true;
   }
   stage_end(h);
   return 0;
+}
+
+int enqueue_p2g(SvbHandle* h, const StepInputs& in) {
+  cudaStream_t s = h->stream;
+  auto& F = h->fs[h->s_cur];
+  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
+  ForceIn force{};
+  force.dt = in.dt; force.gx = in.g[0]; force.gy = in.g[1]; force.gz = in.g[2]; force.factor_b = in.factor_b;
+  force.D = dt_ref(h, in);
+  stage_begin(h, ST_P2G);
+  if (h->has_goals) {
+    force.G.flags_a = h->d_flags_a.as<uint32_t>();
+    force.G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : force.G.flags_a;
+    force.G.goal_a = h->d_goal_a.as<float>();
+    force.G.goal_b = h->has_b ? h->d_goal_b.as<float>() : force.G.goal_a;
+    k_p2g<true><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force);
+  } else {
+    k_p2g<false><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force);
+  }
+  LAUNCH_CHECK();
+  stage_end(h);
+  return 0;
+}
+
+// the substep that was just queued turned out to be a no-op on the device (an earlier substep stopped the run): forget it
+void forget_noop_substep(SvbHandle* h, bool was_ahead, bool back_enqueued) {
+  if (back_enqueued) h->cur ^= 1;   // the queued G2P wrote nothing: undo the buffer swap
+  h->s_cur ^= 1;
+  h->binned_ahead = was_ahead;      // k_offsets aborted before touching the set: its bins still describe the particle state
 }
 
 // The substep that raised a simulation-level error does not count: the reference returns from the failing phase without cycling it
@@ -311,16 +377,20 @@ void rollback_failed_substep(SvbHandle* h) {
 
 // wait for the front half's scalars; on tile overflow grow the capacity and redo the binning
 // (the state is only rewritten by G2P, and k_invert / P2G / G2P no-op on overflow)
-int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
+//   0: fine (back half queued)   1: fine, the caller still has to queue the back half   2: the run was stopped by an earlier substep
+int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued, bool was_ahead) {
   for (int attempt = 0;; ++attempt) {
     CK(cudaEventSynchronize(h->ev_front));
     const StepScalars& r = *h->h_scalars;
-    if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys");
+    if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys (or crossed more than one slab in a substep)");
     if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW)) return fail(h, SVB_COMM_ERROR, "slab exchange failed in an earlier substep (status 0x%x)", r.status);
-    if (r.sticky) {  // the previous substep failed: this one was a no-op on the device
+    if (r.status & ST_ZERO_DT) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
+    if (r.sticky) {  // an earlier substep stopped the run: this one was a no-op on the device
       h->status |= (r.sticky | r.accum) & 0xffffu;
-      if (back_enqueued) { CK(cudaStreamSynchronize(h->stream)); h->cur ^= 1; }
-      rollback_failed_substep(h);
+      CK(cudaStreamSynchronize(h->stream));
+      forget_noop_substep(h, was_ahead, back_enqueued);
+      if (r.sticky & 0xffffu) rollback_failed_substep(h);
+      h->stop_bits = r.sticky;
       return 2;
     }
     if (!(r.status & ST_TILE_OVERFLOW)) {
@@ -335,15 +405,17 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued) {
     if (back_enqueued) h->cur ^= 1;  // the queued G2P was a no-op: undo the buffer swap
     back_enqueued = false;
     if (int rc = ensure_tile_capacity(h, (size_t)r.n_tiles * 2 + 1024)) return rc;
-    if (int rc = enqueue_front(h, in, /*apply_force=*/false, 0.f)) return rc;
+    if (int rc = enqueue_front(h, in, /*redo=*/true)) return rc;
   }
 }
 
 // MeldGrid + CollectVelocity (+ Advance + Cull when fused).  Collider scenes first meld the sibling layers
 // into a velocity grid; without colliders G2P divides by the mass while it stages a tile.
-int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, const MigrateCut* cut = nullptr) {
+// `bin_next`: the fused kernel also bins the advanced positions into the other front set.
+int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next, const MigrateCut* cut = nullptr) {
   cudaStream_t s = h->stream;
   StepScalars* S = cur_scalars(h);
+  auto& F = h->fs[h->s_cur];
   const float4* src = h->grid.as<float4>();
   if (has_mesh) {
     CK(h->melded.ensure(h->tile_cap * 64 * 16));
@@ -353,16 +425,27 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, const MigrateC
   }
   const ParticleBuf P = h->Pc(), D = h->P(h->cur ^ 1);
   const uint32_t* src_of = h->src_of.as<uint32_t>();
-  const uint2* tile_start = h->tile_start.as<uint2>();
+  const uint2* tile_start = F.tile_start.as<uint2>();
   float* en = h->energy.as<float>();
-  const int* nb = h->nbr.as<int>();
+  const int* nb = F.nbr.as<int>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
   const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
   const MigrateCut mc = cut ? *cut : MigrateCut{};
-#define SVB_G2P(F, R, M, SL) k_g2p<F, R, M, SL><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc)
-  if (fuse && cut) { if (has_mesh) SVB_G2P(true, false, true, true); else SVB_G2P(true, false, false, true); }
-  else if (fuse) { if (has_mesh) SVB_G2P(true, false, true, false); else SVB_G2P(true, false, false, false); }
-  else { if (has_mesh) SVB_G2P(false, true, true, false); else SVB_G2P(false, true, false, false); }
+  BinNext bn{};
+  if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
+#define SVB_G2P(F_, R_, M_, SL_, B_) k_g2p<F_, R_, M_, SL_, B_><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn)
+  if (fuse && cut) {
+    if (has_mesh) SVB_G2P(true, false, true, true, false);
+    else if (bin_next) SVB_G2P(true, false, false, true, true);
+    else SVB_G2P(true, false, false, true, false);
+  } else if (fuse) {
+    if (has_mesh) SVB_G2P(true, false, true, false, false);
+    else if (bin_next) SVB_G2P(true, false, false, false, true);
+    else SVB_G2P(true, false, false, false, false);
+  } else {
+    if (has_mesh) SVB_G2P(false, true, true, false, false);
+    else SVB_G2P(false, true, false, false, false);
+  }
 #undef SVB_G2P
   LAUNCH_CHECK();
   h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
@@ -376,139 +459,99 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in);
 int setup_peer_mailboxes(SvbHandle* h);
 int resize_particles(SvbHandle* h, size_t new_cap);
 
-// ---- one substep: the 12 phases of cpu/src/phase/mod.rs:27-41 in the reference's order
+int enqueue_mesh(SvbHandle* h, const StepInputs& in) {
+  cudaStream_t s = h->stream;
+  stage_begin(h, ST_MESH);
+  const uint32_t m = std::max(h->topo.n_vertices * 3, h->topo.n_triangles);
+  k_mesh_lerp<<<blocks_for(m, 256), 256, 0, s>>>(h->M, in.factor_b, dt_ref(h, in));
+  LAUNCH_CHECK();
+  k_mesh_tri_normals<<<blocks_for(h->topo.n_triangles, 256), 256, 0, s>>>(h->M);
+  LAUNCH_CHECK();
+  k_mesh_vertex_normals<<<blocks_for(h->topo.n_vertices, 256), 256, 0, s>>>(h->M);
+  LAUNCH_CHECK();
+  stage_end(h);
+  return 0;
+}
+
+// ---- one substep: the 12 phases of cpu/src/phase/mod.rs:27-41 in the reference's order.
+// Returns 0, a negative fatal status, or 2 when the run was stopped by an earlier substep (this one was a no-op).
 int substep(SvbHandle* h, bool adaptive_steps) {
   cudaStream_t s = h->stream;
   const uint32_t n = h->n;
-  // the scalars pointer flips inside enqueue_front (double buffer): always ask for the current half
-  const float hh = h->K.h;
-
-  if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
-
-  // -- InterpolateInput (interpolate_input.rs:18-107; frame factor xpu/src/frame_input.rs:266-278)
-  const double frame_time = h->time * (double)h->consts.frames_per_second;
-  const uint64_t frame_low = (uint64_t)std::floor(frame_time);
-  if (frame_low != h->frame) return fail(h, SVB_FRAME_INPUT, "Wrong frame loaded: %llu (need %llu)", (unsigned long long)h->frame, (unsigned long long)frame_low);
-  StepInputs in;
-  in.factor_b = (float)std::fmod(frame_time, 1.0);
-  const float factor_a = 1.f - in.factor_b;
-  const float* gb = h->has_b ? h->gravity_b : h->gravity_a;
-  for (int k = 0; k < 3; ++k) in.g[k] = factor_a * h->gravity_a[k] + in.factor_b * gb[k];
+  StepInputs in{};
+  in.adaptive = adaptive_steps;
   in.has_mesh = h->topo.n_triangles > 0;
-  if (in.has_mesh) {
-    stage_begin(h, ST_MESH);
-    const uint32_t m = std::max(h->topo.n_vertices * 3, h->topo.n_triangles);
-    k_mesh_lerp<<<blocks_for(m, 256), 256, 0, s>>>(h->M, in.factor_b);
-    LAUNCH_CHECK();
-    k_mesh_tri_normals<<<blocks_for(h->topo.n_triangles, 256), 256, 0, s>>>(h->M);
-    LAUNCH_CHECK();
-    k_mesh_vertex_normals<<<blocks_for(h->topo.n_vertices, 256), 256, 0, s>>>(h->M);
-    LAUNCH_CHECK();
-    stage_end(h);
+  if (!adaptive_steps) {
+    if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
+    // -- InterpolateInput (interpolate_input.rs:18-107; frame factor xpu/src/frame_input.rs:266-278)
+    const double frame_time = h->time * (double)h->consts.frames_per_second;
+    const uint64_t frame_low = (uint64_t)std::floor(frame_time);
+    if (frame_low != h->frame) return fail(h, SVB_FRAME_INPUT, "Wrong frame loaded: %llu (need %llu)", (unsigned long long)h->frame, (unsigned long long)frame_low);
+    in.factor_b = (float)std::fmod(frame_time, 1.0);
+    const float factor_a = 1.f - in.factor_b;
+    const float* gb = h->has_b ? h->gravity_b : h->gravity_a;
+    for (int k = 0; k < 3; ++k) in.g[k] = factor_a * h->gravity_a[k] + in.factor_b * gb[k];
+    in.dt = h->adaptive.allowed();
   }
+  if (in.has_mesh)
+    if (int rc = enqueue_mesh(h, in)) return rc;
   if (h->slabs) {
     if (adaptive_steps) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps are not supported with slab decomposition yet");
     return h->p2p ? substep_slab_p2p(h, in) : substep_slab(h, in);
   }
   if (n == 0) {
+    if (adaptive_steps) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps need at least one particle");
     h->time_before_last = h->time;
     h->time += (double)h->adaptive.allowed();
     ++h->substeps;
     return 0;
   }
 
-  // -- Collide + ExternalForce + Sort + UpdateGridNodes.  Collide / force are per particle, so running
-  //    them in the pre-bin order is equivalent to the reference's Sort -> Collide -> Force.
-  if (int rc = enqueue_front(h, in, /*apply_force=*/true, h->adaptive.allowed())) return rc;
-  const uint2* tile_start = h->tile_start.as<uint2>();
-  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
-  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
-
-  if (!adaptive_steps) {
-    // fixed dt: queue the whole back half behind the front half, then look at the front half's result
-    const float dt = h->adaptive.allowed();
-    if (int rc = enqueue_rebin(h)) return rc;
-    stage_begin(h, ST_P2G);
-    k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
-    LAUNCH_CHECK();
-    stage_end(h);
+  // -- Sort + UpdateGridNodes (+ Collide): filled ahead by the previous substep's G2P, or binned now.  Collide / force are per
+  //    particle, so running them in the pre-bin order is equivalent to the reference's Sort -> Collide -> Force.
+  const bool was_ahead = h->binned_ahead;
+  const bool bin_next = !in.has_mesh;   // with a mesh the collider bits of the next substep are not known yet
+  if (int rc = enqueue_front(h, in, /*redo=*/false)) return rc;
+  for (int pass = 0;; ++pass) {
+    // the whole back half is queued behind the front half, then the host looks at the front half's result
+    if (int rc = enqueue_rebin(h, bin_next)) return rc;
+    if (int rc = enqueue_p2g(h, in)) return rc;
     stage_begin(h, ST_G2P);
-    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc;
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/!adaptive_steps, in.dt, bin_next && !adaptive_steps)) return rc;
     stage_end(h);
-    const int rc = settle_front(h, in, /*back_enqueued=*/true);
-    if (rc < 0) return rc;
-    if (rc == 2) return 0;  // stopped by an earlier simulation-level error; time does not advance
-    if (rc == 1) {  // the binning was redone with a larger tile capacity: queue the back half again
-      if (int rc2 = enqueue_rebin(h)) return rc2;
-      k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), h->tile_start.as<uint2>(), h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
+    if (adaptive_steps) {
+      // -- LimitTimeStepBeforeIntegrate, AdvanceParticles + CullParticles, the clock: all on the device
+      DtState* D = h->dt_state.as<DtState>();
+      stage_begin(h, ST_LIMIT);
+      k_dt_integrate<<<1, 1, 0, s>>>(D, cur_scalars(h));
       LAUNCH_CHECK();
-      if (int rc2 = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc2;
+      stage_end(h);
+      stage_begin(h, ST_ADVANCE);
+      BinNext bn{};
+      if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
+      if (bin_next) k_advance<true><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, D, bn);
+      else k_advance<false><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, D, bn);
+      LAUNCH_CHECK();
+      k_dt_tail<<<1, 1, 0, s>>>(D, cur_scalars(h));
+      LAUNCH_CHECK();
+      CK(cudaMemcpyAsync(h->h_dt, D, sizeof(DtState), cudaMemcpyDeviceToHost, s));
+      stage_end(h);
     }
-    h->have_grid = true;
-    h->time_before_last = h->time;
-    h->time += (double)dt;
-    ++h->substeps;
-    return 0;
-  }
-
-  // adaptive dt: the host owns the time-step state machine, so every reduction is read back
-  {
-    const int rc = settle_front(h, in, /*back_enqueued=*/false);
+    if (pass > 0) break;
+    const int rc = settle_front(h, in, /*back_enqueued=*/true, was_ahead);
     if (rc < 0) return rc;
-    if (rc == 2) return 0;
+    if (rc == 2) return 2;  // stopped by an earlier substep; time does not advance
+    if (rc == 0) break;
+    // rc == 1: the binning was redone with a larger tile capacity: queue the back half again
   }
-  if (int rc = enqueue_rebin(h)) return rc;
-  tile_start = h->tile_start.as<uint2>();
-  // -- LimitTimeStepBeforeForce (limit_time_step.rs:25-33)
-  stage_begin(h, ST_LIMIT);
-  k_limit_force<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), cur_scalars(h), hh, n);
-  LAUNCH_CHECK();
-  CK(cudaMemcpyAsync(h->h_scalars, cur_scalars(h), sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  stage_end(h);
-  {
-    const bool any = h->h_scalars->live_count > 0;
-    h->adaptive.has_sound = h->adaptive.has_isolated = any;
-    if (any) {
-      h->adaptive.by_sound = total_unkey(h->h_scalars->min_sound_key);
-      h->adaptive.by_isolated = total_unkey(h->h_scalars->min_isolated_key);
-    }
-    h->adaptive.push_current_limit();
-    if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
-  }
-  // -- ScatterMomentum, MeldGrid + CollectVelocity
-  const float dt_scatter = h->adaptive.allowed();
-  stage_begin(h, ST_P2G);
-  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt_scatter);
-  LAUNCH_CHECK();
-  stage_end(h);
-  stage_begin(h, ST_G2P);
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/false, dt_scatter)) return rc;
-
-  // -- LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223)
-  CK(cudaMemcpyAsync(h->h_scalars, cur_scalars(h), sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  stage_end(h);
-  {
-    const bool any = h->n_live > 0;
-    const float max_vel = any ? total_unkey(h->h_scalars->max_velocity_key) : 0.f;
-    h->adaptive.has_velocity = any && max_vel != 0.f;
-    if (h->adaptive.has_velocity) h->adaptive.by_velocity = 0.5f * hh / max_vel;
-    h->adaptive.has_deformation = any;
-    if (any) h->adaptive.by_deformation = total_unkey(h->h_scalars->min_deformation_key);
-    h->adaptive.push_current_limit();
-    if (h->adaptive.allowed() == 0.f) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
-  }
-  // -- AdvanceParticles + CullParticles
-  stage_begin(h, ST_ADVANCE);
-  k_advance<<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, h->adaptive.allowed());
-  LAUNCH_CHECK();
-  stage_end(h);
+  h->binned_ahead = bin_next;
+  h->limits_ahead = adaptive_steps;
   h->have_grid = true;
-  h->time_before_last = h->time;
-  h->time += (double)h->adaptive.allowed();
-  ++h->substeps;
+  if (!adaptive_steps) {
+    h->time_before_last = h->time;
+    h->time += (double)in.dt;
+    ++h->substeps;
+  }
   return 0;
 }
 
@@ -517,42 +560,35 @@ int substep(SvbHandle* h, bool adaptive_steps) {
 // (the neighbours still expect this rank's messages).
 int substep_slab(SvbHandle* h, const StepInputs& in) {
   cudaStream_t s = h->stream;
-  // the scalars pointer flips inside enqueue_front (double buffer): always ask for the current half
-  const float hh = h->K.h;
-  const float dt = h->adaptive.allowed();
-  bool apply_force = true;
+  const float dt = in.dt;
+  bool redo = false;
   for (int attempt = 0;; ++attempt) {
-    if (int rc = enqueue_front(h, in, apply_force, dt)) return rc;
-    const int rc = settle_front(h, in, /*back_enqueued=*/false);
+    if (int rc = enqueue_front(h, in, redo)) return rc;
+    const int rc = settle_front(h, in, /*back_enqueued=*/false, false);
     if (rc < 0) return rc;
+    if (rc == 2) return 2;
     // tiles arriving with the halo need room in the table; growing it loses its contents, so re-bin
     const size_t want = (size_t)h->n_tiles + h->halo_margin;
     if (want <= h->tile_cap) break;
     if (attempt > 4) return fail(h, SVB_COMM_ERROR, "tile capacity did not settle");
     CK(cudaStreamSynchronize(s));
     if (int rc2 = ensure_tile_capacity(h, want + want / 2)) return rc2;
-    apply_force = false;
+    redo = true;
   }
   const uint32_t n_after = h->h_scalars->n_live + h->h_scalars->n_tomb;  // rows of migrated particles are dropped by the re-bin
-  if (int rc = enqueue_rebin(h)) return rc;
-  const uint2* tile_start = h->tile_start.as<uint2>();
-  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
-  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
-  stage_begin(h, ST_P2G);
-  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), hh, dt);
-  LAUNCH_CHECK();
-  stage_end(h);
+  if (int rc = enqueue_rebin(h, false)) return rc;
+  if (int rc = enqueue_p2g(h, in)) return rc;
   stage_begin(h, ST_HALO);
   if (int rc = halo_exchange(h)) return rc;
   stage_end(h);
   stage_begin(h, ST_G2P);
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt)) return rc;
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, false)) return rc;
   h->n = n_after;
   // a FAILED particle on any rank stops every rank after this substep
   uint32_t* flag = h->comm_counts.as<uint32_t>() + 8;
-  CK(cudaMemcpyAsync(flag, &cur_scalars(h)->sticky, 4, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(flag, &cur_scalars(h)->sticky_new, 4, cudaMemcpyDeviceToDevice, s));
   if (ncclAllReduce(flag, flag, 1, ncclUint32, ncclMax, h->comm, s) != ncclSuccess) return fail(h, SVB_COMM_ERROR, "ncclAllReduce failed");
+  CK(cudaMemcpyAsync(&cur_scalars(h)->sticky_new, flag, 4, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(h->h_counts + 8, flag, 4, cudaMemcpyDeviceToHost, s));
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
@@ -570,20 +606,15 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
 // substep is queued, then the host looks at the front half's scalars (one substep of lag at most).
 int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   cudaStream_t s = h->stream;
-  const float hh = h->K.h;
-  const float dt = h->adaptive.allowed();
+  const float dt = in.dt;
   const uint32_t seq = ++h->slab_seq;
-  if (int rc = enqueue_front(h, in, /*apply_force=*/true, dt)) return rc;
-  if (int rc = enqueue_rebin(h)) return rc;
+  const bool was_ahead = h->binned_ahead;
+  const bool bin_next = !in.has_mesh;
+  if (int rc = enqueue_front(h, in, /*redo=*/false)) return rc;
+  if (int rc = enqueue_rebin(h, bin_next)) return rc;
   StepScalars* S = cur_scalars(h);
   const TileTable T = tile_table(h);
-  const uint2* tile_start = h->tile_start.as<uint2>();
-  const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
-  stage_begin(h, ST_P2G);
-  k_p2g<<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), tile_start, h->nbr.as<int>(), S, h->grid.as<float4>(), hh, dt);
-  LAUNCH_CHECK();
-  stage_end(h);
+  if (int rc = enqueue_p2g(h, in)) return rc;
   stage_begin(h, ST_HALO);
   SlabHeader* my_hdr = h->mailbox.as<SlabHeader>();
   unsigned char* my_mb = h->mailbox.as<unsigned char>();
@@ -611,7 +642,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   stage_begin(h, ST_G2P);
   CK(h->mig_list.ensure(2 * h->mb_mig_cap * 4));
   const MigrateCut cut{h->slab_lo, h->slab_hi, h->reach_lo, h->reach_hi, 4.f * (float)h->slab_lo, 4.f * (float)h->slab_hi, h->mig_list.as<uint32_t>(), h->p2p_local + 8, (uint32_t)h->mb_mig_cap};
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, &cut)) return rc;
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, &cut)) return rc;
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
   SlabPeers peers{};
@@ -633,31 +664,35 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
     }
   k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
   LAUNCH_CHECK();
+  BinNext bn{};
+  if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
-                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0);
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0, h->K, bn, bin_next ? 1 : 0);
   LAUNCH_CHECK();
   stage_end(h);
   // ---- the host catches up with the front half of this substep (the back half keeps the GPU busy meanwhile)
   CK(cudaEventSynchronize(h->ev_front));
   const StepScalars& r = *h->h_scalars;
-  if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys");
+  if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys (or crossed more than one slab in a substep)");
   if (r.status & ST_TILE_OVERFLOW) return fail(h, SVB_COMM_ERROR, "tile capacity exceeded on a slab rank (%u tiles > %zu)", r.n_tiles, h->tile_cap);
-  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))   // raised by an earlier substep's back half and carried forward by k_begin
+  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))   // raised by an earlier substep's back half and carried forward
     return fail(h, SVB_COMM_ERROR, r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
-  if (r.sticky) {  // the previous substep failed somewhere: this one was a no-op on every rank (the queued G2P wrote nothing: undo the buffer swap)
+  if (r.sticky) {  // the previous substep failed somewhere: this one was a no-op on every rank
     h->status |= (r.sticky | r.accum) & 0xffffu;
     CK(cudaStreamSynchronize(s));
-    h->cur ^= 1;
+    forget_noop_substep(h, was_ahead, true);
     rollback_failed_substep(h);
-    return 0;
+    h->stop_bits = r.sticky;
+    return 2;
   }
   h->n_tiles = r.n_tiles;
   h->n_ptiles = r.n_ptiles;
   h->n_live = r.n_live;
   h->status |= (r.status | r.accum) & 0xffffu;
+  h->binned_ahead = bin_next;
   if (((size_t)r.n_tiles + h->halo_margin) * 3 / 2 > h->tile_cap) {  // grow ahead of need: an overflow cannot be redone once messages are out
     CK(cudaStreamSynchronize(s));
-    if (int rc = ensure_tile_capacity(h, ((size_t)r.n_tiles + h->halo_margin) * 3)) return rc;
+    if (int rc = ensure_tile_capacity(h, ((size_t)r.n_tiles + h->halo_margin) * 3)) return rc;   // (drops what was binned ahead: the next substep bins with k_bin)
   }
   h->have_grid = true;
   h->time_before_last = h->time;
@@ -711,8 +746,8 @@ int read_status(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  h->status |= (h->h_scalars->status | h->h_scalars->sticky | h->h_scalars->accum) & 0xffffu;
-  if (h->h_scalars->sticky) rollback_failed_substep(h);   // the failing substep was the last one queued
+  h->status |= (h->h_scalars->status | h->h_scalars->sticky | h->h_scalars->sticky_new | h->h_scalars->accum) & 0xffffu;
+  if ((h->h_scalars->sticky_new & 0xffffu) && !h->adaptive.has_override) rollback_failed_substep(h);   // fixed dt: the failing substep was the last one queued
   return 0;
 }
 
@@ -762,8 +797,12 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   for (auto& e : h->ev_adv) CK(cudaEventCreate(&e));
   CK(cudaMallocHost(&h->h_scalars, sizeof(StepScalars)));
+  CK(cudaMallocHost(&h->h_dt, sizeof(DtState)));
+  CK(h->dt_state.ensure(sizeof(DtState)));
+  CK(cudaMemsetAsync(h->dt_state.p, 0, sizeof(DtState), h->stream));
   CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
-  CK(cudaFuncSetAttribute(k_p2g, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+  CK(cudaFuncSetAttribute(k_p2g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
+  CK(cudaFuncSetAttribute(k_p2g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
   const uint32_t n = (uint32_t)p->n;
   h->n = n;
   h->cap = ((size_t)std::max<uint32_t>(n, 1) + 63) & ~(size_t)63;
@@ -796,7 +835,10 @@ void svb_destroy(SvbHandle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->table_slots, &h->tile_key, &h->tile_slot, &h->tile_touch, &h->cell_count, &h->slot_first, &h->tile_start, &h->nbr,
+  for (auto& f : h->fs)
+    for (DevBuf* b : {&f.table_slots, &f.tile_key, &f.tile_slot, &f.tile_touch, &f.cell_count, &f.slot_first, &f.tile_start, &f.nbr}) b->release();
+  if (h->h_dt) cudaFreeHost(h->h_dt);
+  DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->dt_state,
                    &h->grid, &h->melded, &h->mig_list, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tbox, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
@@ -836,8 +878,9 @@ int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
   h->substeps = 0;
   h->status = 0;
   h->adaptive = svbh::AdaptiveTimeStep();
-  CK(cudaMemsetAsync(h->scalars.p, 0, 2 * sizeof(StepScalars), h->stream));
-  h->tables_fresh = true;
+  // (the scalars keep the tile counts of each front set: the next reset undoes exactly those)
+  h->binned_ahead = false;
+  h->limits_ahead = false;
   h->n_ptiles = h->n_live = h->n_tiles = 0;
   h->have_grid = false;
   h->masks_valid = false;
@@ -952,17 +995,22 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (!h) return SVB_BAD_ARGUMENT;
   if (!h->have_keyframes) return fail(h, SVB_INPUT_MISSING, "At this point, interpolated input should be ready (svb_set_keyframes not called)");
   if (int rc = set_device(h)) return rc;
+  const bool adaptive = adaptive_time_steps != 0;
+  cudaStream_t s = h->stream;
   h->adaptive.max_time_step = max_time_step;
   h->status = 0;
-  {  // a new advance starts without status bits; the tile bookkeeping of the last substep stays (k_begin undoes it)
-    StepScalars* S = cur_scalars(h);
-    CK(cudaMemsetAsync(&S->status, 0, 4, h->stream));
-    CK(cudaMemsetAsync(&S->sticky, 0, 8, h->stream));   // sticky + accum
+  h->stop_bits = 0;
+  {  // a new advance starts without status bits; the tile bookkeeping of the last substep stays (the next reset undoes it)
+    for (int k = 0; k < 2; ++k) {
+      StepScalars* S = scalars_of(h, k);
+      CK(cudaMemsetAsync(&S->sticky, 0, 12, s));   // sticky, sticky_new, accum  (the words are adjacent, see svb_device.cuh)
+    }
+    CK(cudaMemsetAsync(&cur_scalars(h)->status, 0, 4, s));   // (the other half may hold what the binning-ahead raised: that stays)
   }
   h->failed_rolled_back = false;
   if (h->timing) std::memset(h->stage_ms, 0, sizeof h->stage_ms);
   const double spf = 1.0 / (double)h->consts.frames_per_second;
-  CK(cudaEventRecord(h->ev_adv[0], h->stream));
+  CK(cudaEventRecord(h->ev_adv[0], s));
   // room for the per-substep inflow (a trickle: the CFL limit keeps travel below one cell per substep); the loop itself never
   // resizes, k_migrate_recv reports a full buffer.  Deliberately NOT sized by the mailboxes (those also serve a rebalance, which
   // makes its own room): slab ranks launch their per-row kernels for the capacity, idle blocks are not free.
@@ -970,13 +1018,74 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (h->p2p && (size_t)h->n + 2 * inflow > h->cap) {
     if (int rc = resize_particles(h, ((size_t)h->n + 2 * inflow) * 5 / 4)) return rc;
   }
-  while (h->time < target_time) {
-    if (cancel && *cancel) return fail(h, SVB_CANCELED, "The computation was canceled");
-    if (int rc = substep(h, adaptive_time_steps != 0)) return rc;
-    if (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED) break;
-    if (progress) progress(user, (size_t)(std::fmod(h->time, spf) * 1000.0));
+  if (adaptive && !h->slabs && h->n > 0) {
+    // ---- the clock and AdaptiveTimeStepState move to the device for the duration of the call
+    DtState d{};
+    d.time = h->time; d.target = target_time; d.fps = (double)h->consts.frames_per_second; d.frame = h->frame;
+    d.max_dt = max_time_step; d.h = h->K.h;
+    const auto& a = h->adaptive;
+    d.has = (a.has_velocity ? 1u : 0u) | (a.has_deformation ? 2u : 0u) | (a.has_isolated ? 4u : 0u) | (a.has_sound ? 8u : 0u);
+    d.by_velocity = a.by_velocity; d.by_deformation = a.by_deformation; d.by_isolated = a.by_isolated; d.by_sound = a.by_sound;
+    d.prior_len = (uint32_t)std::min<size_t>(a.prior.size(), 11);
+    for (uint32_t q = 0; q < d.prior_len; ++q) d.prior[q] = a.prior[q];
+    for (int k = 0; k < 3; ++k) { d.ga[k] = h->gravity_a[k]; d.gb[k] = h->has_b ? h->gravity_b[k] : h->gravity_a[k]; }
+    d.next_min_sound_key = INT32_MAX; d.next_min_isolated_key = INT32_MAX; d.next_live = 0;
+    DtState* D = h->dt_state.as<DtState>();
+    if (h->limits_ahead) {   // the limits of the current state were reduced by the last k_advance: keep them
+      DtState old{};
+      CK(cudaMemcpyAsync(&old, D, sizeof old, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      d.next_min_sound_key = old.next_min_sound_key; d.next_min_isolated_key = old.next_min_isolated_key; d.next_live = old.next_live;
+    }
+    *h->h_dt = d;
+    CK(cudaMemcpyAsync(D, h->h_dt, sizeof d, cudaMemcpyHostToDevice, s));
+    if (!h->limits_ahead) {
+      k_limit_force<<<blocks_for(h->n, 256), 256, 0, s>>>(h->Pc(), D, h->K.h, h->n, nullptr);
+      LAUNCH_CHECK();
+    }
+    k_dt_open<<<1, 1, 0, s>>>(D, cur_scalars(h));
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_dt, D, sizeof d, cudaMemcpyDeviceToHost, s));
+    h->limits_ahead = false;
+    int rc = 0;
+    for (;;) {
+      if (cancel && *cancel) { rc = fail(h, SVB_CANCELED, "The computation was canceled"); break; }
+      rc = substep(h, true);
+      if (rc != 0) break;
+      // (h_dt is the device clock as of the previous substep's tail: the wait for this substep's front half has passed it)
+      if (progress) progress(user, (size_t)(std::fmod(h->h_dt->time, spf) * 1000.0));
+    }
+    if (rc < 0) return rc;
+    // rc == 2: a stop word ended the run — the target time, a failed particle, a wrong frame, a zero time step
+    CK(cudaMemcpyAsync(h->h_dt, D, sizeof d, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const DtState& e = *h->h_dt;
+    h->time = e.time;
+    h->substeps += e.substeps;
+    auto& w = h->adaptive;
+    w.has_velocity = e.has & 1u; w.has_deformation = e.has & 2u; w.has_isolated = e.has & 4u; w.has_sound = e.has & 8u;
+    w.by_velocity = e.by_velocity; w.by_deformation = e.by_deformation; w.by_isolated = e.by_isolated; w.by_sound = e.by_sound;
+    w.prior.assign(e.prior, e.prior + std::min<uint32_t>(e.prior_len, 11));
+    w.allowed_override = e.allowed; w.has_override = true;
+    h->limits_ahead = (h->stop_bits & ST_STOP_DONE) != 0 && !(h->stop_bits & 0xffffu);   // the pending LimitTimeStepBeforeForce belongs to the next call
+    if (h->stop_bits & ST_STOP_ZERO_DT) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
+    if (h->stop_bits & ST_STOP_FRAME) return fail(h, SVB_FRAME_INPUT, "Wrong frame loaded: %llu (need %llu)", (unsigned long long)h->frame, (unsigned long long)std::floor(e.time * e.fps));
+  } else {
+    if (adaptive && h->slabs) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps are not supported with slab decomposition yet");
+    h->adaptive.has_override = false;
+    if (adaptive && h->n == 0) {   // nothing limits the step: the reference walks to the target in steps of max_time_step
+      h->adaptive = svbh::AdaptiveTimeStep();
+      h->adaptive.max_time_step = max_time_step;
+    }
+    while (h->time < target_time) {
+      if (cancel && *cancel) return fail(h, SVB_CANCELED, "The computation was canceled");
+      const int rc = substep(h, false);
+      if (rc < 0) return rc;
+      if (rc == 2 || (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED)) break;
+      if (progress) progress(user, (size_t)(std::fmod(h->time, spf) * 1000.0));
+    }
   }
-  CK(cudaEventRecord(h->ev_adv[1], h->stream));
+  CK(cudaEventRecord(h->ev_adv[1], s));
   if (int rc = read_status(h)) return rc;
   if (h->p2p) {  // the row count lived on the device during the loop
     CK(cudaMemcpy(&h->n, h->n_dev, 4, cudaMemcpyDeviceToHost));
@@ -1183,6 +1292,8 @@ int32_t svb_restore(SvbHandle* h) {
   h->substeps = h->snap_substeps;
   h->n = h->snap_n;
   h->have_grid = false;
+  h->binned_ahead = false;   // the bins in the other front set belong to the state that was just replaced
+  h->limits_ahead = false;
   return 0;
 }
 
@@ -1221,6 +1332,7 @@ int resize_particles(SvbHandle* h, size_t new_cap) {
   CK(h->prank.ensure(new_cap * 4));
   CK(h->src_of.ensure(new_cap * 4));
   h->have_snapshot = false;
+  h->binned_ahead = false;   // pcell / prank were reallocated
   return 0;
 }
 
@@ -1517,7 +1629,8 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
   k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
-                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1);
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1, h->K, BinNext{}, 0);
+  h->binned_ahead = false;   // rows left and arrived: the bins made ahead describe another row set
   LAUNCH_CHECK();
   if (int rc = read_status(h)) return rc;
   if (h->h_scalars->status & ST_COMM_OVERFLOW) return fail(h, SVB_COMM_ERROR, "rebalance: more particles change rank than the mailboxes (%zu rows) or the particle buffer hold", h->mb_mig_cap);

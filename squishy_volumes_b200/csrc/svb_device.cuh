@@ -91,7 +91,8 @@ constexpr uint32_t ST_KEY_RANGE = 0x80000000u;   // a live particle lies outside
 constexpr uint32_t ST_TILE_OVERFLOW = 0x40000000u;  // tile capacity exceeded: the host grows it and redoes the binning
 constexpr uint32_t ST_COMM_TIMEOUT = 0x20000000u;   // slab ranks: a neighbour's message did not arrive
 constexpr uint32_t ST_COMM_OVERFLOW = 0x10000000u;  // slab ranks: a mailbox or the particle buffer ran out of room
-constexpr uint32_t ST_ABORT_MASK = ST_KEY_RANGE | ST_TILE_OVERFLOW | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW;
+constexpr uint32_t ST_ZERO_DT = 0x08000000u;        // adaptive steps: the allowed time step became 0 inside a substep (the rest of it must not run)
+constexpr uint32_t ST_ABORT_MASK = ST_KEY_RANGE | ST_TILE_OVERFLOW | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW | ST_ZERO_DT;
 struct StepScalars {
   uint32_t n;          // resident particles (incl. tombstoned)
   uint32_t n_live;     // particles with a bin (not tombstoned)
@@ -108,14 +109,50 @@ struct StepScalars {
   // adaptive time step reductions (f32::total_cmp keys)
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;
-  uint32_t sticky;     // simulation-level error bits that stop the run (SVB_PARTICLE_CLOSE_TO_INVERTED); survives the per-substep reset
-  uint32_t accum;      // simulation-level bits (SVB_TABLE_*) of the EARLIER substeps of this svb_advance call: k_begin folds the previous
-                       // substep's status word in here, so a bit set in any substep's back half reaches the host at the end of the call
+  // ---- the run's sticky words: three ADJACENT uint32 (the host clears them with one 12-byte memset at the start of an svb_advance call)
+  uint32_t sticky;     // error / stop bits that end the run (SVB_PARTICLE_CLOSE_TO_INVERTED, ST_STOP_*), as carried INTO this substep: constant
+                       // while the substep runs, so every CTA of every kernel takes the same "run / no-op" decision
+  uint32_t sticky_new; // ... raised BY this substep (a FAILED particle in G2P / advance, a neighbour rank's error word, the device clock
+                       // reaching its target): folded into the next substep's `sticky`, which makes that substep and all later ones no-ops
+  uint32_t accum;      // simulation-level bits (SVB_TABLE_*) of the EARLIER substeps of this svb_advance call: the status word of every
+                       // finished substep is folded in here, so a bit set in any substep's back half reaches the host at the end of the call
+  uint32_t reset_done; // blocks of the set-reset that have finished (the last one re-initialises these scalars)
 };
 // abort bits that stay set once raised: every later substep of the call is a no-op and the host reports a fatal error.  (A tile
 // overflow is not carried: the host grows the tables and redoes the binning.)
-constexpr uint32_t ST_CARRY_MASK = ST_KEY_RANGE | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW;
+constexpr uint32_t ST_CARRY_MASK = ST_KEY_RANGE | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW | ST_ZERO_DT;
 #define SVB_ABORTED(S) (((S)->status & ST_ABORT_MASK) || (S)->sticky)
+
+// "stop" bits that travel in the upper half of sticky / sticky_new (never reported as simulation status): they turn every later substep
+// of the call into a no-op exactly like a FAILED particle does, which is how a device-side clock ends a run the host has queued ahead
+constexpr uint32_t ST_STOP_DONE = 0x10000u;      // time >= target_time: produce_next_state's loop is over (cpu_state.rs:166)
+constexpr uint32_t ST_STOP_FRAME = 0x20000u;     // floor(time * fps) != loaded frame (xpu/src/frame_input.rs:266-278: WrongFrameLoaded)
+constexpr uint32_t ST_STOP_ZERO_DT = 0x40000u;   // allowed_time_step() == 0 (cpu_state.rs:170-172: ZeroTimeStep)
+
+// Adaptive time stepping on the device (cpu/src/adaptive_time_step_state.rs:13-64, cpu/src/phase/limit_time_step.rs:25-33,187-195,
+// cpu/src/cpu_state.rs:166-190): the clock, the four limits and the <= 11-entry history live in HBM; kernels read dt from here, three
+// one-thread kernels (k_dt_open / k_dt_integrate / k_dt_tail) play AdaptiveTimeStepState, and the host only reads a lagged copy to
+// learn when the run is over.  Fixed-dt runs keep the clock on the host and pass dt as a launch argument.
+struct DtState {
+  double time, target, fps;
+  unsigned long long frame;
+  float max_dt;
+  float allowed;        // allowed_time_step() as of the last push (what the next phase reads)
+  float dt_force;       // the step Collide / ExternalForce of the current substep see (before LimitTimeStepBeforeForce's push)
+  float h;
+  uint32_t has;         // bit 0 velocity, 1 deformation, 2 isolated, 3 sound: which Option<f32> limits are Some
+  float by_velocity, by_deformation, by_isolated, by_sound;
+  uint32_t prior_len;
+  float prior[12];
+  uint32_t substeps;    // completed by this svb_advance call
+  uint32_t stop;        // ST_STOP_* raised so far (mirror of what went into sticky_new)
+  float factor_b, g[3]; // frame factor and interpolated gravity of the CURRENT substep (interpolate_input.rs:25-33)
+  float ga[3], gb[3];
+  // LimitTimeStepBeforeForce of the NEXT substep, reduced by the kernel that already holds the advanced F (k_advance) or by k_limit_force
+  int32_t next_min_sound_key, next_min_isolated_key;
+  uint32_t next_live;
+  uint32_t pad;
+};
 
 struct MeshDev {
   uint32_t n_vertices, n_triangles, n_colliders;

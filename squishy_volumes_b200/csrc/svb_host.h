@@ -213,6 +213,9 @@ struct AdaptiveTimeStep {  // cpu/src/adaptive_time_step_state.rs:13-64
   bool has_velocity = false, has_deformation = false, has_isolated = false, has_sound = false;
   float by_velocity = 0, by_deformation = 0, by_isolated = 0, by_sound = 0;
   std::deque<float> prior;
+  // after an adaptive svb_advance the state machine ran on the device: `allowed()` then reports the device's last value
+  bool has_override = false;
+  float allowed_override = 0;
   float allowed_without_prior() const {
     const float fmax = std::numeric_limits<float>::max();
     float r = max_time_step;
@@ -223,6 +226,7 @@ struct AdaptiveTimeStep {  // cpu/src/adaptive_time_step_state.rs:13-64
     return r;
   }
   float allowed() const {
+    if (has_override) return allowed_override;
     float r = allowed_without_prior();
     for (float p : prior) r = total_min(r, p);
     return r;

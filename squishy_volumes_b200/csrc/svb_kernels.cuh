@@ -52,7 +52,8 @@ __global__ void k_iota(uint32_t* a, uint32_t n, uint32_t offset) {
 
 // ------------------------------------------------------------------------------------------------
 // collider mesh interpolation (interpolate_input.rs:36-96)
-__global__ void k_mesh_lerp(MeshDev M, float factor_b) {
+__global__ void k_mesh_lerp(MeshDev M, float factor_b, const DtState* __restrict__ D) {
+  if (D) factor_b = D->factor_b;   // adaptive steps: the clock lives on the device
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float fa = 1.f - factor_b;
   if (i < M.n_vertices * 3) M.vpos[i] = fa * M.va[i] + factor_b * M.vb[i];
@@ -259,8 +260,9 @@ __global__ void __launch_bounds__(256) k_collide_query(ParticleBuf P, StepScalar
   if (kind == 1) candidates[base_s + __popc(ms & below)] = i;                    // the two lists cannot meet: together they hold <= n <= cap entries
   if (kind == 2) candidates[cap - 1 - (base_b + __popc(mb & below))] = i;
 }
-__global__ void __launch_bounds__(128) k_collide_small(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, float dt) {
+__global__ void __launch_bounds__(128) k_collide_small(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, float dt, const DtState* __restrict__ D) {
   if (S->sticky) return;
+  if (D) dt = D->dt_force;
   const uint32_t n_cand = S->n_candidates;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
     const uint32_t i = candidates[q];
@@ -288,8 +290,9 @@ __global__ void __launch_bounds__(128) k_collide_small(ParticleBuf P, const Step
     P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
   }
 }
-__global__ void __launch_bounds__(256) k_collide_big(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, uint32_t cap, float dt) {
+__global__ void __launch_bounds__(256) k_collide_big(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, uint32_t cap, float dt, const DtState* __restrict__ D) {
   if (S->sticky) return;
+  if (D) dt = D->dt_force;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t n_cand = S->n_candidates_big;
@@ -457,17 +460,74 @@ __device__ __forceinline__ int tile_find(const TileTable& T, unsigned long long 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_bin — external force + binning, one thread per particle in the CURRENT order.
-//   * external_force.rs edits v in place (skipped on a re-bin redo), after the collide pass of the same substep;
-//   * the particle's tile (block of its base node, layer of its collider bits) is found or created in
-//     the tile table, warp-aggregated: lanes with equal keys elect one lane to touch the table;
-//   * the particle takes a slot in its cell: rank = atomicAdd(cell_count[tile*64 + cell]) (again one
-//     atomic per distinct cell per warp) — a single-pass counting sort on (tile, cell);
-//   * the tile remembers which of its 8 neighbour blocks its particles' stencils reach.
+// binning (sort.rs:29-33 cell keys + update_grid_nodes.rs:31-156 tile activation): a single-pass counting sort on (tile, cell)
 struct GoalDev {
   const uint32_t* flags_a; const uint32_t* flags_b;   // original order, may be null
   const float* goal_a; const float* goal_b;           // 3 per particle, original order
 };
+// A "front set" = the per-substep tile bookkeeping (tile table, per-slot cell counters and touch masks).  Two sets alternate: while
+// substep n runs on set n % 2, the fused G2P of substep n already bins the ADVANCED positions into the other set for substep n + 1
+// (scenes without a collider mesh; with a mesh the collider bits — hence the layer of a particle's tile — are only known after the
+// collide pass of substep n + 1, so those scenes bin at the start of the substep with k_bin).
+//
+// reset_set: undo exactly what the set's previous use left in it (its tiles' hash slots, touch masks and cell counters) instead of
+// memset-ing whole allocations, then — last block done — re-initialise the set's scalars, carrying the run's sticky words over from
+// `from` (the scalars of the substep before the one this set will serve).  `S` still describes the set's previous content while the
+// blocks work, which is why its re-initialisation waits for the last of them.
+__device__ __forceinline__ void reset_set(const StepScalars* __restrict__ from, StepScalars* __restrict__ S, const TileTable& T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_touch,
+                                          uint32_t n, const uint32_t* __restrict__ n_dev, int tables_fresh, uint32_t block, uint32_t n_blocks) {
+  // tables_fresh: the host has just (re)allocated and memset the tables, tile_slot holds nothing to undo
+  const uint32_t n_tiles = tables_fresh ? 0u : min(S->n_tiles, T.tile_cap), n_ptiles = tables_fresh ? 0u : min(S->n_ptiles, T.tile_cap);
+  const uint32_t gtid = block * blockDim.x + threadIdx.x, gsz = n_blocks * blockDim.x;
+  for (uint32_t t = gtid; t < n_tiles; t += gsz) {
+    const uint32_t slot = T.tile_slot[t];
+    T.slots[slot] = make_ulonglong2(TILE_EMPTY, ~0ull);
+    tile_touch[slot] = 0u;
+  }
+  uint4* cc = reinterpret_cast<uint4*>(cell_count);
+  for (uint32_t q = gtid; q < n_ptiles * 16u; q += gsz) cc[(size_t)T.tile_slot[q >> 4] * 16u + (q & 15u)] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&S->reset_done, 1u) == n_blocks - 1) {
+      StepScalars z{};
+      z.n = n_dev ? min(*n_dev, n) : n;   // slab ranks: the row count lives on the device (migration changes it without the host)
+      z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
+      z.sticky = from->sticky | from->sticky_new;
+      z.accum = from->accum | (from->status & 0xffffu);
+      z.status = from->status & ST_CARRY_MASK;
+      *S = z;
+    }
+  }
+}
+// Start of a substep that bins with k_bin: reset the set this substep uses and (mesh scenes) the layer set of the previous substep.
+__global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ prev, StepScalars* __restrict__ cur, TileTable T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_touch,
+                                               unsigned long long* __restrict__ layer_slots, uint32_t n, const uint32_t* __restrict__ n_dev, int tables_fresh) {
+  // an earlier substep stopped the run (a FAILED particle, the device clock reached its target, an exchange error): this substep is a
+  // no-op — leave the tables (the grid of the last real substep is still downloadable) and only hand the stop on
+  const uint32_t stop = prev->sticky | prev->sticky_new, carry = prev->status & ST_CARRY_MASK;
+  if (stop | carry) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      cur->sticky = stop;
+      cur->sticky_new = 0u;
+      cur->accum = prev->accum | (prev->status & 0xffffu);
+      cur->status = carry;
+      cur->bin_blocks_done = 0u;
+    }
+    return;
+  }
+  if (prev->n_layers && !tables_fresh)
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < LAYER_SLOTS; q += gridDim.x * blockDim.x) layer_slots[q] = 0ull;
+  reset_set(prev, cur, T, cell_count, tile_touch, n, n_dev, tables_fresh, blockIdx.x, gridDim.x);
+}
+
+// Binning of one particle, WARP-COLLECTIVE (all 32 lanes call it; `state`: 0 = live, 1 = tombstoned, 2 = gone / no particle):
+//   * the particle's tile (block of its base node, layer of its collider bits) is found or created in the tile table,
+//     warp-aggregated: lanes with equal keys elect one lane to touch the table;
+//   * the particle takes a slot in its cell: rank = atomicAdd(cell_count[tile*64 + cell]) (again one atomic per distinct cell per
+//     warp) — a single-pass counting sort on (tile, cell);
+//   * the tile remembers which of its 8 neighbour blocks its particles' stencils reach.
+// Writes pcell[row] / prank[row] when `row` is valid.  x must be the position the NEXT P2G will see.
 struct BinArrays {
   uint32_t* pcell;        // [n] table slot * 64 + cell, 0xffffffff for tombstoned
   uint32_t* prank;        // [n] rank inside the cell (or among the tombstoned)
@@ -476,84 +536,27 @@ struct BinArrays {
   unsigned long long* layer_slots;
   uint32_t* layer_list;
 };
-// Start of a substep: undo exactly what the previous substep left in the per-substep tables (its tiles'
-// hash slots, touch masks and cell counters; the layer set) instead of memset-ing whole allocations, and
-// initialise this substep's scalars.  `prev` / `cur` are the two halves of a double buffer, so no thread
-// of this launch reads what another one writes.
-__global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ prev, StepScalars* __restrict__ cur, TileTable T, uint32_t* __restrict__ cell_count, uint32_t* __restrict__ tile_touch,
-                                               unsigned long long* __restrict__ layer_slots, uint32_t n, const uint32_t* __restrict__ n_dev, int tables_fresh) {
-  // tables_fresh: the host has just (re)allocated and memset the tables, tile_slot holds nothing to undo
-  const uint32_t n_tiles = tables_fresh ? 0u : min(prev->n_tiles, T.tile_cap), n_ptiles = tables_fresh ? 0u : min(prev->n_ptiles, T.tile_cap);
-  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  for (uint32_t t = gtid; t < n_tiles; t += gsz) {
-    const uint32_t slot = T.tile_slot[t];
-    T.slots[slot] = make_ulonglong2(TILE_EMPTY, ~0ull);
-    tile_touch[slot] = 0u;
-  }
-  uint4* cc = reinterpret_cast<uint4*>(cell_count);
-  for (uint32_t q = gtid; q < n_ptiles * 16u; q += gsz) cc[(size_t)T.tile_slot[q >> 4] * 16u + (q & 15u)] = make_uint4(0u, 0u, 0u, 0u);
-  if (prev->n_layers && !tables_fresh)
-    for (uint32_t q = gtid; q < LAYER_SLOTS; q += gsz) layer_slots[q] = 0ull;
-  if (gtid == 0) {
-    StepScalars z{};
-    z.n = n_dev ? min(*n_dev, n) : n;   // slab ranks: the row count lives on the device (migration changes it without the host)
-    z.min_sound_key = INT32_MAX; z.min_isolated_key = INT32_MAX; z.max_velocity_key = INT32_MIN; z.min_deformation_key = INT32_MAX;
-    z.sticky = prev->sticky;
-    z.accum = prev->accum | (prev->status & 0xffffu);
-    z.status = prev->status & ST_CARRY_MASK;
-    *cur = z;
-  }
-}
-template <bool HAS_MESH, bool APPLY_FORCE>
-__global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, GoalDev G, TileTable T, BinArrays B, uint32_t n, float dt, float gx, float gy,
-                                             float gz, float factor_b) {
-  if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is (every later kernel no-ops too)
-  n = min(n, S->n);       // the launch covers an upper bound of the row count
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31;
-  bool live = false, tomb = false, gone = false;
+template <bool HAS_MESH>
+__device__ __forceinline__ void bin_warp(int state, V3 x, uint32_t bits, bool has_row, uint32_t row, const SimConsts& K, const TileTable& T, const BinArrays& B, StepScalars* S, uint32_t lane) {
+  bool live = false;
   unsigned long long key = TILE_EMPTY;
   uint32_t cell = 0, touch = 0;
-  if (i < n) {
-    // every load of the row is issued before the flags are looked at: one memory latency instead of two in the chain
-    const uint32_t flags = P.u(PFLAGS)[i];
-    const V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-    V3 v = V3{0.f, 0.f, 0.f};
-    if (APPLY_FORCE) v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-    uint32_t bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
-    gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
-    tomb = !gone && (flags & F_TOMBSTONED) != 0;
-    if (!tomb && !gone) {
-      if (APPLY_FORCE) {   // (collide has already edited v and the bits of this substep: k_collide_query / k_collide_candidates)
-        bool goal = false;
-        if (G.flags_a) {
-          const uint32_t o = P.u(PORIG)[i];
-          if ((G.flags_a[o] & F_HAS_GOAL) && (G.flags_b[o] & F_HAS_GOAL)) {
-            const float fa = 1.f - factor_b;
-            const V3 target = fa * ld3(G.goal_a, o) + factor_b * ld3(G.goal_b, o);
-            v = (target - x) / dt;
-            goal = true;
-          }
-        }
-        if (!goal) v = v + dt * V3{gx, gy, gz};
-        P.f(PV)[i] = v.x; P.f(PV + 1)[i] = v.y; P.f(PV + 2)[i] = v.z;
-      }
-      const int s0 = base_node(x.x, K.h), s1 = base_node(x.y, K.h), s2 = base_node(x.z, K.h);
-      const int b0 = floor_div4(s0), b1 = floor_div4(s1), b2 = floor_div4(s2);
-      const int lim = BLOCK_BIAS - 2;
-      if (b0 < -lim || b0 > lim || b1 < -lim || b1 > lim || b2 < -lim || b2 > lim) {
-        atomicOr(&S->status, ST_KEY_RANGE);
-      } else {
-        live = true;
-        const uint32_t layer = HAS_MESH ? layer_find_or_insert(B.layer_slots, B.layer_list, bits, S) : 0u;
-        key = tile_key_pack(b0, b1, b2, layer);
-        cell = ((uint32_t)(s0 & 3) << 4) | ((uint32_t)(s1 & 3) << 2) | (uint32_t)(s2 & 3);
-        // neighbour offsets reached by the 3-node stencil: +1 on an axis iff the in-block coordinate >= 2
-        touch = 1u;
-        if (s0 & 2) touch |= touch << 1;
-        if (s1 & 2) touch |= touch << 2;
-        if (s2 & 2) touch |= touch << 4;
-      }
+  if (state == 0) {
+    const int s0 = base_node(x.x, K.h), s1 = base_node(x.y, K.h), s2 = base_node(x.z, K.h);
+    const int b0 = floor_div4(s0), b1 = floor_div4(s1), b2 = floor_div4(s2);
+    const int lim = BLOCK_BIAS - 2;
+    if (b0 < -lim || b0 > lim || b1 < -lim || b1 > lim || b2 < -lim || b2 > lim) {
+      atomicOr(&S->status, ST_KEY_RANGE);
+    } else {
+      live = true;
+      const uint32_t layer = HAS_MESH ? layer_find_or_insert(B.layer_slots, B.layer_list, bits, S) : 0u;
+      key = tile_key_pack(b0, b1, b2, layer);
+      cell = ((uint32_t)(s0 & 3) << 4) | ((uint32_t)(s1 & 3) << 2) | (uint32_t)(s2 & 3);
+      // neighbour offsets reached by the 3-node stencil: +1 on an axis iff the in-block coordinate >= 2
+      touch = 1u;
+      if (s0 & 2) touch |= touch << 1;
+      if (s1 & 2) touch |= touch << 2;
+      if (s2 & 2) touch |= touch << 4;
     }
   }
   // ---- tile: one table access per distinct key in the warp
@@ -566,7 +569,8 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   if (live && (int)lane == leader && tile != ~0u) atomicOr(&B.tile_touch[tile], tm);  // result unused: a fire-and-forget RED
   // ---- rank in the cell: one atomic per distinct (tile, cell) in the warp
   const bool binned = live && tile != ~0u;
-  const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : (gone ? 0xfffffffdu : 0xfffffffeu));
+  const bool tomb = state == 1;
+  const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : (state == 2 ? 0xfffffffdu : 0xfffffffeu));
   const unsigned cpeers = __match_any_sync(SVB_FULL, ci);
   const int cleader = __ffs(cpeers) - 1;
   uint32_t base = 0;
@@ -575,19 +579,58 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
     else if (tomb) base = atomicAdd(&S->n_tomb, (uint32_t)__popc(cpeers));
   }
   base = __shfl_sync(SVB_FULL, base, cleader);
-  if (i < n) {
-    B.pcell[i] = ci;
-    B.prank[i] = base + __popc(cpeers & ((1u << lane) - 1u));
+  if (has_row) {
+    B.pcell[row] = ci;
+    B.prank[row] = base + __popc(cpeers & ((1u << lane) - 1u));
   }
+}
+
+// k_bin — binning as its own pass, one thread per particle in the CURRENT order: the first substep after an upload, every substep
+// of a collider scene (after its collide pass), and the redo after a tile-capacity overflow.  (The external force moved into P2G:
+// the forced velocity is only ever read there — collect_velocity.rs overwrites v — so it never has to be stored.)
+template <bool HAS_MESH>
+__global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimConsts K, TileTable T, BinArrays B, uint32_t n) {
+  if (S->sticky) return;  // an earlier substep hit a simulation-level error: leave the state as it is (every later kernel no-ops too)
+  n = min(n, S->n);       // the launch covers an upper bound of the row count
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  int state = 2;
+  V3 x = V3{0.f, 0.f, 0.f};
+  uint32_t bits = 0u;
+  if (i < n) {
+    // every load of the row is issued before the flags are looked at: one memory latency instead of two in the chain
+    const uint32_t flags = P.u(PFLAGS)[i];
+    x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+    bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
+    const bool gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
+    state = gone ? 2 : ((flags & F_TOMBSTONED) ? 1 : 0);
+  }
+  bin_warp<HAS_MESH>(state, x, bits, i < n, i, K, T, B, S, lane);
   if (i == 0) S->bin_blocks_done = 1u;   // "this substep was binned" (a sticky error makes the kernel return at the top instead)
 }
 
 // per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile's slot range
 // [first, end) in the binned order (S->n_live ends up as the number of binned particles), and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
 // (update_grid_nodes.rs:102-108)
-__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, TileTable T, uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, uint32_t* __restrict__ slot_first,
-                                                 const uint32_t* __restrict__ tile_touch, int* __restrict__ nbr) {
-  if (SVB_ABORTED(S)) return;
+// `Sprev` != null: this substep's set was filled ahead of time by the previous substep's G2P, so this is the FIRST kernel of the substep
+// and it folds what the previous substep's back half raised (a FAILED particle, table status bits, exchange errors) into this
+// substep's scalars — they were initialised before that back half ran — plus, on slab ranks, the row count migration left behind.
+__global__ void __launch_bounds__(256) k_offsets(StepScalars* S, const StepScalars* __restrict__ Sprev, uint32_t n_rows, const uint32_t* __restrict__ n_dev, TileTable T,
+                                                 uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, uint32_t* __restrict__ slot_first, const uint32_t* __restrict__ tile_touch,
+                                                 int* __restrict__ nbr) {
+  bool aborted = SVB_ABORTED(S);
+  if (Sprev) {
+    const uint32_t carry = Sprev->status & ST_CARRY_MASK, stop = Sprev->sticky | Sprev->sticky_new;
+    aborted = aborted || carry || stop;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      S->sticky |= stop;
+      S->accum |= Sprev->accum | (Sprev->status & 0xffffu);
+      if (carry) atomicOr(&S->status, carry);
+      S->n = n_dev ? min(*n_dev, n_rows) : n_rows;
+      if (!aborted) S->bin_blocks_done = 1u;   // "this substep was binned"
+    }
+  }
+  if (aborted) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t n_ptiles = min(S->n_ptiles, T.tile_cap);   // final: only k_bin creates particle tiles
@@ -669,13 +712,23 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* a, const uint32_t
 // buffer, so the physical permutation of the 136-byte state costs no pass of its own: consecutive
 // slots come from (nearly) consecutive rows of the previous order, the gathers stay coalesced.
 // The same launch also clears the grid tiles of this substep (blocks beyond the particle range).
+// With `prep.blocks` > 0 the last blocks also prepare the OTHER front set for the G2P of this substep, which bins the advanced
+// positions into it (reset_set; its scalars start from this substep's, k_offsets of the next substep folds the rest).
+struct PrepareNext {
+  StepScalars* S; TileTable T; uint32_t* cell_count; uint32_t* tile_touch;
+  uint32_t n; const uint32_t* n_dev; int tables_fresh; uint32_t blocks;
+};
 __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank, const uint32_t* __restrict__ cell_offset,
                                                      const uint32_t* __restrict__ slot_first, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
-                                                     unsigned long long* __restrict__ node_mask, uint32_t tile_cap) {
+                                                     unsigned long long* __restrict__ node_mask, uint32_t tile_cap, PrepareNext prep) {
   if (SVB_ABORTED(S)) return;
+  if (blockIdx.x >= gridDim.x - prep.blocks) {
+    reset_set(S, prep.S, prep.T, prep.cell_count, prep.tile_touch, prep.n, prep.n_dev, prep.tables_fresh, blockIdx.x - (gridDim.x - prep.blocks), prep.blocks);
+    return;
+  }
   if (blockIdx.x >= invert_blocks) {
     const size_t total = (size_t)min(S->n_tiles, tile_cap) * 64;
-    const size_t stride = (size_t)(gridDim.x - invert_blocks) * blockDim.x;
+    const size_t stride = (size_t)(gridDim.x - prep.blocks - invert_blocks) * blockDim.x;
     for (size_t q = (size_t)(blockIdx.x - invert_blocks) * blockDim.x + threadIdx.x; q < total; q += stride) {
       grid[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (node_mask && (q & 63) == 0) node_mask[q >> 6] = 0ull;
@@ -762,8 +815,16 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// The external force (external_force.rs:17-50) is applied here, in registers: v + dt g, or (goal - x) / dt for a goal particle.  The
+// forced velocity is only ever read by the scatter (collect_velocity.rs overwrites v), so it is never stored.
+struct ForceIn {
+  GoalDev G;
+  float dt, gx, gy, gz, factor_b;   // dt: the time step ExternalForce sees (with adaptive steps the one BEFORE LimitTimeStepBeforeForce)
+  const DtState* D;                 // adaptive steps: dt (scatter and force), gravity and the frame factor come from the device clock
+};
+template <bool HAS_GOALS>
 __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint2* __restrict__ group_range, const int* __restrict__ nbr,
-                                                           StepScalars* S, float4* __restrict__ grid, float h, float dt) {
+                                                           StepScalars* S, float4* __restrict__ grid, float h, float dt, ForceIn force) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   float* stage_all = reinterpret_cast<float*>(smem_raw + P2G_WARPS * TILE_NODES * 16);
@@ -772,6 +833,10 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   float4* my_tile = tiles + warp * TILE_NODES;
   float* stage = stage_all + warp * 32 * STAGE_STRIDE;
   if (SVB_ABORTED(S)) return;
+  if (force.D) {
+    dt = force.D->allowed;
+    force.dt = force.D->dt_force; force.gx = force.D->g[0]; force.gy = force.D->g[1]; force.gz = force.D->g[2]; force.factor_b = force.D->factor_b;
+  }
   const uint32_t n_groups = S->n_ptiles;
   const float scaling = dt * 4.f / (h * h);
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
@@ -830,7 +895,21 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
 #pragma unroll
           for (int q = 0; q < 9; ++q) A.m[q] -= sj * cauchy.m[q];
         }
-        const float mv0 = mass * P.f(PV)[i], mv1 = mass * P.f(PV + 1)[i], mv2 = mass * P.f(PV + 2)[i];
+        V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+        {   // ExternalForce, after the collide pass of the same substep like phase/mod.rs:27-41
+          bool goal = false;
+          if (HAS_GOALS) {
+            const uint32_t o = P.u(PORIG)[i];
+            if ((force.G.flags_a[o] & F_HAS_GOAL) && (force.G.flags_b[o] & F_HAS_GOAL)) {
+              const float fa = 1.f - force.factor_b;
+              const V3 target = fa * ld3(force.G.goal_a, o) + force.factor_b * ld3(force.G.goal_b, o);
+              v = (target - V3{x0, x1, x2}) / force.dt;
+              goal = true;
+            }
+          }
+          if (!goal) v = v + force.dt * V3{force.gx, force.gy, force.gz};
+        }
+        const float mv0 = mass * v.x, mv1 = mass * v.y, mv2 = mass * v.z;
         const float t0 = n0 - (float)s0, t1 = n1 - (float)s1, t2 = n2 - (float)s2;
 #pragma unroll
         for (int q = 0; q < 9; ++q) A.m[q] *= h;
@@ -990,10 +1069,15 @@ struct MigrateCut {
   uint32_t* counts;   // [2]
   uint32_t cap;
 };
-template <bool FUSE, bool REDUCE, bool MELDED, bool SLAB>
+// BIN: the thread that holds a particle's ADVANCED position also bins it for the next substep, into the other front set (bin_warp):
+// the next substep then starts at k_offsets — no k_bin pass over the particles, no k_begin launch (scenes without a collider mesh).
+struct BinNext {
+  StepScalars* S; TileTable T; BinArrays B;
+};
+template <bool FUSE, bool REDUCE, bool MELDED, bool SLAB, bool BIN>
 __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
                                                         const uint2* __restrict__ group_range, const int* __restrict__ nbr, StepScalars* S,
-                                                        const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc) {
+                                                        const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
   __shared__ int s_nbr[8];
@@ -1023,7 +1107,12 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       tile[t] = MELDED ? v : finish_node(v);
     }
     __syncthreads();
-    for (uint32_t i = start + threadIdx.x; i < end; i += blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t base = start + (threadIdx.x & ~31u); base < end; base += blockDim.x) {   // warp-uniform trip count (bin_warp is warp-collective)
+      const uint32_t i = base + lane;
+      int bin_state = 2;
+      V3 bin_x = V3{0.f, 0.f, 0.f};
+      if (i < end) {
       const uint32_t si = src_of[i];   // (fetching the next iteration's row index one iteration ahead: measured neutral, r1n)
       V3 x = V3{P.f(PX)[si], P.f(PX + 1)[si], P.f(PX + 2)[si]};
       // issue the loads of everything this thread carries / updates before the gather needs them
@@ -1097,6 +1186,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
         else { flags |= F_FAILED; failed = 1; }
         const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
         if (!within) flags |= F_TOMBSTONED;
+        bool leaving = false;
         // cheap filter first (x * (1/h) is within a small fraction of a cell of the exact x / h): only particles within half a
         // cell of a cut evaluate the bit-exact base node
         const float approx_node = x.x * inv_h - 0.5f;
@@ -1108,9 +1198,12 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
               const int side = bx < mc.lo ? 0 : 1;
               const uint32_t slot = atomicAdd(&mc.counts[side], 1u);
               if (slot < mc.cap) mc.list[(size_t)side * mc.cap + slot] = i;
+              leaving = true;
             }
           }
         }
+        bin_state = leaving ? 2 : ((flags & F_TOMBSTONED) ? 1 : 0);
+        bin_x = x;
       }
       D.f(PX)[i] = x.x; D.f(PX + 1)[i] = x.y; D.f(PX + 2)[i] = x.z;
       D.f(PV)[i] = v.x; D.f(PV + 1)[i] = v.y; D.f(PV + 2)[i] = v.z;
@@ -1119,6 +1212,8 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
 #pragma unroll
       for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
       D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
+      }
+      if (BIN) bin_warp<false>(bin_state, bin_x, 0u, i < end, i, K, bn.T, bn.B, bn.S, lane);
     }
   }
   // tombstoned particles take no part in P2G / G2P: carry their rows over as they are (behind the live ones)
@@ -1128,6 +1223,10 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       const uint32_t i = src_of[j];
 #pragma unroll 1
       for (int f = 0; f < NFIELDS; ++f) D.base[(size_t)f * D.cap + j] = P.base[(size_t)f * P.cap + i];
+      if (BIN) {   // stays tombstoned: behind the live rows of the next substep as well
+        bn.B.pcell[j] = 0xffffffffu;
+        bn.B.prank[j] = atomicAdd(&bn.S->n_tomb, 1u);
+      }
     }
   }
   if (REDUCE) {
@@ -1141,43 +1240,180 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       if (red_def != INT32_MAX) atomicMin(&S->min_deformation_key, red_def);
     }
   }
-  if (FUSE && failed) atomicOr(&S->sticky, 8u /*SVB_PARTICLE_CLOSE_TO_INVERTED*/);
+  if (FUSE && failed) atomicOr(&S->sticky_new, 8u /*SVB_PARTICLE_CLOSE_TO_INVERTED*/);
 }
 
-// advance + cull as its own pass (adaptive time stepping: dt is only known after the G2P reductions)
-__global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, float dt) {
+// ------------------------------------------------------------------------------------------------
+// adaptive time stepping with the state machine on the device (DtState, svb_device.cuh)
+__device__ __forceinline__ float dt_total_min(float a, float b) { return total_key(b) < total_key(a) ? b : a; }   // min_by(f32::total_cmp) keeps the first minimum
+__device__ __forceinline__ float dt_allowed_without_prior(const DtState& d) {   // adaptive_time_step_state.rs:36-47
+  const float fmax = 3.402823466e+38f;
+  float r = d.max_dt;
+  r = dt_total_min(r, (d.has & 1u) ? d.by_velocity : fmax);
+  r = dt_total_min(r, (d.has & 2u) ? d.by_deformation : fmax);
+  r = dt_total_min(r, (d.has & 8u) ? d.by_sound : fmax);
+  r = dt_total_min(r, (d.has & 4u) ? d.by_isolated : fmax);
+  return r;
+}
+__device__ __forceinline__ float dt_allowed(const DtState& d) {   // :49-54
+  float r = dt_allowed_without_prior(d);
+  for (uint32_t q = 0; q < d.prior_len; ++q) r = dt_total_min(r, d.prior[q]);
+  return r;
+}
+__device__ __forceinline__ void dt_push(DtState& d) {   // :56-63 (pop when len > 10, then push: at most 11 entries)
+  if (d.prior_len > 10) {
+    for (uint32_t q = 1; q < d.prior_len; ++q) d.prior[q - 1] = d.prior[q];
+    --d.prior_len;
+  }
+  d.prior[d.prior_len++] = dt_allowed_without_prior(d);
+}
+// frame factor + gravity of the substep that starts at d.time; false when the loaded frame is the wrong one
+__device__ __forceinline__ bool dt_interpolate_input(DtState& d) {
+  const double frame_time = d.time * d.fps;
+  if ((unsigned long long)floor(frame_time) != d.frame) return false;
+  d.factor_b = (float)fmod(frame_time, 1.0);
+  const float fa = 1.f - d.factor_b;
+  for (int k = 0; k < 3; ++k) d.g[k] = fa * d.ga[k] + d.factor_b * d.gb[k];
+  return true;
+}
+// LimitTimeStepBeforeForce (limit_time_step.rs:25-33) from the reductions in next_*; resets them for the next round
+__device__ __forceinline__ void dt_limit_before_force(DtState& d) {
+  const bool any = d.next_live > 0;
+  d.has = (d.has & ~12u) | (any ? 12u : 0u);
+  if (any) {
+    d.by_sound = total_unkey(d.next_min_sound_key);
+    d.by_isolated = total_unkey(d.next_min_isolated_key);
+  }
+  dt_push(d);
+  d.allowed = dt_allowed(d);
+  d.next_min_sound_key = INT32_MAX; d.next_min_isolated_key = INT32_MAX; d.next_live = 0;
+}
+// Start of an svb_advance call (one thread).  The host has written time / target / max_dt / fps / frame / gravities and cleared `stop`.
+// `S` = the scalars of the substep about to run (its sticky words were cleared by the host).
+__global__ void k_dt_open(DtState* D, StepScalars* S) {
+  DtState d = *D;
+  uint32_t stop = 0;
+  d.substeps = 0;
+  d.allowed = dt_allowed(d);                              // max_time_step may have changed (cpu_state.rs:164)
+  if (d.allowed == 0.f) stop |= ST_STOP_ZERO_DT;          // cpu_state.rs:170-172
+  if (!(d.time < d.target)) stop |= ST_STOP_DONE;
+  else if (!dt_interpolate_input(d)) stop |= ST_STOP_FRAME;
+  d.dt_force = d.allowed;
+  if (!stop) {
+    dt_limit_before_force(d);
+    if (d.allowed == 0.f) stop |= ST_STOP_ZERO_DT;
+  }
+  d.stop = stop;
+  *D = d;
+  if (stop) S->sticky |= stop;   // no kernel of this substep has started yet: the whole substep is a no-op
+}
+// LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223) from the G2P reductions of this substep
+__global__ void k_dt_integrate(DtState* D, StepScalars* S) {
+  if (SVB_ABORTED(S)) return;
+  DtState d = *D;
+  const bool any = S->n_live > 0;
+  const float max_vel = any ? total_unkey(S->max_velocity_key) : 0.f;
+  const bool has_vel = any && max_vel != 0.f;
+  d.has = (d.has & ~3u) | (has_vel ? 1u : 0u) | (any ? 2u : 0u);
+  if (has_vel) d.by_velocity = 0.5f * d.h / max_vel;
+  if (any) d.by_deformation = total_unkey(S->min_deformation_key);
+  dt_push(d);
+  d.allowed = dt_allowed(d);
+  *D = d;
+  if (d.allowed == 0.f) { D->stop |= ST_STOP_ZERO_DT; atomicOr(&S->status, ST_ZERO_DT); }   // the advance of this substep must not run
+}
+// End of a substep: the clock moves on (cpu_state.rs:187-190), then everything the NEXT substep needs before its first kernel:
+// the run-is-over test, the frame factor and gravity, and LimitTimeStepBeforeForce from the limits k_advance reduced on the advanced F.
+__global__ void k_dt_tail(DtState* D, StepScalars* S) {
+  if (SVB_ABORTED(S)) return;
+  if (S->sticky_new & 0xffffu) return;   // a FAILED particle: the reference returns from the Advance phase without moving the clock (cpu_state.rs:176-184)
+  DtState d = *D;
+  d.time += (double)d.allowed;
+  ++d.substeps;
+  uint32_t stop = 0;
+  if (d.allowed == 0.f) stop |= ST_STOP_ZERO_DT;
+  if (!(d.time < d.target)) stop |= ST_STOP_DONE;
+  else if (!dt_interpolate_input(d)) stop |= ST_STOP_FRAME;
+  d.dt_force = d.allowed;
+  if (!stop) {
+    dt_limit_before_force(d);
+    if (d.allowed == 0.f) stop |= ST_STOP_ZERO_DT;
+  }
+  d.stop |= stop;
+  *D = d;
+  if (stop) atomicOr(&S->sticky_new, stop);
+}
+
+// advance + cull as its own pass (adaptive time stepping: dt is only known after the G2P reductions).  Also — it holds the advanced
+// position and F — the binning of the next substep (BIN, scenes without a collider mesh) and the per-particle limits of the next
+// substep's LimitTimeStepBeforeForce (limit_time_step.rs:35-182).  One thread per row of the binned buffer, tombstoned rows included.
+template <bool BIN>
+__global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn) {
+  if (SVB_ABORTED(S)) return;
+  n = min(n, S->n_live + S->n_tomb);
+  const float dt = D->allowed;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t flags = P.u(PFLAGS)[i];
-  if (flags & F_TOMBSTONED) return;
-  V3 x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-  const V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-  M3 C, F;
+  const uint32_t lane = threadIdx.x & 31;
+  int bin_state = 2;
+  V3 x = V3{0.f, 0.f, 0.f};
+  int ks = INT32_MAX, ki = INT32_MAX;
+  uint32_t live = 0;
+  if (i < n) {
+    uint32_t flags = P.u(PFLAGS)[i];
+    bin_state = 1;
+    if (!(flags & F_TOMBSTONED)) {
+      x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+      const V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+      M3 C, F;
 #pragma unroll
-  for (int q = 0; q < 9; ++q) { C.m[q] = P.f(PC + q)[i]; F.m[q] = P.f(PF + q)[i]; }
-  x = x + v * dt;
-  const M3 CF = mul(C, F);
+      for (int q = 0; q < 9; ++q) { C.m[q] = P.f(PC + q)[i]; F.m[q] = P.f(PF + q)[i]; }
+      const float p0 = P.f(PP0)[i], p1 = P.f(PP1)[i];
+      x = x + v * dt;
+      const M3 CF = mul(C, F);
 #pragma unroll
-  for (int q = 0; q < 9; ++q) F.m[q] += CF.m[q] * dt;
-  float e;
-  if (return_map_and_energy(flags, P.f(PP0)[i], P.f(PP1)[i], (flags & F_USE_SAND_ALPHA) ? P.f(PALPHA)[i] : 0.f, F, e)) energy[i] = e;
-  else { flags |= F_FAILED; atomicOr(&S->sticky, 8u); }
-  const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
-  if (!within) flags |= F_TOMBSTONED;
-  P.f(PX)[i] = x.x; P.f(PX + 1)[i] = x.y; P.f(PX + 2)[i] = x.z;
+      for (int q = 0; q < 9; ++q) F.m[q] += CF.m[q] * dt;
+      float e;
+      if (return_map_and_energy(flags, p0, p1, (flags & F_USE_SAND_ALPHA) ? P.f(PALPHA)[i] : 0.f, F, e)) energy[i] = e;
+      else { flags |= F_FAILED; atomicOr(&S->sticky_new, 8u); }
+      const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
+      if (!within) flags |= F_TOMBSTONED;
+      P.f(PX)[i] = x.x; P.f(PX + 1)[i] = x.y; P.f(PX + 2)[i] = x.z;
 #pragma unroll
-  for (int q = 0; q < 9; ++q) P.f(PF + q)[i] = F.m[q];
-  P.u(PFLAGS)[i] = flags;
+      for (int q = 0; q < 9; ++q) P.f(PF + q)[i] = F.m[q];
+      P.u(PFLAGS)[i] = flags;
+      if (within) {
+        bin_state = 0;
+        const ParticleLimits l = particle_time_step_limits((flags & F_IS_FLUID) != 0, p0, p1, P.f(PMASS)[i], P.f(PVOL)[i], F, K.h);
+        ks = total_key(l.by_sound);
+        ki = total_key(l.by_isolated);
+        live = 1;
+      }
+    }
+  }
+  if (BIN) bin_warp<false>(bin_state, x, 0u, i < n, i, K, bn.T, bn.B, bn.S, lane);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ks = min(ks, __shfl_xor_sync(SVB_FULL, ks, o));
+    ki = min(ki, __shfl_xor_sync(SVB_FULL, ki, o));
+    live += __shfl_xor_sync(SVB_FULL, live, o);
+  }
+  if (lane == 0 && live) {
+    atomicMin(&D->next_min_sound_key, ks);
+    atomicMin(&D->next_min_isolated_key, ki);
+    atomicAdd(&D->next_live, live);
+  }
 }
 
-// limit_time_step.rs:25-182: global minima of the sound-speed and isolated-particle bounds
-__global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, StepScalars* S, float h, uint32_t n) {
+// limit_time_step.rs:25-182 as its own pass (the first substep after an upload: no k_advance has reduced the limits yet):
+// global minima of the sound-speed and isolated-particle bounds into DtState::next_*
+__global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, DtState* D, float h, uint32_t n, const uint32_t* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   int ks = INT32_MAX, ki = INT32_MAX;
   uint32_t live = 0;
   if (i < n) {
     const uint32_t flags = P.u(PFLAGS)[i];
-    if (!(flags & F_TOMBSTONED)) {
+    if (!(flags & (F_TOMBSTONED | F_GONE))) {
       M3 F;
 #pragma unroll
       for (int q = 0; q < 9; ++q) F.m[q] = P.f(PF + q)[i];
@@ -1194,9 +1430,9 @@ __global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, StepScalars*
     live += __shfl_xor_sync(SVB_FULL, live, o);
   }
   if ((threadIdx.x & 31) == 0 && live) {
-    atomicMin(&S->min_sound_key, ks);
-    atomicMin(&S->min_isolated_key, ki);
-    atomicAdd(&S->live_count, live);
+    atomicMin(&D->next_min_sound_key, ks);
+    atomicMin(&D->next_min_isolated_key, ki);
+    atomicAdd(&D->next_live, live);
   }
 }
 
@@ -1458,7 +1694,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
       }
       mc.counts[side] = 0;
     }
-    const uint32_t err = atomicOr(&S->sticky, 0u);
+    const uint32_t err = (S->sticky | atomicOr(&S->sticky_new, 0u)) & 0xffffu;   // simulation-level errors only: stop bits are every rank's own
     for (int r = 0; r < peers.n_ranks; ++r)
       if (peers.err_val[r]) { st_sys(peers.err_val[r], err); st_sys(peers.err_seq[r], seq); }
     *blocks_done = 0;
@@ -1468,7 +1704,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
 // and fold every rank's error word into this rank's (a FAILED particle anywhere stops every rank after this substep)
 __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __restrict__ energy, StepScalars* S, const SlabHeader* __restrict__ hdr, const uint32_t* __restrict__ rows_left,
                                                       const uint32_t* __restrict__ rows_right, int has_left, int has_right, int rank, int n_ranks, uint32_t seq, uint32_t* __restrict__ n_dev,
-                                                      int between_substeps) {
+                                                      int between_substeps, SimConsts K, BinNext bn, int bin) {
   __shared__ uint32_t s_c[2];
   if (threadIdx.x == 0) {
     uint32_t c[2] = {0, 0};
@@ -1488,7 +1724,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
           if (wait_seq(&hdr->err_seq[r], seq)) err |= ld_sys(&hdr->err_val[r]);
           else atomicOr(&S->status, ST_COMM_TIMEOUT);
         }
-      if (err) atomicOr(&S->sticky, err);
+      if (err) atomicOr(&S->sticky_new, err);
     }
   }
   __syncthreads();
@@ -1498,12 +1734,23 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
   const uint32_t room = (uint32_t)P.cap > base ? (uint32_t)P.cap - base : 0u;
   if (cl + cr > room) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_OVERFLOW); }
   const uint32_t total = min(cl + cr, room);
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
-    const uint32_t* row = q < cl ? rows_left + (size_t)q * MIG_WORDS : rows_right + (size_t)(q - cl) * MIG_WORDS;
-    const uint32_t i = base + q;
+  const bool ran = S->bin_blocks_done != 0 && !(S->sticky);   // this substep was a real one (not the no-op after a stop)
+  const uint32_t lane = threadIdx.x & 31;
+  // warp-uniform trip count: bin_warp (the arrivals join the next substep's bins, like the rows G2P wrote) is warp-collective
+  for (uint32_t q0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); q0 < total; q0 += gridDim.x * blockDim.x) {
+    const uint32_t q = q0 + lane;
+    int state = 2;
+    V3 x = V3{0.f, 0.f, 0.f};
+    if (q < total) {
+      const uint32_t* row = q < cl ? rows_left + (size_t)q * MIG_WORDS : rows_right + (size_t)(q - cl) * MIG_WORDS;
+      const uint32_t i = base + q;
 #pragma unroll
-    for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
-    energy[i] = __uint_as_float(row[NFIELDS]);
+      for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
+      energy[i] = __uint_as_float(row[NFIELDS]);
+      x = V3{__uint_as_float(row[PX]), __uint_as_float(row[PX + 1]), __uint_as_float(row[PX + 2])};
+      state = (row[PFLAGS] & F_TOMBSTONED) ? 1 : 0;
+    }
+    if (bin && ran) bin_warp<false>(state, x, 0u, q < total, base + q, K, bn.T, bn.B, bn.S, lane);
   }
   // a substep that was a no-op on every rank (an earlier substep failed: k_bin returned at once) keeps the row count
   if (between_substeps) {

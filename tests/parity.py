@@ -25,13 +25,16 @@ FIELDS = ("positions", "velocities", "position_gradients", "velocity_gradients")
 #   positions            floor = h            (the error is measured in grid cells: the origin is arbitrary)
 #   velocities           floor = 1e-3 * max_i ||v_i||
 #   position_gradients   floor = 1            (F is O(1) by construction, I at rest)
-#   velocity_gradients   floor = 1e-3 * max(max_i ||C_i||, 0.05 * max_i ||v_i|| / h)     (C = 4/h^2 sum w v (x_n - x)^T)
+#   velocity_gradients   floor = 1e-3 * max_i ||v_i|| / h     (C = 4/h^2 sum w v (x_n - x)^T enters the path as C*h next to v — scatter_momentum.rs:60,
+#                        advance_particles.rs:44 — so the floor is the velocity floor divided by h; in rigid motion C is pure summation noise)
 # Bounds asserted on the percentiles of e over the live particles (P50, P99, P99.9, max):
 PCT = (50.0, 99.0, 99.9, 100.0)
-PCT_STEP = {"positions": (1e-6, 1e-5, 5e-5, 5e-4), "velocities": (1e-5, 2e-4, 1e-3, 1e-2), "position_gradients": (1e-6, 1e-5, 5e-5, 1e-3),
-            "velocity_gradients": (1e-4, 2e-3, 1e-2, 1e-1)}            # one substep from identical state
-PCT_RUN = {"positions": (1e-4, 1e-3, 5e-3, 5e-2), "velocities": (1e-3, 1e-2, 5e-2, 5e-1), "position_gradients": (1e-4, 1e-3, 5e-3, 5e-2),
-           "velocity_gradients": (1e-2, 1e-1, 5e-1, 2.0)}              # tens to hundreds of substeps (errors compound through contact)
+# (measured on B200, profiles/r2_parity_percentiles.txt: one substep x/v/F max 1e-7 / 6e-7 / 1.2e-7, C max 1.8e-3; 12-40 substeps with
+#  colliders, sand and fluid: x/v/F max 4e-6 / 7e-4 / 4e-6, C max 1e-2 — the bounds leave about one order of magnitude)
+PCT_STEP = {"positions": (2e-7, 1e-6, 1e-6, 2e-6), "velocities": (1e-6, 3e-6, 5e-6, 1e-5), "position_gradients": (5e-7, 1e-6, 2e-6, 5e-6),
+            "velocity_gradients": (1e-3, 3e-3, 4e-3, 5e-3)}            # one substep from identical state
+PCT_RUN = {"positions": (1e-5, 1e-4, 5e-4, 5e-3), "velocities": (1e-4, 1e-3, 5e-3, 5e-2), "position_gradients": (1e-5, 1e-4, 5e-4, 5e-3),
+           "velocity_gradients": (1e-2, 3e-2, 5e-2, 1e-1)}             # tens to hundreds of substeps (errors compound through contact)
 
 
 def particle_relative_errors(got, ref, name, h, mask=None):
@@ -59,7 +62,7 @@ def particle_relative_errors(got, ref, name, h, mask=None):
     elif name == "position_gradients":
         floor = 1.0
     else:
-        floor = 1e-3 * max(float(mag.max()), 0.05 * vmax / float(h))
+        floor = 1e-3 * vmax / float(h)
     floor = max(floor, 1e-30)
     return np.linalg.norm(a - b, axis=1) / np.maximum(mag, floor)
 

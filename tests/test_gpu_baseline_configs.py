@@ -38,6 +38,7 @@ def test_config2_million_jelly_binning_every_substep():
     scene = scenes.jelly_collision(side=80)
     assert scene.n == 1_024_000
     scene.io_state.particles.velocities[:, 0] *= 8.0   # the 2h gap closes after ~5 substeps: 95 of the 100 substeps are in contact
+    scene.frame_input.consts.frames_per_second = 1     # one long frame: no keyframe reload inside the loop
     h = scene.frame_input.consts.scaled_grid_node_size()
     dt = scene.time_step
     o, g = _states(scene)

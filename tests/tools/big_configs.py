@@ -48,7 +48,10 @@ def run(name, scale, steps=10, warm=3):
     gm = float(st.grid_nodes.masses.sum(dtype=np.float64))
     pm = float(p0.mass[live].sum(dtype=np.float64))
     out["grid_mass_rel_err"] = abs(gm - pm) / pm
-    assert out["grid_mass_rel_err"] < 1e-4, out
+    # without collider layers the melded grid holds every particle's mass exactly once; with layers meld_grid.rs:41-59 adds the mass of
+    # every compatible sibling to each of them, so the sum over (node, bits) entries counts shared mass once per sibling: >= particle mass
+    n_layers = int(np.unique(st.grid_nodes.collider_bits).shape[0])
+    assert (out["grid_mass_rel_err"] < 1e-4) if n_layers == 1 else (pm * (1 - 1e-4) <= gm <= pm * n_layers), out
     # materials are carried, never mixed up by the re-bin
     for f in ("mass", "initial_volume", "mu_or_bulk_modulus", "lambda_or_exponent", "sand_alpha"):
         assert np.array_equal(getattr(p1, f), getattr(p0, f)), f
