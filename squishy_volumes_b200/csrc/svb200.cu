@@ -234,7 +234,7 @@ TileTable tile_table(SvbHandle* h, int which) {
 TileTable tile_table(SvbHandle* h) { return tile_table(h, h->s_cur); }
 BinArrays bin_arrays(SvbHandle* h, int which) {
   auto& f = h->fs[which];
-  return BinArrays{h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), f.cell_count.as<uint32_t>(), f.tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>()};
+  return BinArrays{h->pcell.as<uint32_t>(), f.cell_count.as<uint32_t>(), f.tile_touch.as<uint32_t>(), h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>()};
 }
 int memset_fresh_set(SvbHandle* h, int which) {
   auto& f = h->fs[which];
@@ -283,9 +283,10 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool redo) {
       uint32_t* candidates = h->prank.as<uint32_t>();   // free until k_bin writes the ranks
       k_collide_query<<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, n);
       LAUNCH_CHECK();
-      k_collide_small<<<148 * 8, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, in.dt, dt_ref(h, in));
-      LAUNCH_CHECK();
-      k_collide_big<<<148 * 8, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, in.dt, dt_ref(h, in));
+      const uint32_t nc = h->M.n_colliders;
+#define SVB_CAND(NC) k_collide_cand<NC><<<148 * 16, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, in.dt, dt_ref(h, in))
+      if (nc <= 1) SVB_CAND(1); else if (nc <= 2) SVB_CAND(2); else if (nc <= 4) SVB_CAND(4); else SVB_CAND(16);
+#undef SVB_CAND
       LAUNCH_CHECK();
     }
     const BinArrays B = bin_arrays(h, h->s_cur);
@@ -322,7 +323,7 @@ int enqueue_rebin(SvbHandle* h, bool prepare_next) {
     N.fresh = false;
   }
   const uint32_t invert_blocks = blocks_for(n, 256);
-  k_invert_zero<<<invert_blocks + 148 * 2 + prep.blocks, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), h->prank.as<uint32_t>(), F.cell_count.as<uint32_t>(), F.slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n,
+  k_invert_zero<<<invert_blocks + 148 * 2 + prep.blocks, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), F.cell_count.as<uint32_t>(), F.slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n,
                                                                       invert_blocks, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap, prep);
   LAUNCH_CHECK();
   h->masks_valid = false;
@@ -433,7 +434,7 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next,
   const MigrateCut mc = cut ? *cut : MigrateCut{};
   BinNext bn{};
   if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
-#define SVB_G2P(F_, R_, M_, SL_, B_) k_g2p<F_, R_, M_, SL_, B_><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn)
+#define SVB_G2P(F_, R_, M_, SL_, B_) k_g2p<F_, R_, M_, SL_, B_><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn, F.tile_key.as<unsigned long long>())
   if (fuse && cut) {
     if (has_mesh) SVB_G2P(true, false, true, true, false);
     else if (bin_next) SVB_G2P(true, false, false, true, true);

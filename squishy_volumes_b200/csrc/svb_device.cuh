@@ -97,6 +97,7 @@ struct StepScalars {
   uint32_t n;          // resident particles (incl. tombstoned)
   uint32_t n_live;     // particles with a bin (not tombstoned)
   uint32_t n_tomb;
+  uint32_t tomb_cursor; // k_invert_zero: next free row among the tombstoned (behind the live rows)
   uint32_t n_tiles;    // active (block, layer) grid tiles
   uint32_t n_ptiles;   // tiles that own particles = ids [0, n_ptiles): the work list of P2G / G2P
   uint32_t n_layers;   // distinct non-zero collider-bit patterns
@@ -104,8 +105,8 @@ struct StepScalars {
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
-  uint32_t n_candidates;     // particles whose BVH leaf holds a few triangles (k_collide_query -> k_collide_small)
-  uint32_t n_candidates_big; // ... many triangles (-> k_collide_big, one warp each)
+  uint32_t n_candidates;     // particles whose BVH leaf holds triangles within reach (k_collide_query -> k_collide_cand)
+  uint32_t n_candidates_unused;
   // adaptive time step reductions (f32::total_cmp keys)
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;

@@ -159,8 +159,12 @@ __device__ __forceinline__ void bvh_query(const MeshDev& M, int qx, int qy, int 
 
 // collide.rs:128-204 for one particle, given the closest triangle per collider (0xffffffff = none within the forget
 // distance): feature classification, side bits, friction / damping / push-out.  Returns the new collider bits; edits `vel`.
+// NC = number of colliders handled in registers (the scene has <= NC); the reference loops over all 16 slots and forgets the
+// colliders it found no triangle for — for the slots >= NC that is the final mask.
+template <int NC>
 __device__ __forceinline__ uint32_t collide_respond(const MeshDev& M, const SimConsts& K, float dt, V3 p, V3& vel, uint32_t bits, const uint32_t* closest) {
-  for (unsigned collider = 0; collider < 16; ++collider) {
+#pragma unroll
+  for (unsigned collider = 0; collider < (unsigned)NC; ++collider) {
     const uint32_t ct = closest[collider];
     if (ct == 0xffffffffu) { bits = bits_set(bits, collider, -1); continue; }
     const uint32_t ia = M.tri[3 * ct], ib = M.tri[3 * ct + 1], ic = M.tri[3 * ct + 2];
@@ -211,104 +215,69 @@ __device__ __forceinline__ uint32_t collide_respond(const MeshDev& M, const SimC
     }
     vel = vel - res.to_p / dt;
   }
+  if (NC < 16) bits &= 0x00010001u * ((1u << NC) - 1u);   // slots of colliders that do not exist: forgotten (collide.rs:163-166 with no triangle)
   return bits;
 }
 
-// Collide (collide.rs:21-206) in passes over compacted lists, so that the triangle loops of the particles near a collider do
+// Collide (collide.rs:21-206) in two passes over the particles, so that the triangle loops of the particles near a collider do
 // not stall the warps of the many that are not:
 //   k_collide_query   one thread per particle: BVH point query of its leaf cell; an empty leaf clears the collider bits
-//                     (collide.rs:57-61); a leaf with triangles puts the particle on the "small" list (front of the scratch
-//                     array) or, beyond COLLIDE_SMALL_MAX triangles, on the "big" list (back of the array);
-//   k_collide_small   one thread per small candidate: the reference's sequential scan (collide.rs:63-88);
-//   k_collide_big     one WARP per big candidate: the lanes share the leaf's triangle run, the closest triangle per collider
-//                     comes from a warp reduction on (distance, position in the run) — the same "first minimum" the
-//                     sequential scan keeps — and lane 0 finishes the particle.
+//                     (collide.rs:57-61), a leaf with triangles puts the particle on the candidate list (warp-aggregated append:
+//                     32 consecutive rows of the binned state stay together);
+//   k_collide_cand    one thread per candidate: the reference's sequential scan of the leaf's triangle run for the closest triangle
+//                     per collider (collide.rs:63-88; strict `<` keeps the first minimum, so the bits stay bit-exact), then the
+//                     response.  Consecutive candidates are consecutive rows of the binned state — neighbours in space, mostly in
+//                     the same BVH leaf — so the lanes of a warp walk the SAME triangle run: uniform trip counts, broadcast loads.
+//                     (Round 1 gave a warp to every candidate of a long run and lane 0 the response: 16 of 32 lanes idle, 550
+//                     warp instructions per candidate, 141 us for 1 M sand particles resting on a torus.)
+//                     NC = colliders tracked in registers (instantiated for 1, 2, 4, 16).
 constexpr int COLLIDE_SMALL_MAX = 24;
 __global__ void __launch_bounds__(256) k_collide_query(ParticleBuf P, StepScalars* S, SimConsts K, MeshDev M, uint32_t* __restrict__ candidates, uint32_t cap, uint32_t n) {
   if (S->sticky) return;
   n = min(n, S->n);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  int kind = 0;   // 1 small, 2 big
+  bool cand = false;
   if (i < n) {
     const uint32_t flags = P.u(PFLAGS)[i];
     const float x0 = P.f(PX)[i], x1 = P.f(PX + 1)[i], x2 = P.f(PX + 2)[i];
     if (!(flags & (F_TOMBSTONED | F_GONE))) {
       int first, count;
       bvh_query(M, (int)floorf(x0 / K.leaf_size), (int)floorf(x1 / K.leaf_size), (int)floorf(x2 / K.leaf_size), first, count);
-      if (count > COLLIDE_SMALL_MAX) kind = 2;
+      if (count > COLLIDE_SMALL_MAX) cand = true;
       else {
         // a leaf with few triangles (a coarse mesh: the whole box collider of a dam break is ONE leaf) — look for any triangle
         // whose bounding box is within reach; with none, every collider ends "not near": the same bits as an empty leaf
         const V3 p = V3{x0, x1, x2};
         const float reach = K.forget_distance * 1.001f;
-        for (int r = 0; r < count && kind == 0; ++r)
-          if (!triangle_out_of_reach(M, M.tri_indices[first + r], p, reach)) kind = 1;
+        for (int r = 0; r < count && !cand; ++r)
+          if (!triangle_out_of_reach(M, M.tri_indices[first + r], p, reach)) cand = true;
       }
-      if (kind == 0) P.u(PBITS)[i] = 0u;
+      if (!cand) P.u(PBITS)[i] = 0u;
     }
   }
   const uint32_t lane = threadIdx.x & 31;
-  const unsigned ms = __ballot_sync(SVB_FULL, kind == 1), mb = __ballot_sync(SVB_FULL, kind == 2);
-  uint32_t base_s = 0, base_b = 0;
-  if (lane == 0) {
-    if (ms) base_s = atomicAdd(&S->n_candidates, (uint32_t)__popc(ms));
-    if (mb) base_b = atomicAdd(&S->n_candidates_big, (uint32_t)__popc(mb));
-  }
+  const unsigned ms = __ballot_sync(SVB_FULL, cand);
+  uint32_t base_s = 0;
+  if (lane == 0 && ms) base_s = atomicAdd(&S->n_candidates, (uint32_t)__popc(ms));
   base_s = __shfl_sync(SVB_FULL, base_s, 0);
-  base_b = __shfl_sync(SVB_FULL, base_b, 0);
-  const unsigned below = (1u << lane) - 1u;
-  if (kind == 1) candidates[base_s + __popc(ms & below)] = i;                    // the two lists cannot meet: together they hold <= n <= cap entries
-  if (kind == 2) candidates[cap - 1 - (base_b + __popc(mb & below))] = i;
+  if (cand) candidates[base_s + __popc(ms & ((1u << lane) - 1u))] = i;   // <= n <= cap entries
 }
-__global__ void __launch_bounds__(128) k_collide_small(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, float dt, const DtState* __restrict__ D) {
+template <int NC>
+__global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, float dt, const DtState* __restrict__ D) {
   if (S->sticky) return;
   if (D) dt = D->dt_force;
   const uint32_t n_cand = S->n_candidates;
+  const float reach = K.forget_distance * 1.001f;
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
     const uint32_t i = candidates[q];
     const V3 p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
     int first, count;
     bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
-    uint32_t closest[16];
-    float min_dist[16];
-    const float reach = K.forget_distance * 1.001f;
+    uint32_t closest[NC];
+    float min_dist[NC];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) { closest[c] = 0xffffffffu; min_dist[c] = 3.402823466e+38f; }
+    for (int c = 0; c < NC; ++c) { closest[c] = 0xffffffffu; min_dist[c] = 3.402823466e+38f; }
     for (int r = 0; r < count; ++r) {
-      const uint32_t t = M.tri_indices[first + r];
-      if (triangle_out_of_reach(M, t, p, reach)) continue;
-      const V3 n = ld3(M.tnormal, t);
-      if (is_zero(n)) continue;
-      const float d = triangle_distance(p, ld3(M.vpos, M.tri[3 * t]), ld3(M.vpos, M.tri[3 * t + 1]), ld3(M.vpos, M.tri[3 * t + 2]), n);
-      if (d >= K.forget_distance) continue;
-      const uint32_t c = M.tri_collider[t] & 15u;
-      if (d < min_dist[c]) { min_dist[c] = d; closest[c] = t; }
-    }
-    V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-    const uint32_t bits = collide_respond(M, K, dt, p, vel, P.u(PBITS)[i], closest);
-    P.u(PBITS)[i] = bits;
-    P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
-  }
-}
-__global__ void __launch_bounds__(256) k_collide_big(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, uint32_t cap, float dt, const DtState* __restrict__ D) {
-  if (S->sticky) return;
-  if (D) dt = D->dt_force;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t n_cand = S->n_candidates_big;
-  const uint32_t n_colliders = min(M.n_colliders, 16u);
-  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_cand; q += warps) {
-    const uint32_t i = candidates[cap - 1 - q];
-    const V3 p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-    int first, count;
-    bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
-    // per lane: closest triangle per collider among the run entries lane, lane + 32, ... as (distance bits << 32 | run position):
-    // distances are >= 0, so the unsigned order of the bits is the numeric order and ties go to the earlier entry
-    unsigned long long best[16];
-    const float reach = K.forget_distance * 1.001f;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) best[c] = ~0ull;
-    for (int r = (int)lane; r < count; r += 32) {
       const uint32_t t = M.tri_indices[first + r];
       if (triangle_out_of_reach(M, t, p, reach)) continue;
       const V3 n = ld3(M.tnormal, t);
@@ -316,31 +285,14 @@ __global__ void __launch_bounds__(256) k_collide_big(ParticleBuf P, const StepSc
       const float d = triangle_distance(p, ld3(M.vpos, M.tri[3 * t]), ld3(M.vpos, M.tri[3 * t + 1]), ld3(M.vpos, M.tri[3 * t + 2]), n);
       if (!(d < K.forget_distance)) continue;   // (also drops a NaN distance, which the reference's `d < min` never selects)
       const uint32_t c = M.tri_collider[t] & 15u;
-      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)r;
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if ((uint32_t)k == c && key < best[k]) best[k] = key;
+      for (int k = 0; k < NC; ++k)
+        if ((uint32_t)k == c && d < min_dist[k]) { min_dist[k] = d; closest[k] = t; }
     }
-    uint32_t closest[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      closest[c] = 0xffffffffu;
-      if ((uint32_t)c < n_colliders) {   // warp-uniform: scenes with one or two colliders reduce one or two keys
-        unsigned long long b = best[c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(SVB_FULL, b, o);
-          b = other < b ? other : b;
-        }
-        if (b != ~0ull) closest[c] = M.tri_indices[first + (uint32_t)b];
-      }
-    }
-    if (lane == 0) {
-      V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-      const uint32_t bits = collide_respond(M, K, dt, p, vel, P.u(PBITS)[i], closest);
-      P.u(PBITS)[i] = bits;
-      P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
-    }
+    V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+    const uint32_t bits = collide_respond<NC>(M, K, dt, p, vel, P.u(PBITS)[i], closest);
+    P.u(PBITS)[i] = bits;
+    P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
   }
 }
 
@@ -524,23 +476,28 @@ __global__ void __launch_bounds__(256) k_begin(const StepScalars* __restrict__ p
 // Binning of one particle, WARP-COLLECTIVE (all 32 lanes call it; `state`: 0 = live, 1 = tombstoned, 2 = gone / no particle):
 //   * the particle's tile (block of its base node, layer of its collider bits) is found or created in the tile table,
 //     warp-aggregated: lanes with equal keys elect one lane to touch the table;
-//   * the particle takes a slot in its cell: rank = atomicAdd(cell_count[tile*64 + cell]) (again one atomic per distinct cell per
-//     warp) — a single-pass counting sort on (tile, cell);
+//   * its cell is counted: cell_count[tile*64 + cell] += 1 (one reduction per distinct cell per warp) — the counting half of a
+//     single-pass counting sort on (tile, cell); the RANK inside the cell is handed out later by k_invert_zero from the same
+//     counters (turned into offsets by k_offsets), so nothing here waits for the return value of an atomic;
 //   * the tile remembers which of its 8 neighbour blocks its particles' stencils reach.
-// Writes pcell[row] / prank[row] when `row` is valid.  x must be the position the NEXT P2G will see.
+// Writes pcell[row] when `row` is valid.  x must be the position the NEXT P2G will see.
+// CACHED (the fused G2P, one CTA per tile): the table slots of the 27 blocks around the CTA's tile are cached in shared memory
+// (`cache`, ~0u = not looked up yet; `cb*` = the tile's block), because a particle moves less than a cell per substep: after the
+// first particle of a tile has found or created a neighbour's slot no other one probes the table in HBM for it.
 struct BinArrays {
-  uint32_t* pcell;        // [n] table slot * 64 + cell, 0xffffffff for tombstoned
-  uint32_t* prank;        // [n] rank inside the cell (or among the tombstoned)
+  uint32_t* pcell;        // [n] table slot * 64 + cell; 0xffffffff tombstoned, 0xfffffffd gone, 0xfffffffe unbinned
   uint32_t* cell_count;   // [table slots * 64]: indexed by the tile's TABLE SLOT, so counting never waits for a tile id
   uint32_t* tile_touch;   // [table slots] 8-bit mask over neighbour offsets d
   unsigned long long* layer_slots;
   uint32_t* layer_list;
 };
-template <bool HAS_MESH>
-__device__ __forceinline__ void bin_warp(int state, V3 x, uint32_t bits, bool has_row, uint32_t row, const SimConsts& K, const TileTable& T, const BinArrays& B, StepScalars* S, uint32_t lane) {
+template <bool HAS_MESH, bool CACHED>
+__device__ __forceinline__ void bin_warp(int state, V3 x, uint32_t bits, bool has_row, uint32_t row, const SimConsts& K, const TileTable& T, const BinArrays& B, StepScalars* S, uint32_t lane,
+                                         volatile uint32_t* cache = nullptr, int cbx = 0, int cby = 0, int cbz = 0) {
   bool live = false;
   unsigned long long key = TILE_EMPTY;
   uint32_t cell = 0, touch = 0;
+  int cache_at = -1;
   if (state == 0) {
     const int s0 = base_node(x.x, K.h), s1 = base_node(x.y, K.h), s2 = base_node(x.z, K.h);
     const int b0 = floor_div4(s0), b1 = floor_div4(s1), b2 = floor_div4(s2);
@@ -557,32 +514,36 @@ __device__ __forceinline__ void bin_warp(int state, V3 x, uint32_t bits, bool ha
       if (s0 & 2) touch |= touch << 1;
       if (s1 & 2) touch |= touch << 2;
       if (s2 & 2) touch |= touch << 4;
+      if (CACHED) {
+        const int d0 = b0 - cbx + 1, d1 = b1 - cby + 1, d2 = b2 - cbz + 1;
+        if ((unsigned)d0 < 3u && (unsigned)d1 < 3u && (unsigned)d2 < 3u) cache_at = (d0 * 3 + d1) * 3 + d2;
+      }
     }
   }
-  // ---- tile: one table access per distinct key in the warp
+  // ---- tile: one table access per distinct key in the warp (none when the CTA's cache knows the slot)
   const unsigned peers = __match_any_sync(SVB_FULL, key);
   const int leader = __ffs(peers) - 1;
   uint32_t tile = ~0u;   // the tile's table slot
-  if (live && (int)lane == leader) tile = tile_slot_find_or_insert(T, key, S);
+  if (live && (int)lane == leader) {
+    if (CACHED && cache_at >= 0) tile = cache[cache_at];
+    if (tile == ~0u) {
+      tile = tile_slot_find_or_insert(T, key, S);
+      if (CACHED && cache_at >= 0 && tile != ~0u) cache[cache_at] = tile;
+    }
+  }
   tile = __shfl_sync(SVB_FULL, tile, leader);
   const uint32_t tm = __reduce_or_sync(peers, touch);
   if (live && (int)lane == leader && tile != ~0u) atomicOr(&B.tile_touch[tile], tm);  // result unused: a fire-and-forget RED
-  // ---- rank in the cell: one atomic per distinct (tile, cell) in the warp
+  // ---- count the cell: one reduction per distinct (tile, cell) in the warp, result unused (RED)
   const bool binned = live && tile != ~0u;
   const bool tomb = state == 1;
   const uint32_t ci = binned ? tile * 64u + cell : (tomb ? 0xffffffffu : (state == 2 ? 0xfffffffdu : 0xfffffffeu));
   const unsigned cpeers = __match_any_sync(SVB_FULL, ci);
-  const int cleader = __ffs(cpeers) - 1;
-  uint32_t base = 0;
-  if ((int)lane == cleader) {
-    if (binned) base = atomicAdd(&B.cell_count[ci], (uint32_t)__popc(cpeers));
-    else if (tomb) base = atomicAdd(&S->n_tomb, (uint32_t)__popc(cpeers));
+  if ((int)lane == __ffs(cpeers) - 1) {
+    if (binned) atomicAdd(&B.cell_count[ci], (uint32_t)__popc(cpeers));
+    else if (tomb) atomicAdd(&S->n_tomb, (uint32_t)__popc(cpeers));
   }
-  base = __shfl_sync(SVB_FULL, base, cleader);
-  if (has_row) {
-    B.pcell[row] = ci;
-    B.prank[row] = base + __popc(cpeers & ((1u << lane) - 1u));
-  }
+  if (has_row) B.pcell[row] = ci;
 }
 
 // k_bin — binning as its own pass, one thread per particle in the CURRENT order: the first substep after an upload, every substep
@@ -605,7 +566,7 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
     const bool gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
     state = gone ? 2 : ((flags & F_TOMBSTONED) ? 1 : 0);
   }
-  bin_warp<HAS_MESH>(state, x, bits, i < n, i, K, T, B, S, lane);
+  bin_warp<HAS_MESH, false>(state, x, bits, i < n, i, K, T, B, S, lane);
   if (i == 0) S->bin_blocks_done = 1u;   // "this substep was binned" (a sticky error makes the kernel return at the top instead)
 }
 
@@ -718,7 +679,7 @@ struct PrepareNext {
   StepScalars* S; TileTable T; uint32_t* cell_count; uint32_t* tile_touch;
   uint32_t n; const uint32_t* n_dev; int tables_fresh; uint32_t blocks;
 };
-__global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, const uint32_t* __restrict__ prank, const uint32_t* __restrict__ cell_offset,
+__global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, uint32_t* __restrict__ cell_offset,
                                                      const uint32_t* __restrict__ slot_first, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
                                                      unsigned long long* __restrict__ node_mask, uint32_t tile_cap, PrepareNext prep) {
   if (SVB_ABORTED(S)) return;
@@ -736,15 +697,22 @@ __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S
     if (blockIdx.x == invert_blocks && threadIdx.x == 0) S->n_tiles_zeroed = (uint32_t)(total >> 6);
     return;
   }
+  // the rank of a particle inside its cell is handed out HERE, from the cell's offset used as a cursor (one atomic per distinct
+  // cell per warp: consecutive rows share cells) — the binning itself only counted, so the kernels that bin never wait on an atomic
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= min(n, S->n)) return;
-  const uint32_t ci = pcell[i];
-  uint32_t j;
-  if (ci >= 0xfffffffdu) {
-    if (ci != 0xffffffffu) return;  // migrated away (or unbinned after an abort): no slot
-    j = S->n_live + prank[i];
-  } else j = slot_first[ci >> 6] + cell_offset[ci] + prank[i];
-  src_of[j] = i;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ci = i < min(n, S->n) ? pcell[i] : 0xfffffffeu;
+  const bool binned = ci < 0xfffffffdu, tomb = ci == 0xffffffffu;
+  const unsigned peers = __match_any_sync(SVB_FULL, ci);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) {
+    if (binned) base = atomicAdd(&cell_offset[ci], (uint32_t)__popc(peers));
+    else if (tomb) base = atomicAdd(&S->tomb_cursor, (uint32_t)__popc(peers));
+  }
+  base = __shfl_sync(SVB_FULL, base, leader) + __popc(peers & ((1u << lane) - 1u));
+  if (binned) src_of[slot_first[ci >> 6] + base] = i;
+  else if (tomb) src_of[S->n_live + base] = i;   // (migrated away, or unbinned after an abort: no slot)
 }
 // ------------------------------------------------------------------------------------------------
 // P2G (scatter_momentum.rs:22-93).  One CTA per (block, layer) run of particles, claimed from a
@@ -1077,10 +1045,13 @@ struct BinNext {
 template <bool FUSE, bool REDUCE, bool MELDED, bool SLAB, bool BIN>
 __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
                                                         const uint2* __restrict__ group_range, const int* __restrict__ nbr, StepScalars* S,
-                                                        const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn) {
+                                                        const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn,
+                                                        const unsigned long long* __restrict__ tile_key) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
   __shared__ int s_nbr[8];
+  __shared__ uint32_t s_cache[27];   // BIN: table slots (in the NEXT substep's set) of the 27 blocks around this tile
+  __shared__ int s_block[3];
   if (SVB_ABORTED(S)) return;
   const uint32_t n_groups = S->n_ptiles;
   const float h = K.h, inv_h = 1.f / K.h;
@@ -1093,7 +1064,14 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       if (threadIdx.x == 0) s_group = g0 = atomicAdd(&S->work_counter[1], 1u);
       g0 = __shfl_sync(0xffu, g0, 0);
       if (g0 < n_groups) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
+      if (BIN && threadIdx.x == 0 && g0 < n_groups) {
+        int bx, by, bz;
+        uint32_t layer;
+        tile_key_unpack(tile_key[g0], bx, by, bz, layer);
+        s_block[0] = bx; s_block[1] = by; s_block[2] = bz;
+      }
     }
+    if (BIN && threadIdx.x >= 32 && threadIdx.x < 32 + 27) s_cache[threadIdx.x - 32] = ~0u;
     __syncthreads();
     const uint32_t g = s_group;
     if (g >= n_groups) break;
@@ -1213,7 +1191,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
       D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
       }
-      if (BIN) bin_warp<false>(bin_state, bin_x, 0u, i < end, i, K, bn.T, bn.B, bn.S, lane);
+      if (BIN) bin_warp<false, true>(bin_state, bin_x, 0u, i < end, i, K, bn.T, bn.B, bn.S, lane, s_cache, s_block[0], s_block[1], s_block[2]);
     }
   }
   // tombstoned particles take no part in P2G / G2P: carry their rows over as they are (behind the live ones)
@@ -1225,7 +1203,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       for (int f = 0; f < NFIELDS; ++f) D.base[(size_t)f * D.cap + j] = P.base[(size_t)f * P.cap + i];
       if (BIN) {   // stays tombstoned: behind the live rows of the next substep as well
         bn.B.pcell[j] = 0xffffffffu;
-        bn.B.prank[j] = atomicAdd(&bn.S->n_tomb, 1u);
+        atomicAdd(&bn.S->n_tomb, 1u);
       }
     }
   }
@@ -1390,7 +1368,7 @@ __global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restric
       }
     }
   }
-  if (BIN) bin_warp<false>(bin_state, x, 0u, i < n, i, K, bn.T, bn.B, bn.S, lane);
+  if (BIN) bin_warp<false, false>(bin_state, x, 0u, i < n, i, K, bn.T, bn.B, bn.S, lane);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ks = min(ks, __shfl_xor_sync(SVB_FULL, ks, o));
@@ -1750,7 +1728,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
       x = V3{__uint_as_float(row[PX]), __uint_as_float(row[PX + 1]), __uint_as_float(row[PX + 2])};
       state = (row[PFLAGS] & F_TOMBSTONED) ? 1 : 0;
     }
-    if (bin && ran) bin_warp<false>(state, x, 0u, q < total, base + q, K, bn.T, bn.B, bn.S, lane);
+    if (bin && ran) bin_warp<false, false>(state, x, 0u, q < total, base + q, K, bn.T, bn.B, bn.S, lane);
   }
   // a substep that was a no-op on every rank (an earlier substep failed: k_bin returned at once) keeps the row count
   if (between_substeps) {
