@@ -65,7 +65,7 @@ struct SvbHandle {
   std::vector<float> initial_positions;  // never read by the path; echoed by svb_download
   // binning scratch + the two alternating "front sets" of per-substep tile bookkeeping (svb_kernels.cuh: reset_set): substep n runs on
   // set n % 2 while its G2P already bins the advanced positions into the other one
-  DevBuf pcell, prank, src_of, grid, melded, node_mask, node_offset, scratch;
+  DevBuf pcell, prank, src_of, grid, melded, node_mask, node_offset, scratch, work_list;
   struct FrontBufs {
     DevBuf table_slots, tile_key, tile_slot, tile_touch, cell_count, slot_first, tile_start, nbr;
     bool fresh = true;      // (re)allocated: memset once before its next use, later uses undo only what they left
@@ -78,8 +78,12 @@ struct SvbHandle {
   DevBuf dt_state;          // DtState: adaptive time stepping on the device
   DtState* h_dt = nullptr;  // pinned lagged copy
   DevBuf scalars, layer_slots, layer_list;
-  StepScalars* h_scalars = nullptr;  // pinned
+  StepScalars* h_scalars = nullptr;  // pinned: where the current substep's front-half scalars land (a slot of `lag`)
   cudaEvent_t ev_front = nullptr;
+  // peer-memory slab ranks run up to two substeps ahead of the host's look at the front-half scalars, so that a late host thread
+  // (eight processes share the box's cores) never leaves its GPU — and through the exchange waits its neighbours — idle
+  struct FrontLag { StepScalars* host = nullptr; cudaEvent_t ev = nullptr; double time_before = 0; uint64_t substeps_before = 0; bool was_ahead = false; } lag[4];
+  uint64_t lag_issued = 0, lag_done = 0;
   uint32_t n_ptiles = 0, n_live = 0, n_tiles = 0;
   bool have_grid = false;
   bool store_grid = false, masks_valid = false;
@@ -211,6 +215,7 @@ int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
     f.fresh = true;  // new allocations: the next use memsets them instead of undoing the previous one
   }
   CK(h->grid.ensure(c * 64 * 16));
+  CK(h->work_list.ensure(2 * c * 4));
   CK(h->node_mask.ensure(c * 8));
   CK(h->node_offset.ensure((c + 1) * 4));
   h->tile_cap = c;
@@ -298,7 +303,8 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool redo) {
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
   k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, ahead ? S_prev : nullptr, n, h->p2p ? h->n_dev : nullptr, T, F.cell_count.as<uint32_t>(),
-                                                                                                 F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(), F.tile_touch.as<uint32_t>(), F.nbr.as<int>());
+                                                                                                 F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(), F.tile_touch.as<uint32_t>(), F.nbr.as<int>(),
+                                                                                                 h->p2p ? SlabColumns{h->slab_lo, h->slab_hi, h->work_list.as<uint32_t>()} : SlabColumns{0, 0, nullptr});
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(h->ev_front, s));
@@ -336,26 +342,34 @@ int enqueue_rebin(SvbHandle* h, bool prepare_next) {
   return 0;
 }
 
-int enqueue_p2g(SvbHandle* h, const StepInputs& in) {
+// the tiles a P2G / G2P launch works through: all particle tiles, or (peer-memory slab ranks) the boundary / interior list of k_offsets
+WorkList work_all(SvbHandle* h, int counter, int tail) {
+  StepScalars* S = cur_scalars(h);
+  return WorkList{nullptr, &S->n_ptiles, &S->work_counter[counter], tail};
+}
+WorkList work_part(SvbHandle* h, int which, int counter, int tail) {
+  StepScalars* S = cur_scalars(h);
+  return WorkList{h->work_list.as<uint32_t>() + (size_t)which * h->tile_cap, &S->n_work[which], &S->work_counter[counter], tail};
+}
+
+int enqueue_p2g(SvbHandle* h, const StepInputs& in, const WorkList& W, uint32_t grid_cap = 148 * P2G_CTAS_PER_SM) {
   cudaStream_t s = h->stream;
   auto& F = h->fs[h->s_cur];
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * P2G_CTAS_PER_SM));
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, grid_cap));
   ForceIn force{};
   force.dt = in.dt; force.gx = in.g[0]; force.gy = in.g[1]; force.gz = in.g[2]; force.factor_b = in.factor_b;
   force.D = dt_ref(h, in);
-  stage_begin(h, ST_P2G);
   if (h->has_goals) {
     force.G.flags_a = h->d_flags_a.as<uint32_t>();
     force.G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : force.G.flags_a;
     force.G.goal_a = h->d_goal_a.as<float>();
     force.G.goal_b = h->has_b ? h->d_goal_b.as<float>() : force.G.goal_a;
-    k_p2g<true><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force);
+    k_p2g<true><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force, W);
   } else {
-    k_p2g<false><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force);
+    k_p2g<false><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force, W);
   }
   LAUNCH_CHECK();
-  stage_end(h);
   return 0;
 }
 
@@ -410,31 +424,33 @@ int settle_front(SvbHandle* h, const StepInputs& in, bool back_enqueued, bool wa
   }
 }
 
-// MeldGrid + CollectVelocity (+ Advance + Cull when fused).  Collider scenes first meld the sibling layers
-// into a velocity grid; without colliders G2P divides by the mass while it stages a tile.
-// `bin_next`: the fused kernel also bins the advanced positions into the other front set.
-int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next, const MigrateCut* cut = nullptr) {
+// MeldGrid (collider scenes: the sibling layers are melded into a velocity grid first; without colliders G2P divides by the mass
+// while it stages a tile)
+int enqueue_meld(SvbHandle* h) {
+  CK(h->melded.ensure(h->tile_cap * 64 * 16));
+  k_meld<<<148 * 8, 256, 0, h->stream>>>(cur_scalars(h), h->grid.as<float4>(), h->melded.as<float4>(), tile_table(h), meld_info(h));
+  LAUNCH_CHECK();
+  return 0;
+}
+// CollectVelocity (+ Advance + Cull when fused) over the tiles of `W`, from particle buffer `src_buf` into `dst_buf` (the caller
+// swaps `cur` once all launches of the substep are queued).  `bin_next`: the fused kernel also bins the advanced positions into the
+// other front set.
+int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next, const WorkList& W, int src_buf, const MigrateCut* cut = nullptr, uint32_t grid_cap = 148 * 12) {
   cudaStream_t s = h->stream;
   StepScalars* S = cur_scalars(h);
   auto& F = h->fs[h->s_cur];
-  const float4* src = h->grid.as<float4>();
-  if (has_mesh) {
-    CK(h->melded.ensure(h->tile_cap * 64 * 16));
-    k_meld<<<148 * 8, 256, 0, s>>>(S, h->grid.as<float4>(), h->melded.as<float4>(), tile_table(h), meld_info(h));
-    LAUNCH_CHECK();
-    src = h->melded.as<float4>();
-  }
-  const ParticleBuf P = h->Pc(), D = h->P(h->cur ^ 1);
+  const float4* src = has_mesh ? h->melded.as<float4>() : h->grid.as<float4>();
+  const ParticleBuf P = h->P(src_buf), D = h->P(src_buf ^ 1);
   const uint32_t* src_of = h->src_of.as<uint32_t>();
   const uint2* tile_start = F.tile_start.as<uint2>();
   float* en = h->energy.as<float>();
   const int* nb = F.nbr.as<int>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, 148 * 12));
+  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, grid_cap));
   const MigrateCut mc = cut ? *cut : MigrateCut{};
   BinNext bn{};
   if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
-#define SVB_G2P(F_, R_, M_, SL_, B_) k_g2p<F_, R_, M_, SL_, B_><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn, F.tile_key.as<unsigned long long>())
+#define SVB_G2P(F_, R_, M_, SL_, B_) k_g2p<F_, R_, M_, SL_, B_><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn, F.tile_key.as<unsigned long long>(), W)
   if (fuse && cut) {
     if (has_mesh) SVB_G2P(true, false, true, true, false);
     else if (bin_next) SVB_G2P(true, false, false, true, true);
@@ -449,7 +465,6 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next,
   }
 #undef SVB_G2P
   LAUNCH_CHECK();
-  h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
   return 0;
 }
 
@@ -516,9 +531,14 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   for (int pass = 0;; ++pass) {
     // the whole back half is queued behind the front half, then the host looks at the front half's result
     if (int rc = enqueue_rebin(h, bin_next)) return rc;
-    if (int rc = enqueue_p2g(h, in)) return rc;
+    stage_begin(h, ST_P2G);
+    if (int rc = enqueue_p2g(h, in, work_all(h, 0, 0))) return rc;
+    stage_end(h);
     stage_begin(h, ST_G2P);
-    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/!adaptive_steps, in.dt, bin_next && !adaptive_steps)) return rc;
+    if (in.has_mesh)
+      if (int rc = enqueue_meld(h)) return rc;
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/!adaptive_steps, in.dt, bin_next && !adaptive_steps, work_all(h, 1, 1), h->cur)) return rc;
+    h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
     stage_end(h);
     if (adaptive_steps) {
       // -- LimitTimeStepBeforeIntegrate, AdvanceParticles + CullParticles, the clock: all on the device
@@ -578,12 +598,17 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   }
   const uint32_t n_after = h->h_scalars->n_live + h->h_scalars->n_tomb;  // rows of migrated particles are dropped by the re-bin
   if (int rc = enqueue_rebin(h, false)) return rc;
-  if (int rc = enqueue_p2g(h, in)) return rc;
+  stage_begin(h, ST_P2G);
+  if (int rc = enqueue_p2g(h, in, work_all(h, 0, 0))) return rc;
+  stage_end(h);
   stage_begin(h, ST_HALO);
   if (int rc = halo_exchange(h)) return rc;
   stage_end(h);
   stage_begin(h, ST_G2P);
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, false)) return rc;
+  if (in.has_mesh)
+    if (int rc = enqueue_meld(h)) return rc;
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, false, work_all(h, 1, 1), h->cur)) return rc;
+  h->cur ^= 1;
   h->n = n_after;
   // a FAILED particle on any rank stops every rank after this substep
   uint32_t* flag = h->comm_counts.as<uint32_t>() + 8;
@@ -603,23 +628,72 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
   return 0;
 }
 
-// one fixed-dt substep of a slab rank over peer memory: nothing on the data path returns to the host.  The whole
-// substep is queued, then the host looks at the front half's scalars (one substep of lag at most).
+// The host's (lagged) look at the front-half scalars of the oldest unchecked substep of a peer-memory slab rank.
+//   0: fine   2: that substep was a no-op (an earlier one stopped the run); every substep queued since is forgotten
+int process_front_p2p(SvbHandle* h) {
+  cudaStream_t s = h->stream;
+  SvbHandle::FrontLag& L = h->lag[h->lag_done % 4];
+  CK(cudaEventSynchronize(L.ev));
+  const StepScalars& r = *L.host;
+  if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys (or crossed more than one slab in a substep)");
+  if (r.status & ST_TILE_OVERFLOW) return fail(h, SVB_COMM_ERROR, "tile capacity exceeded on a slab rank (%u tiles > %zu)", r.n_tiles, h->tile_cap);
+  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))   // raised by an earlier substep's back half and carried forward
+    return fail(h, SVB_COMM_ERROR, r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
+  if (r.sticky) {  // the previous substep failed somewhere: this one and everything queued behind it were no-ops on every rank
+    h->status |= (r.sticky | r.accum) & 0xffffu;
+    CK(cudaStreamSynchronize(s));
+    const uint64_t noops = h->lag_issued - h->lag_done;
+    if (noops & 1) { h->cur ^= 1; h->s_cur ^= 1; }   // each queued G2P swapped the buffers and each front the set: undo (they wrote nothing)
+    h->binned_ahead = L.was_ahead;
+    // the clock of the substep that raised the error does not count either (cpu_state.rs:176-190)
+    const SvbHandle::FrontLag& failing = h->lag_done > 0 ? h->lag[(h->lag_done - 1) % 4] : L;
+    h->time = failing.time_before;
+    h->substeps = failing.substeps_before;
+    h->failed_rolled_back = true;
+    h->stop_bits = r.sticky;
+    h->lag_done = h->lag_issued;
+    return 2;
+  }
+  h->n_tiles = r.n_tiles;
+  h->n_ptiles = r.n_ptiles;
+  h->n_live = r.n_live;
+  h->status |= (r.status | r.accum) & 0xffffu;
+  ++h->lag_done;
+  if (((size_t)r.n_tiles + h->halo_margin) * 3 / 2 > h->tile_cap) {  // grow ahead of need: an overflow cannot be redone once messages are out
+    CK(cudaStreamSynchronize(s));   // (every substep queued so far completes first: they are real ones)
+    while (h->lag_done < h->lag_issued) {
+      const int rc = process_front_p2p(h);
+      if (rc) return rc;
+    }
+    if (int rc = ensure_tile_capacity(h, ((size_t)r.n_tiles + h->halo_margin) * 3)) return rc;   // (drops what was binned ahead: the next substep bins with k_bin)
+  }
+  return 0;
+}
+
+// one fixed-dt substep of a slab rank over peer memory: nothing on the data path returns to the host, and the exchanges hide
+// behind the interior tiles' work:
+//   P2G(boundary tiles) -> halo send -> P2G(interior) -> halo receive -> G2P(boundary) -> migration send -> G2P(interior) -> migration receive
+// The whole substep is queued, then the host looks at the front half of an EARLIER substep (up to two stay in flight).
 int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   cudaStream_t s = h->stream;
   const float dt = in.dt;
   const uint32_t seq = ++h->slab_seq;
-  const bool was_ahead = h->binned_ahead;
   const bool bin_next = !in.has_mesh;
+  SvbHandle::FrontLag& L = h->lag[h->lag_issued % 4];
+  L.time_before = h->time; L.substeps_before = h->substeps; L.was_ahead = h->binned_ahead;
+  h->h_scalars = L.host;
+  h->ev_front = L.ev;
   if (int rc = enqueue_front(h, in, /*redo=*/false)) return rc;
   if (int rc = enqueue_rebin(h, bin_next)) return rc;
   StepScalars* S = cur_scalars(h);
   const TileTable T = tile_table(h);
-  if (int rc = enqueue_p2g(h, in)) return rc;
-  stage_begin(h, ST_HALO);
   SlabHeader* my_hdr = h->mailbox.as<SlabHeader>();
   unsigned char* my_mb = h->mailbox.as<unsigned char>();
   const bool has[2] = {h->rank > 0, h->rank + 1 < h->n_ranks};
+  stage_begin(h, ST_P2G);
+  if (int rc = enqueue_p2g(h, in, work_part(h, 0, 0, 0), 148 * 2)) return rc;
+  stage_end(h);
+  stage_begin(h, ST_HALO);
   if (has[0] || has[1]) {
     // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right; a message lands in the
     // neighbour's slot for "from the right" (when I am its right neighbour) / "from the left"
@@ -635,6 +709,13 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       }
     k_halo_send2<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local);
     LAUNCH_CHECK();
+  }
+  stage_end(h);
+  stage_begin(h, ST_P2G);
+  if (int rc = enqueue_p2g(h, in, work_part(h, 1, 2, 0))) return rc;
+  stage_end(h);
+  stage_begin(h, ST_HALO);
+  if (has[0] || has[1]) {
     k_halo_recv2<<<148 * 2, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(), h->grid.as<float4>(), reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[0]),
                                         reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[1]), my_hdr, has[0] ? 1 : 0, has[1] ? 1 : 0, seq);
     LAUNCH_CHECK();
@@ -643,7 +724,10 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   stage_begin(h, ST_G2P);
   CK(h->mig_list.ensure(2 * h->mb_mig_cap * 4));
   const MigrateCut cut{h->slab_lo, h->slab_hi, h->reach_lo, h->reach_hi, 4.f * (float)h->slab_lo, 4.f * (float)h->slab_hi, h->mig_list.as<uint32_t>(), h->p2p_local + 8, (uint32_t)h->mb_mig_cap};
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, &cut)) return rc;
+  if (in.has_mesh)
+    if (int rc = enqueue_meld(h)) return rc;
+  const int src_buf = h->cur;
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 0, 1, 1), src_buf, &cut, 148 * 2)) return rc;
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
   SlabPeers peers{};
@@ -663,42 +747,32 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       peers.err_seq[r] = &ph->err_seq[h->rank];
       peers.err_val[r] = &ph->err_val[h->rank];
     }
-  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
+  // (the rows G2P wrote live in the OTHER buffer until `cur` is swapped below)
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
   LAUNCH_CHECK();
+  stage_end(h);
+  stage_begin(h, ST_G2P);
+  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 1, 3, 0), src_buf, &cut)) return rc;
+  h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
+  stage_end(h);
+  stage_begin(h, ST_MIGRATE);
   BinNext bn{};
   if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0, h->K, bn, bin_next ? 1 : 0);
   LAUNCH_CHECK();
   stage_end(h);
-  // ---- the host catches up with the front half of this substep (the back half keeps the GPU busy meanwhile)
-  CK(cudaEventSynchronize(h->ev_front));
-  const StepScalars& r = *h->h_scalars;
-  if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys (or crossed more than one slab in a substep)");
-  if (r.status & ST_TILE_OVERFLOW) return fail(h, SVB_COMM_ERROR, "tile capacity exceeded on a slab rank (%u tiles > %zu)", r.n_tiles, h->tile_cap);
-  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))   // raised by an earlier substep's back half and carried forward
-    return fail(h, SVB_COMM_ERROR, r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
-  if (r.sticky) {  // the previous substep failed somewhere: this one was a no-op on every rank
-    h->status |= (r.sticky | r.accum) & 0xffffu;
-    CK(cudaStreamSynchronize(s));
-    forget_noop_substep(h, was_ahead, true);
-    rollback_failed_substep(h);
-    h->stop_bits = r.sticky;
-    return 2;
-  }
-  h->n_tiles = r.n_tiles;
-  h->n_ptiles = r.n_ptiles;
-  h->n_live = r.n_live;
-  h->status |= (r.status | r.accum) & 0xffffu;
+  ++h->lag_issued;
   h->binned_ahead = bin_next;
-  if (((size_t)r.n_tiles + h->halo_margin) * 3 / 2 > h->tile_cap) {  // grow ahead of need: an overflow cannot be redone once messages are out
-    CK(cudaStreamSynchronize(s));
-    if (int rc = ensure_tile_capacity(h, ((size_t)r.n_tiles + h->halo_margin) * 3)) return rc;   // (drops what was binned ahead: the next substep bins with k_bin)
-  }
   h->have_grid = true;
   h->time_before_last = h->time;
   h->time += (double)dt;
   ++h->substeps;
+  // ---- the host catches up with the front half of an earlier substep (the queued work keeps the GPU busy meanwhile)
+  while (h->lag_issued - h->lag_done > (h->timing ? 0u : 2u)) {
+    const int rc = process_front_p2p(h);
+    if (rc) return rc;
+  }
   return 0;
 }
 
@@ -797,11 +871,15 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   for (auto& e : h->ev_adv) CK(cudaEventCreate(&e));
-  CK(cudaMallocHost(&h->h_scalars, sizeof(StepScalars)));
+  for (auto& L : h->lag) {
+    CK(cudaMallocHost(&L.host, sizeof(StepScalars)));
+    CK(cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming));
+  }
+  h->h_scalars = h->lag[0].host;
+  h->ev_front = h->lag[0].ev;
   CK(cudaMallocHost(&h->h_dt, sizeof(DtState)));
   CK(h->dt_state.ensure(sizeof(DtState)));
   CK(cudaMemsetAsync(h->dt_state.p, 0, sizeof(DtState), h->stream));
-  CK(cudaEventCreateWithFlags(&h->ev_front, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(k_p2g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
   CK(cudaFuncSetAttribute(k_p2g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
   const uint32_t n = (uint32_t)p->n;
@@ -840,14 +918,16 @@ void svb_destroy(SvbHandle* h) {
     for (DevBuf* b : {&f.table_slots, &f.tile_key, &f.tile_slot, &f.tile_touch, &f.cell_count, &f.slot_first, &f.tile_start, &f.nbr}) b->release();
   if (h->h_dt) cudaFreeHost(h->h_dt);
   DevBuf* all[] = {&h->pbuf[0], &h->pbuf[1], &h->energy, &h->pcell, &h->prank, &h->src_of, &h->dt_state,
-                   &h->grid, &h->melded, &h->mig_list, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
+                   &h->grid, &h->melded, &h->mig_list, &h->work_list, &h->node_mask, &h->node_offset, &h->scratch, &h->scalars, &h->layer_slots, &h->layer_list,
                    &h->d_tri, &h->d_opp, &h->d_tri_collider, &h->d_fan_offsets, &h->d_fan_tris, &h->d_va, &h->d_vb, &h->d_vvel, &h->d_fric_a, &h->d_fric_b, &h->d_damp_a, &h->d_damp_b,
                    &h->d_vpos, &h->d_vnormal, &h->d_tnormal, &h->d_tbox, &h->d_tfric, &h->d_tdamp, &h->d_node_min, &h->d_node_max, &h->d_node_first, &h->d_node_count, &h->d_children,
                    &h->d_tri_indices, &h->d_flags_a, &h->d_flags_b, &h->d_goal_a, &h->d_goal_b, &h->snap_p, &h->snap_e,
                    &h->comm_counts, &h->mailbox, &h->halo_send[0], &h->halo_send[1], &h->halo_recv[0], &h->halo_recv[1], &h->mig_send[0], &h->mig_send[1], &h->mig_recv[0], &h->mig_recv[1]};
   for (DevBuf* b : all) b->release();
-  if (h->h_scalars) cudaFreeHost(h->h_scalars);
-  if (h->ev_front) cudaEventDestroy(h->ev_front);
+  for (auto& L : h->lag) {
+    if (L.host) cudaFreeHost(L.host);
+    if (L.ev) cudaEventDestroy(L.ev);
+  }
   for (void* pm : h->peer_mailbox)
     if (pm) cudaIpcCloseMemHandle(pm);
   if (h->comm) ncclCommDestroy(h->comm);
@@ -1084,6 +1164,11 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
       if (rc < 0) return rc;
       if (rc == 2 || (h->status & SVB_PARTICLE_CLOSE_TO_INVERTED)) break;
       if (progress) progress(user, (size_t)(std::fmod(h->time, spf) * 1000.0));
+    }
+    while (h->p2p && h->lag_done < h->lag_issued) {   // the fronts of the last substeps have not been looked at yet
+      const int rc = process_front_p2p(h);
+      if (rc < 0) return rc;
+      if (rc == 2) break;
     }
   }
   CK(cudaEventRecord(h->ev_adv[1], s));

@@ -103,7 +103,8 @@ struct StepScalars {
   uint32_t n_layers;   // distinct non-zero collider-bit patterns
   uint32_t n_tiles_zeroed;  // tiles cleared by k_invert_zero (tiles created later by a halo message are stored, not added)
   uint32_t status;     // SVB_* simulation-level bits | ST_*
-  uint32_t work_counter[4];
+  uint32_t work_counter[4];  // tile claims: [0] P2G, [1] G2P (all tiles, or a slab rank's boundary tiles), [2] / [3] the same for its interior tiles
+  uint32_t n_work[2];        // slab ranks: particle tiles in the boundary / interior work list (k_offsets)
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
   uint32_t n_candidates;     // particles whose BVH leaf holds triangles within reach (k_collide_query -> k_collide_cand)
   uint32_t n_candidates_unused;

@@ -27,6 +27,18 @@ __device__ __forceinline__ int ceil_log2_u32(uint32_t v) {  // bits needed to re
 // cpu/src/kernels.rs:46-49 — must be bit-exact: IEEE divide, subtract, floor, no contraction.
 __device__ __forceinline__ int base_node(float x, float h) { return (int)floorf(__fsub_rn(__fdiv_rn(x, h), 0.5f)); }
 
+// The same integer without the IEEE division when x * (1/h) - 1/2 is clearly inside a cell: x * (1/h) differs from the correctly
+// rounded quotient by a few ulps of |x / h| (two roundings instead of one), so only a value within that distance of an integer
+// takes the exact sequence.  Bit-exact by construction; used where the divisions are pure overhead (binning inside G2P).
+__device__ __forceinline__ int base_node_fast(float x, float h, float inv_h) {
+  const float t = fmaf(x, inv_h, -0.5f);
+  const float fl = floorf(t);
+  const float f = t - fl;
+  const float margin = fmaf(fabsf(t), 4e-7f, 1e-6f);
+  if (f > margin && f < 1.f - margin) return (int)fl;
+  return base_node(x, h);
+}
+
 // ------------------------------------------------------------------------------------------------
 // wire <-> SoA
 template <int K>
@@ -573,12 +585,26 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
 // per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile's slot range
 // [first, end) in the binned order (S->n_live ends up as the number of binned particles), and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
 // (update_grid_nodes.rs:102-108)
+// Which particle tiles a launch of P2G / G2P works through, claimed one at a time from `cursor`.  Slab ranks split their tiles into
+// BOUNDARY tiles (block columns lo and hi - 1: the only ones that write grid nodes a neighbour rank also writes, read nodes that
+// receive a neighbour's sums, or hold particles that can leave the slab) and INTERIOR tiles, so that the exchanges overlap work:
+//   P2G(boundary) -> halo send -> P2G(interior) -> halo receive -> G2P(boundary) -> migration send -> G2P(interior) -> migration receive
+struct WorkList {
+  const uint32_t* ids;     // null: the tile ids [0, n_ptiles) themselves
+  const uint32_t* count;   // tiles in the list (a word of the scalars)
+  uint32_t* cursor;
+  int tail;                // G2P: this launch also carries the tombstoned rows over
+};
+struct SlabColumns {
+  int lo, hi;
+  uint32_t* list;          // [2 * tile_cap]: boundary tile ids from 0, interior tile ids from tile_cap; null on a single GPU
+};
 // `Sprev` != null: this substep's set was filled ahead of time by the previous substep's G2P, so this is the FIRST kernel of the substep
 // and it folds what the previous substep's back half raised (a FAILED particle, table status bits, exchange errors) into this
 // substep's scalars — they were initialised before that back half ran — plus, on slab ranks, the row count migration left behind.
 __global__ void __launch_bounds__(256) k_offsets(StepScalars* S, const StepScalars* __restrict__ Sprev, uint32_t n_rows, const uint32_t* __restrict__ n_dev, TileTable T,
                                                  uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, uint32_t* __restrict__ slot_first, const uint32_t* __restrict__ tile_touch,
-                                                 int* __restrict__ nbr) {
+                                                 int* __restrict__ nbr, SlabColumns cols) {
   bool aborted = SVB_ABORTED(S);
   if (Sprev) {
     const uint32_t carry = Sprev->status & ST_CARRY_MASK, stop = Sprev->sticky | Sprev->sticky_new;
@@ -620,6 +646,13 @@ __global__ void __launch_bounds__(256) k_offsets(StepScalars* S, const StepScala
       const uint32_t first = atomicAdd(&S->n_live, inc);
       tile_range[t] = make_uint2(first, first + inc);
       slot_first[slot] = first;
+      if (cols.list) {
+        int bx, by, bz;
+        uint32_t layer;
+        tile_key_unpack(T.tile_key[t], bx, by, bz, layer);
+        const int which = (bx == cols.lo || bx == cols.hi - 1) ? 0 : 1;
+        cols.list[(size_t)which * T.tile_cap + atomicAdd(&S->n_work[which], 1u)] = t;
+      }
     }
     if (lane < 8) nbr[(size_t)t * 8 + lane] = r;
   }
@@ -792,7 +825,7 @@ struct ForceIn {
 };
 template <bool HAS_GOALS>
 __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(ParticleBuf P, const uint32_t* __restrict__ src_of, const uint2* __restrict__ group_range, const int* __restrict__ nbr,
-                                                           StepScalars* S, float4* __restrict__ grid, float h, float dt, ForceIn force) {
+                                                           StepScalars* S, float4* __restrict__ grid, float h, float dt, ForceIn force, WorkList W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   float* stage_all = reinterpret_cast<float*>(smem_raw + P2G_WARPS * TILE_NODES * 16);
@@ -805,7 +838,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
     dt = force.D->allowed;
     force.dt = force.D->dt_force; force.gx = force.D->g[0]; force.gy = force.D->g[1]; force.gz = force.D->g[2]; force.factor_b = force.D->factor_b;
   }
-  const uint32_t n_groups = S->n_ptiles;
+  const uint32_t n_groups = *W.count;
   const float scaling = dt * 4.f / (h * h);
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
@@ -827,10 +860,13 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
 
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_group = atomicAdd(&S->work_counter[0], 1u);
+    if (threadIdx.x == 0) {
+      const uint32_t q = atomicAdd(W.cursor, 1u);
+      s_group = q < n_groups ? (W.ids ? W.ids[q] : q) : 0xffffffffu;
+    }
     __syncthreads();
     const uint32_t g = s_group;
-    if (g >= n_groups) break;
+    if (g == 0xffffffffu) break;
     const uint2 range = group_range[g];
     const uint32_t start = range.x, end = range.y;
     for (int q = threadIdx.x; q < P2G_WARPS * TILE_NODES; q += blockDim.x) tiles[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1046,35 +1082,58 @@ template <bool FUSE, bool REDUCE, bool MELDED, bool SLAB, bool BIN>
 __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
                                                         const uint2* __restrict__ group_range, const int* __restrict__ nbr, StepScalars* S,
                                                         const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn,
-                                                        const unsigned long long* __restrict__ tile_key) {
+                                                        const unsigned long long* __restrict__ tile_key, WorkList W) {
   __shared__ float4 tile[TILE_NODES];
   __shared__ uint32_t s_group;
   __shared__ int s_nbr[8];
-  __shared__ uint32_t s_cache[27];   // BIN: table slots (in the NEXT substep's set) of the 27 blocks around this tile
+  // BIN: a particle moves less than a cell per substep, so its next tile is one of the 27 blocks around this CTA's tile: their table
+  // slots (in the NEXT substep's set) are cached, the cell counts and touch masks of the tile's particles are collected in shared
+  // memory (native integer atomics) and go to HBM once per tile — no table probe, no global atomic and no warp vote per particle
+  __shared__ uint32_t s_cache[27];   // ~0u = not looked up yet
+  __shared__ uint32_t s_touch[27];
+  __shared__ uint32_t s_cnt[BIN ? 27 * 64 : 1];
   __shared__ int s_block[3];
   if (SVB_ABORTED(S)) return;
-  const uint32_t n_groups = S->n_ptiles;
+  if (BIN) {
+    for (int q = threadIdx.x; q < 27 * 64; q += blockDim.x) s_cnt[q] = 0u;
+    if (threadIdx.x < 27) { s_touch[threadIdx.x] = 0u; s_cache[threadIdx.x] = ~0u; }
+  }
+  const uint32_t n_groups = *W.count;
   const float h = K.h, inv_h = 1.f / K.h;
   int red_vel = INT32_MIN, red_def = INT32_MAX;
   uint32_t failed = 0;
   for (;;) {
     __syncthreads();
+    if (BIN) {   // flush what the previous tile's particles counted (every thread flushes and clears its own counters)
+      for (int q = threadIdx.x; q < 27 * 64; q += blockDim.x) {
+        const uint32_t c = s_cnt[q];
+        if (c) { atomicAdd(&bn.B.cell_count[(size_t)s_cache[q >> 6] * 64 + (q & 63)], c); s_cnt[q] = 0u; }
+      }
+      if (threadIdx.x >= 64 && threadIdx.x < 64 + 27) {
+        const uint32_t m = s_touch[threadIdx.x - 64];
+        if (m) { atomicOr(&bn.B.tile_touch[s_cache[threadIdx.x - 64]], m); s_touch[threadIdx.x - 64] = 0u; }
+      }
+    }
     if (threadIdx.x < 8) {
-      uint32_t g0 = 0;
-      if (threadIdx.x == 0) s_group = g0 = atomicAdd(&S->work_counter[1], 1u);
+      uint32_t g0 = 0xffffffffu;
+      if (threadIdx.x == 0) {
+        const uint32_t q = atomicAdd(W.cursor, 1u);
+        if (q < n_groups) g0 = W.ids ? W.ids[q] : q;
+        s_group = g0;
+      }
       g0 = __shfl_sync(0xffu, g0, 0);
-      if (g0 < n_groups) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
-      if (BIN && threadIdx.x == 0 && g0 < n_groups) {
+      if (g0 != 0xffffffffu) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
+      if (BIN && threadIdx.x == 0 && g0 != 0xffffffffu) {
         int bx, by, bz;
         uint32_t layer;
         tile_key_unpack(tile_key[g0], bx, by, bz, layer);
         s_block[0] = bx; s_block[1] = by; s_block[2] = bz;
       }
     }
-    if (BIN && threadIdx.x >= 32 && threadIdx.x < 32 + 27) s_cache[threadIdx.x - 32] = ~0u;
     __syncthreads();
+    if (BIN && threadIdx.x >= 32 && threadIdx.x < 32 + 27) s_cache[threadIdx.x - 32] = ~0u;   // (the flush above has read the old slots)
     const uint32_t g = s_group;
-    if (g >= n_groups) break;
+    if (g == 0xffffffffu) break;
     const uint2 range = group_range[g];
     const uint32_t start = range.x, end = range.y;
     for (int t = threadIdx.x; t < TILE_NODES; t += blockDim.x) {
@@ -1191,11 +1250,48 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
       D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
       }
-      if (BIN) bin_warp<false, true>(bin_state, bin_x, 0u, i < end, i, K, bn.T, bn.B, bn.S, lane, s_cache, s_block[0], s_block[1], s_block[2]);
+      if (BIN && i < end) {
+        uint32_t ci = bin_state == 1 ? 0xffffffffu : 0xfffffffdu;
+        if (bin_state == 1) atomicAdd(&bn.S->n_tomb, 1u);   // culled just now (rare)
+        if (bin_state == 0) {
+          const int s0 = base_node_fast(bin_x.x, h, inv_h), s1 = base_node_fast(bin_x.y, h, inv_h), s2 = base_node_fast(bin_x.z, h, inv_h);
+          const int b0 = floor_div4(s0), b1 = floor_div4(s1), b2 = floor_div4(s2);
+          const uint32_t cell = ((uint32_t)(s0 & 3) << 4) | ((uint32_t)(s1 & 3) << 2) | (uint32_t)(s2 & 3);
+          uint32_t touch = 1u;   // neighbour offsets reached by the 3-node stencil: +1 on an axis iff the in-block coordinate >= 2
+          if (s0 & 2) touch |= touch << 1;
+          if (s1 & 2) touch |= touch << 2;
+          if (s2 & 2) touch |= touch << 4;
+          const int d0 = b0 - s_block[0] + 1, d1 = b1 - s_block[1] + 1, d2 = b2 - s_block[2] + 1;
+          const int lim = BLOCK_BIAS - 2;
+          ci = 0xfffffffeu;
+          if (b0 < -lim || b0 > lim || b1 < -lim || b1 > lim || b2 < -lim || b2 > lim) atomicOr(&bn.S->status, ST_KEY_RANGE);
+          else if ((unsigned)d0 < 3u && (unsigned)d1 < 3u && (unsigned)d2 < 3u) {
+            const int at = (d0 * 3 + d1) * 3 + d2;
+            uint32_t slot = ((volatile uint32_t*)s_cache)[at];
+            if (slot == ~0u) {   // the first particle(s) of this tile that reach the block look its tile up (or create it)
+              slot = tile_slot_find_or_insert(bn.T, tile_key_pack(b0, b1, b2, 0u), bn.S);
+              if (slot != ~0u) ((volatile uint32_t*)s_cache)[at] = slot;
+            }
+            if (slot != ~0u) {
+              atomicAdd(&s_cnt[at * 64 + cell], 1u);
+              atomicOr(&s_touch[at], touch);
+              ci = slot * 64u + cell;
+            }
+          } else {   // more than a block away (no CFL-respecting step does this): straight to the tables
+            const uint32_t slot = tile_slot_find_or_insert(bn.T, tile_key_pack(b0, b1, b2, 0u), bn.S);
+            if (slot != ~0u) {
+              atomicAdd(&bn.B.cell_count[(size_t)slot * 64 + cell], 1u);
+              atomicOr(&bn.B.tile_touch[slot], touch);
+              ci = slot * 64u + cell;
+            }
+          }
+        }
+        bn.B.pcell[i] = ci;
+      }
     }
   }
   // tombstoned particles take no part in P2G / G2P: carry their rows over as they are (behind the live ones)
-  {
+  if (W.tail) {
     const uint32_t n_live = S->n_live, n_end = n_live + S->n_tomb;  // rows of migrated particles are gone
     for (uint32_t j = n_live + blockIdx.x * blockDim.x + threadIdx.x; j < n_end; j += gridDim.x * blockDim.x) {
       const uint32_t i = src_of[j];
