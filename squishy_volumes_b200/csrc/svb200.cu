@@ -82,7 +82,7 @@ struct SvbHandle {
   cudaEvent_t ev_front = nullptr;
   // peer-memory slab ranks run up to two substeps ahead of the host's look at the front-half scalars, so that a late host thread
   // (eight processes share the box's cores) never leaves its GPU — and through the exchange waits its neighbours — idle
-  struct FrontLag { StepScalars* host = nullptr; cudaEvent_t ev = nullptr; double time_before = 0; uint64_t substeps_before = 0; bool was_ahead = false; } lag[4];
+  struct FrontLag { StepScalars* host = nullptr; cudaEvent_t ev = nullptr; double time_before = 0; uint64_t substeps_before = 0; bool was_ahead = false; uint32_t seq_before = 0, dtx_before = 0; } lag[4];
   uint64_t lag_issued = 0, lag_done = 0;
   uint32_t n_ptiles = 0, n_live = 0, n_tiles = 0;
   bool have_grid = false;
@@ -118,12 +118,14 @@ struct SvbHandle {
   void* peer_mailbox[16] = {};          // every rank's mailbox mapped into this process (null for self)
   size_t mb_halo_cap = 0, mb_mig_cap = 0, mb_halo_off[2] = {0, 0}, mb_mig_off[2] = {0, 0};
   uint32_t slab_seq = 0;                // message sequence number = slab substeps started
+  uint32_t dt_exchanges = 0;            // adaptive time steps: limit exchanges started (the same on every rank)
   uint32_t* n_dev = nullptr;            // device word: rows currently in the particle buffer
   uint32_t* p2p_local = nullptr;        // device scratch of the sending kernels (slot counters, blocks done)
 
   double time = 0;
   double time_before_last = 0;      // clock before the most recent substep (taken back when that substep turns out to have failed)
   bool failed_rolled_back = false;
+  bool device_clock = false;        // this svb_advance call runs adaptive steps: the clock lives in DtState
   uint32_t stop_bits = 0;           // sticky word (errors | ST_STOP_*) that ended the last substep loop
   svbh::AdaptiveTimeStep adaptive;
   uint64_t substeps = 0;
@@ -475,6 +477,24 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in);
 int setup_peer_mailboxes(SvbHandle* h);
 int resize_particles(SvbHandle* h, size_t new_cap);
 
+// slab ranks exchange the limit reductions of adaptive time stepping through the mailbox headers (k_dt_*: dt_exchange)
+DtPeers dt_peers(SvbHandle* h) {
+  DtPeers p{};
+  p.rank = h->rank;
+  p.n_ranks = h->p2p ? h->n_ranks : 1;
+  if (h->p2p) {
+    p.mine = h->mailbox.as<SlabHeader>();
+    for (int r = 0; r < h->n_ranks; ++r)
+      if (r != h->rank) {
+        SlabHeader* ph = reinterpret_cast<SlabHeader*>(h->peer_mailbox[r]);
+        p.post_seq[r] = &ph->dt_seq[0][h->rank];
+        p.post_val[r] = ph->dt_val[0][h->rank];
+      }
+    p.exchange = ++h->dt_exchanges;
+  }
+  return p;
+}
+
 int enqueue_mesh(SvbHandle* h, const StepInputs& in) {
   cudaStream_t s = h->stream;
   stage_begin(h, ST_MESH);
@@ -512,7 +532,7 @@ int substep(SvbHandle* h, bool adaptive_steps) {
   if (in.has_mesh)
     if (int rc = enqueue_mesh(h, in)) return rc;
   if (h->slabs) {
-    if (adaptive_steps) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps are not supported with slab decomposition yet");
+    if (adaptive_steps && !h->p2p) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps on slab ranks need the peer-memory exchange path (SVB_SLAB_NCCL forces the NCCL fallback)");
     return h->p2p ? substep_slab_p2p(h, in) : substep_slab(h, in);
   }
   if (n == 0) {
@@ -544,16 +564,16 @@ int substep(SvbHandle* h, bool adaptive_steps) {
       // -- LimitTimeStepBeforeIntegrate, AdvanceParticles + CullParticles, the clock: all on the device
       DtState* D = h->dt_state.as<DtState>();
       stage_begin(h, ST_LIMIT);
-      k_dt_integrate<<<1, 1, 0, s>>>(D, cur_scalars(h));
+      k_dt_integrate<<<1, 1, 0, s>>>(D, cur_scalars(h), dt_peers(h));
       LAUNCH_CHECK();
       stage_end(h);
       stage_begin(h, ST_ADVANCE);
       BinNext bn{};
       if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
-      if (bin_next) k_advance<true><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, D, bn);
-      else k_advance<false><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, D, bn);
+      if (bin_next) k_advance<true><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, D, bn, MigrateCut{});
+      else k_advance<false><<<blocks_for(n, 256), 256, 0, s>>>(h->Pc(), h->energy.as<float>(), cur_scalars(h), h->K, n, D, bn, MigrateCut{});
       LAUNCH_CHECK();
-      k_dt_tail<<<1, 1, 0, s>>>(D, cur_scalars(h));
+      k_dt_tail<<<1, 1, 0, s>>>(D, cur_scalars(h), dt_peers(h));
       LAUNCH_CHECK();
       CK(cudaMemcpyAsync(h->h_dt, D, sizeof(DtState), cudaMemcpyDeviceToHost, s));
       stage_end(h);
@@ -645,10 +665,14 @@ int process_front_p2p(SvbHandle* h) {
     const uint64_t noops = h->lag_issued - h->lag_done;
     if (noops & 1) { h->cur ^= 1; h->s_cur ^= 1; }   // each queued G2P swapped the buffers and each front the set: undo (they wrote nothing)
     h->binned_ahead = L.was_ahead;
+    h->slab_seq = L.seq_before;       // the no-op substeps sent nothing (the exchange kernels return on a stopped run): every rank
+    h->dt_exchanges = L.dtx_before;   // forgets its own — possibly different — number of them and the message numbers stay in step
     // the clock of the substep that raised the error does not count either (cpu_state.rs:176-190)
     const SvbHandle::FrontLag& failing = h->lag_done > 0 ? h->lag[(h->lag_done - 1) % 4] : L;
-    h->time = failing.time_before;
-    h->substeps = failing.substeps_before;
+    if (!h->device_clock) {
+      h->time = failing.time_before;
+      h->substeps = failing.substeps_before;
+    }
     h->failed_rolled_back = true;
     h->stop_bits = r.sticky;
     h->lag_done = h->lag_issued;
@@ -677,10 +701,10 @@ int process_front_p2p(SvbHandle* h) {
 int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   cudaStream_t s = h->stream;
   const float dt = in.dt;
+  SvbHandle::FrontLag& L = h->lag[h->lag_issued % 4];
+  L.time_before = h->time; L.substeps_before = h->substeps; L.was_ahead = h->binned_ahead; L.seq_before = h->slab_seq; L.dtx_before = h->dt_exchanges;
   const uint32_t seq = ++h->slab_seq;
   const bool bin_next = !in.has_mesh;
-  SvbHandle::FrontLag& L = h->lag[h->lag_issued % 4];
-  L.time_before = h->time; L.substeps_before = h->substeps; L.was_ahead = h->binned_ahead;
   h->h_scalars = L.host;
   h->ev_front = L.ev;
   if (int rc = enqueue_front(h, in, /*redo=*/false)) return rc;
@@ -727,7 +751,22 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   if (in.has_mesh)
     if (int rc = enqueue_meld(h)) return rc;
   const int src_buf = h->cur;
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 0, 1, 1), src_buf, &cut, 148 * 2)) return rc;
+  BinNext bn{};
+  if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
+  DtState* D = h->dt_state.as<DtState>();
+  if (!in.adaptive) {
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 0, 1, 1), src_buf, &cut, 148 * 2)) return rc;
+  } else {
+    // adaptive steps: G2P with the reductions of LimitTimeStepBeforeIntegrate over all tiles, the global limits (all ranks), then
+    // the advance — which notes the leavers and bins the rest ahead — as its own pass (the step is only known now)
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/false, dt, false, work_all(h, 1, 1), src_buf)) return rc;
+    k_dt_integrate<<<1, 1, 0, s>>>(D, S, dt_peers(h));
+    LAUNCH_CHECK();
+    const uint32_t rows = (uint32_t)h->cap;
+    if (bin_next) k_advance<true><<<blocks_for(rows, 256), 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, h->K, rows, D, bn, cut);
+    else k_advance<false><<<blocks_for(rows, 256), 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, h->K, rows, D, bn, cut);
+    LAUNCH_CHECK();
+  }
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
   SlabPeers peers{};
@@ -748,26 +787,33 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       peers.err_val[r] = &ph->err_val[h->rank];
     }
   // (the rows G2P wrote live in the OTHER buffer until `cur` is swapped below)
-  k_migrate_send_list<<<148, 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0);
   LAUNCH_CHECK();
   stage_end(h);
   stage_begin(h, ST_G2P);
-  if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 1, 3, 0), src_buf, &cut)) return rc;
+  if (!in.adaptive)
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 1, 3, 0), src_buf, &cut)) return rc;
   h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
-  BinNext bn{};
-  if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0, h->K, bn, bin_next ? 1 : 0);
   LAUNCH_CHECK();
+  if (in.adaptive) {   // the clock moves on every rank alike (after the error words of this substep have been folded in)
+    k_dt_tail<<<1, 1, 0, s>>>(D, S, dt_peers(h));
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(h->h_dt, D, sizeof(DtState), cudaMemcpyDeviceToHost, s));
+  }
   stage_end(h);
   ++h->lag_issued;
   h->binned_ahead = bin_next;
+  h->limits_ahead = in.adaptive;
   h->have_grid = true;
-  h->time_before_last = h->time;
-  h->time += (double)dt;
-  ++h->substeps;
+  if (!in.adaptive) {
+    h->time_before_last = h->time;
+    h->time += (double)dt;
+    ++h->substeps;
+  }
   // ---- the host catches up with the front half of an earlier substep (the queued work keeps the GPU busy meanwhile)
   while (h->lag_issued - h->lag_done > (h->timing ? 0u : 2u)) {
     const int rc = process_front_p2p(h);
@@ -1099,7 +1145,8 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (h->p2p && (size_t)h->n + 2 * inflow > h->cap) {
     if (int rc = resize_particles(h, ((size_t)h->n + 2 * inflow) * 5 / 4)) return rc;
   }
-  if (adaptive && !h->slabs && h->n > 0) {
+  h->device_clock = adaptive && (h->slabs ? h->p2p : h->n > 0);
+  if (h->device_clock) {
     // ---- the clock and AdaptiveTimeStepState move to the device for the duration of the call
     DtState d{};
     d.time = h->time; d.target = target_time; d.fps = (double)h->consts.frames_per_second; d.frame = h->frame;
@@ -1121,10 +1168,11 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
     *h->h_dt = d;
     CK(cudaMemcpyAsync(D, h->h_dt, sizeof d, cudaMemcpyHostToDevice, s));
     if (!h->limits_ahead) {
-      k_limit_force<<<blocks_for(h->n, 256), 256, 0, s>>>(h->Pc(), D, h->K.h, h->n, nullptr);
+      const uint32_t rows = h->p2p ? (uint32_t)h->cap : h->n;
+      k_limit_force<<<std::max<uint32_t>(blocks_for(rows, 256), 1), 256, 0, s>>>(h->Pc(), D, h->K.h, rows, h->p2p ? h->n_dev : nullptr);
       LAUNCH_CHECK();
     }
-    k_dt_open<<<1, 1, 0, s>>>(D, cur_scalars(h));
+    k_dt_open<<<1, 1, 0, s>>>(D, cur_scalars(h), dt_peers(h));
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(h->h_dt, D, sizeof d, cudaMemcpyDeviceToHost, s));
     h->limits_ahead = false;
@@ -1137,6 +1185,11 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
       if (progress) progress(user, (size_t)(std::fmod(h->h_dt->time, spf) * 1000.0));
     }
     if (rc < 0) return rc;
+    while (h->p2p && h->lag_done < h->lag_issued) {   // (a slab rank may not have looked at its last fronts yet)
+      const int rc2 = process_front_p2p(h);
+      if (rc2 < 0) return rc2;
+      if (rc2 == 2) break;
+    }
     // rc == 2: a stop word ended the run — the target time, a failed particle, a wrong frame, a zero time step
     CK(cudaMemcpyAsync(h->h_dt, D, sizeof d, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1152,7 +1205,7 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
     if (h->stop_bits & ST_STOP_ZERO_DT) return fail(h, SVB_ZERO_TIME_STEP, "The time step ended up being 0");
     if (h->stop_bits & ST_STOP_FRAME) return fail(h, SVB_FRAME_INPUT, "Wrong frame loaded: %llu (need %llu)", (unsigned long long)h->frame, (unsigned long long)std::floor(e.time * e.fps));
   } else {
-    if (adaptive && h->slabs) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps are not supported with slab decomposition yet");
+    if (adaptive && h->slabs) return fail(h, SVB_BAD_ARGUMENT, "adaptive time steps on slab ranks need the peer-memory exchange path (SVB_SLAB_NCCL forces the NCCL fallback)");
     h->adaptive.has_override = false;
     if (adaptive && h->n == 0) {   // nothing limits the step: the reference walks to the target in steps of max_time_step
       h->adaptive = svbh::AdaptiveTimeStep();
@@ -1712,7 +1765,7 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
       peers.err_seq[r] = &ph->err_seq[h->rank];
       peers.err_val[r] = &ph->err_val[h->rank];
     }
-  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10);
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 1);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1, h->K, BinNext{}, 0);

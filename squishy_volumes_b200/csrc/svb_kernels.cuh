@@ -1317,6 +1317,68 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
   if (FUSE && failed) atomicOr(&S->sticky_new, 8u /*SVB_PARTICLE_CLOSE_TO_INVERTED*/);
 }
 
+// ---- peer-memory mailbox header and system-scope accessors (used by the slab exchanges below and by the time-step kernels)
+constexpr int SLAB_MAX_RANKS = 16;
+constexpr uint32_t SLAB_OVERFLOW = 0x80000000u;   // count word: the sender ran out of mailbox capacity
+struct SlabHeader {
+  uint32_t halo_seq[2], halo_count[2];   // [0] written by the left neighbour, [1] by the right one
+  uint32_t mig_seq[2], mig_count[2];
+  uint32_t err_seq[SLAB_MAX_RANKS], err_val[SLAB_MAX_RANKS];  // every rank posts its sticky error word to every rank
+  // adaptive time steps: every rank posts its limit reductions to every rank; two slots alternate (an exchange may only overwrite
+  // the slot of the exchange before last, which every rank has provably finished reading)
+  uint32_t dt_seq[2][SLAB_MAX_RANKS];
+  int32_t dt_val[2][SLAB_MAX_RANKS][4];
+};
+__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// true when *p reached `seq`; gives up after ~2 s so a lost neighbour cannot hang the GPU
+__device__ __forceinline__ bool wait_seq(const uint32_t* p, uint32_t seq) {
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    if ((int32_t)(ld_sys(p) - seq) >= 0) return true;
+    __nanosleep(spin < 64 ? 32 : 400);
+  }
+  return false;
+}
+
+// slab ranks: the limit reductions of adaptive time stepping are global minima / maxima over all ranks.  Every rank posts its three
+// words to every rank and waits for everybody else's; min / max are order-independent, so all ranks compute the same step.
+struct DtPeers {
+  int rank, n_ranks;                       // n_ranks <= 1: single device, nothing to exchange
+  uint32_t* post_seq[SLAB_MAX_RANKS];      // [r]: &header_of_rank_r.dt_seq[0][rank]   (null for r == rank)
+  int32_t* post_val[SLAB_MAX_RANKS];       // [r]: header_of_rank_r.dt_val[0][rank]
+  const SlabHeader* mine;
+  uint32_t exchange;                       // number of this exchange (same on every rank, strictly increasing)
+};
+// combine (a: min, b: min, c: max, d: max) over all ranks; false on a timeout
+__device__ __forceinline__ bool dt_exchange(const DtPeers& P, int32_t& a, int32_t& b, int32_t& c, int32_t& d) {
+  if (P.n_ranks <= 1) return true;
+  const uint32_t slot = P.exchange & 1u, stride_seq = SLAB_MAX_RANKS, stride_val = SLAB_MAX_RANKS * 4;
+  for (int r = 0; r < P.n_ranks; ++r)
+    if (r != P.rank) {
+      int32_t* v = P.post_val[r] + slot * stride_val;
+      asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(v), "r"(a) : "memory");
+      asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(v + 1), "r"(b) : "memory");
+      asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(v + 2), "r"(c) : "memory");
+      asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(v + 3), "r"(d) : "memory");
+      st_sys(P.post_seq[r] + slot * stride_seq, P.exchange);
+    }
+  bool ok = true;
+  for (int r = 0; r < P.n_ranks; ++r)
+    if (r != P.rank) {
+      if (!wait_seq(&P.mine->dt_seq[slot][r], P.exchange)) { ok = false; continue; }
+      const int32_t* v = P.mine->dt_val[slot][r];
+      a = min(a, (int32_t)ld_sys((const uint32_t*)v));
+      b = min(b, (int32_t)ld_sys((const uint32_t*)(v + 1)));
+      c = max(c, (int32_t)ld_sys((const uint32_t*)(v + 2)));
+      d = max(d, (int32_t)ld_sys((const uint32_t*)(v + 3)));
+    }
+  return ok;
+}
+
 // ------------------------------------------------------------------------------------------------
 // adaptive time stepping with the state machine on the device (DtState, svb_device.cuh)
 __device__ __forceinline__ float dt_total_min(float a, float b) { return total_key(b) < total_key(a) ? b : a; }   // min_by(f32::total_cmp) keeps the first minimum
@@ -1350,9 +1412,12 @@ __device__ __forceinline__ bool dt_interpolate_input(DtState& d) {
   for (int k = 0; k < 3; ++k) d.g[k] = fa * d.ga[k] + d.factor_b * d.gb[k];
   return true;
 }
-// LimitTimeStepBeforeForce (limit_time_step.rs:25-33) from the reductions in next_*; resets them for the next round
-__device__ __forceinline__ void dt_limit_before_force(DtState& d) {
-  const bool any = d.next_live > 0;
+// LimitTimeStepBeforeForce (limit_time_step.rs:25-33) from the reductions in next_*; resets them for the next round.
+// false: a slab neighbour did not answer
+__device__ __forceinline__ bool dt_limit_before_force(DtState& d, const DtPeers& peers) {
+  int32_t live = d.next_live > 0 ? 1 : 0, unused = 0;
+  const bool ok = dt_exchange(peers, d.next_min_sound_key, d.next_min_isolated_key, live, unused);
+  const bool any = live > 0;
   d.has = (d.has & ~12u) | (any ? 12u : 0u);
   if (any) {
     d.by_sound = total_unkey(d.next_min_sound_key);
@@ -1361,10 +1426,11 @@ __device__ __forceinline__ void dt_limit_before_force(DtState& d) {
   dt_push(d);
   d.allowed = dt_allowed(d);
   d.next_min_sound_key = INT32_MAX; d.next_min_isolated_key = INT32_MAX; d.next_live = 0;
+  return ok;
 }
 // Start of an svb_advance call (one thread).  The host has written time / target / max_dt / fps / frame / gravities and cleared `stop`.
 // `S` = the scalars of the substep about to run (its sticky words were cleared by the host).
-__global__ void k_dt_open(DtState* D, StepScalars* S) {
+__global__ void k_dt_open(DtState* D, StepScalars* S, DtPeers peers) {
   DtState d = *D;
   uint32_t stop = 0;
   d.substeps = 0;
@@ -1373,8 +1439,8 @@ __global__ void k_dt_open(DtState* D, StepScalars* S) {
   if (!(d.time < d.target)) stop |= ST_STOP_DONE;
   else if (!dt_interpolate_input(d)) stop |= ST_STOP_FRAME;
   d.dt_force = d.allowed;
-  if (!stop) {
-    dt_limit_before_force(d);
+  if (!stop) {   // (every rank takes the same branch: time, target, frame and the step history are the same everywhere)
+    if (!dt_limit_before_force(d, peers)) atomicOr(&S->status, ST_COMM_TIMEOUT);
     if (d.allowed == 0.f) stop |= ST_STOP_ZERO_DT;
   }
   d.stop = stop;
@@ -1382,15 +1448,18 @@ __global__ void k_dt_open(DtState* D, StepScalars* S) {
   if (stop) S->sticky |= stop;   // no kernel of this substep has started yet: the whole substep is a no-op
 }
 // LimitTimeStepBeforeIntegrate (limit_time_step.rs:187-223) from the G2P reductions of this substep
-__global__ void k_dt_integrate(DtState* D, StepScalars* S) {
+__global__ void k_dt_integrate(DtState* D, StepScalars* S, DtPeers peers) {
   if (SVB_ABORTED(S)) return;
   DtState d = *D;
-  const bool any = S->n_live > 0;
-  const float max_vel = any ? total_unkey(S->max_velocity_key) : 0.f;
+  // global over all slab ranks: min deformation limit, max velocity, any live particle anywhere
+  int32_t def_key = S->min_deformation_key, unused = INT32_MAX, vel_key = S->max_velocity_key, live = S->n_live > 0 ? 1 : 0;
+  if (!dt_exchange(peers, def_key, unused, vel_key, live)) atomicOr(&S->status, ST_COMM_TIMEOUT);
+  const bool any = live > 0;
+  const float max_vel = any && vel_key != INT32_MIN ? total_unkey(vel_key) : 0.f;
   const bool has_vel = any && max_vel != 0.f;
   d.has = (d.has & ~3u) | (has_vel ? 1u : 0u) | (any ? 2u : 0u);
   if (has_vel) d.by_velocity = 0.5f * d.h / max_vel;
-  if (any) d.by_deformation = total_unkey(S->min_deformation_key);
+  if (any) d.by_deformation = total_unkey(def_key);
   dt_push(d);
   d.allowed = dt_allowed(d);
   *D = d;
@@ -1398,7 +1467,7 @@ __global__ void k_dt_integrate(DtState* D, StepScalars* S) {
 }
 // End of a substep: the clock moves on (cpu_state.rs:187-190), then everything the NEXT substep needs before its first kernel:
 // the run-is-over test, the frame factor and gravity, and LimitTimeStepBeforeForce from the limits k_advance reduced on the advanced F.
-__global__ void k_dt_tail(DtState* D, StepScalars* S) {
+__global__ void k_dt_tail(DtState* D, StepScalars* S, DtPeers peers) {
   if (SVB_ABORTED(S)) return;
   if (S->sticky_new & 0xffffu) return;   // a FAILED particle: the reference returns from the Advance phase without moving the clock (cpu_state.rs:176-184)
   DtState d = *D;
@@ -1410,7 +1479,7 @@ __global__ void k_dt_tail(DtState* D, StepScalars* S) {
   else if (!dt_interpolate_input(d)) stop |= ST_STOP_FRAME;
   d.dt_force = d.allowed;
   if (!stop) {
-    dt_limit_before_force(d);
+    if (!dt_limit_before_force(d, peers)) atomicOr(&S->status, ST_COMM_TIMEOUT);
     if (d.allowed == 0.f) stop |= ST_STOP_ZERO_DT;
   }
   d.stop |= stop;
@@ -1422,7 +1491,7 @@ __global__ void k_dt_tail(DtState* D, StepScalars* S) {
 // position and F — the binning of the next substep (BIN, scenes without a collider mesh) and the per-particle limits of the next
 // substep's LimitTimeStepBeforeForce (limit_time_step.rs:35-182).  One thread per row of the binned buffer, tombstoned rows included.
 template <bool BIN>
-__global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn) {
+__global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn, MigrateCut mc) {
   if (SVB_ABORTED(S)) return;
   n = min(n, S->n_live + S->n_tomb);
   const float dt = D->allowed;
@@ -1457,6 +1526,21 @@ __global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restric
       P.u(PFLAGS)[i] = flags;
       if (within) {
         bin_state = 0;
+        if (mc.list) {   // slab ranks: note the particles whose advanced position left the rank's block columns (like the fused G2P)
+          const float approx_node = x.x * (1.f / K.h) - 0.5f;
+          if (approx_node < mc.node_lo + 0.5f || approx_node > mc.node_hi - 0.5f) {
+            const int bx = floor_div4(base_node(x.x, K.h));
+            if (bx < mc.lo || bx >= mc.hi) {
+              if (bx < mc.reach_lo || bx >= mc.reach_hi) atomicOr(&S->status, ST_KEY_RANGE);   // crossed more than one slab in a substep
+              else {
+                const int side = bx < mc.lo ? 0 : 1;
+                const uint32_t slot = atomicAdd(&mc.counts[side], 1u);
+                if (slot < mc.cap) mc.list[(size_t)side * mc.cap + slot] = i;
+                bin_state = 2;
+              }
+            }
+          }
+        }
         const ParticleLimits l = particle_time_step_limits((flags & F_IS_FLUID) != 0, p0, p1, P.f(PMASS)[i], P.f(PVOL)[i], F, K.h);
         ks = total_key(l.by_sound);
         ki = total_key(l.by_isolated);
@@ -1581,28 +1665,6 @@ __global__ void __launch_bounds__(256) k_unpack_add(StepScalars* S, TileTable T,
 // publishes the count and then the substep sequence number with system-scope fences.  The receiving kernel
 // spins (bounded) on the sequence number in its own HBM.  Buffers are reused safely because a rank can only
 // send message k+1 after it has consumed the neighbour's message k of the other kind.
-constexpr int SLAB_MAX_RANKS = 16;
-constexpr uint32_t SLAB_OVERFLOW = 0x80000000u;   // count word: the sender ran out of mailbox capacity
-struct SlabHeader {
-  uint32_t halo_seq[2], halo_count[2];   // [0] written by the left neighbour, [1] by the right one
-  uint32_t mig_seq[2], mig_count[2];
-  uint32_t err_seq[SLAB_MAX_RANKS], err_val[SLAB_MAX_RANKS];  // every rank posts its sticky error word to every rank
-};
-__device__ __forceinline__ uint32_t ld_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-// true when *p reached `seq`; gives up after ~2 s so a lost neighbour cannot hang the GPU
-__device__ __forceinline__ bool wait_seq(const uint32_t* p, uint32_t seq) {
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
-    if ((int32_t)(ld_sys(p) - seq) >= 0) return true;
-    __nanosleep(spin < 64 ? 32 : 400);
-  }
-  return false;
-}
-
 // both directions in one launch: tiles of my first column go to the left neighbour, tiles of my halo column (== hi) to the
 // right one; `local` = [0], [1] slot counters, [2] blocks done
 struct HaloPeers {
@@ -1611,6 +1673,9 @@ struct HaloPeers {
 };
 __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid, int lo, int hi,
                                                     HaloPeers peers, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local) {
+  // a run that was stopped by an earlier substep (sticky is the same word on every rank: error words are exchanged, stop bits come
+  // from identical clocks) exchanges nothing: every rank skips the same messages, however many no-op substeps its host queued
+  if (S->sticky) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   if (!SVB_ABORTED(S)) {
@@ -1657,6 +1722,7 @@ __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restric
 __global__ void __launch_bounds__(256) k_halo_recv2(StepScalars* S, TileTable T, unsigned long long* layer_slots, uint32_t* layer_list, float4* __restrict__ grid, const HaloEntry* __restrict__ in_left,
                                                     const HaloEntry* __restrict__ in_right, const SlabHeader* __restrict__ hdr, int has_left, int has_right, uint32_t seq) {
   __shared__ uint32_t s_count[2];
+  if (S->sticky) return;   // stopped run: nothing was sent (see k_halo_send2)
   if (threadIdx.x == 0) {
     const int has[2] = {has_left, has_right};
     for (int side = 0; side < 2; ++side) {
@@ -1736,8 +1802,9 @@ struct SlabPeers {
 // Sending side, driven by the lists k_g2p<SLAB> filled (slots whose advanced position left the slab): one thread per
 // migrating row; the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
 __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, MigrateCut mc, SlabPeers peers, uint32_t cap, uint32_t seq,
-                                                           uint32_t* __restrict__ blocks_done) {
+                                                           uint32_t* __restrict__ blocks_done, int between_substeps) {
   __shared__ uint32_t s_c[2];
+  if (!between_substeps && S->sticky) return;   // stopped run: no message (see k_halo_send2)
   if (threadIdx.x < 2) s_c[threadIdx.x] = atomicAdd(&mc.counts[threadIdx.x], 0u);
   __syncthreads();
   const uint32_t c0 = s_c[0], c1 = s_c[1];
@@ -1780,6 +1847,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
                                                       const uint32_t* __restrict__ rows_right, int has_left, int has_right, int rank, int n_ranks, uint32_t seq, uint32_t* __restrict__ n_dev,
                                                       int between_substeps, SimConsts K, BinNext bn, int bin) {
   __shared__ uint32_t s_c[2];
+  if (!between_substeps && S->sticky) return;   // stopped run: nothing was sent (see k_halo_send2)
   if (threadIdx.x == 0) {
     uint32_t c[2] = {0, 0};
     const int has[2] = {has_left, has_right};

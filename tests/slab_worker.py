@@ -35,6 +35,19 @@ def build_scene(name):
     if name == "sand":
         sc, _, _ = golden_scenes.GOLDEN["sand_torus"]()
         return sc
+    if name == "jelly_adaptive":
+        # adaptive time steps on slab ranks: max_time_step 4x the fixed step, so the four limits decide; the global minima / maxima
+        # travel through the mailbox headers (k_dt_*: dt_exchange) and every rank must take the very same steps
+        sc = scenes.jelly_collision(side=16)
+        sc.io_state.particles.velocities[:, 0] *= 6.0
+        sc.time_step = 4e-3
+        return sc
+    if name == "energy_error":
+        # a FAILED particle on one rank stops every rank; the state of the failing substep comes back with the simulation-level error
+        sc = scenes.jelly_collision(side=16)
+        sc.io_state.particles.velocities[:, 0] *= 6.0
+        sc.io_state.particles.position_gradients[7] = -np.eye(3, dtype=np.float32)
+        return sc
     raise SystemExit(name)
 
 
@@ -65,6 +78,27 @@ def main():
         plan = [(bounds[r], bounds[r + 1]) for r in range(world)]
     st = slabs.SlabState.from_io_state(sc.io_state, sc.frame_input, rank, world, local, box[0], plan=plan)
     params = RunParameters(target_time=(steps - 0.5) * sc.time_step, max_time_step=sc.time_step)
+    adaptive = name == "jelly_adaptive"
+    if adaptive:
+        params = RunParameters(target_time=steps * 1e-3, max_time_step=sc.time_step, adaptive_time_steps=True)
+    if name == "energy_error":
+        err = st.advance(None, sc.frame_input, params)
+        idx, rows = st.resident()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (idx, rows, st.substeps, st.time, None if err is None else err.status))
+        if rank == 0:
+            single = B200State.from_io_state(sc.io_state, sc.frame_input, device=local)
+            ref, err1 = single.produce_next_state(None, sc.frame_input, params)
+            assert err1 is not None and err1.status & 8
+            assert all(g[4] is not None and g[4] & 8 for g in gathered), [g[4] for g in gathered]          # every rank reports it
+            assert all(g[2] == single.substeps and g[3] == single.time for g in gathered), ([(g[2], g[3]) for g in gathered], single.substeps, single.time)
+            got = slabs.assemble(sc.n, [(g[0], g[1]) for g in gathered], sc.io_state.particles)
+            assert np.array_equal(got.flags, ref.particles.flags) and got.flags[7] & ParticleFlags.FAILED
+            print(f"[{name}] world={world}: every rank stopped after the failing substep ({single.substeps} counted), flags equal the single-GPU run; within tolerance", flush=True)
+        st.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if name == "jelly_rebalance":
         half = RunParameters(target_time=(steps // 2 - 0.5) * sc.time_step, max_time_step=sc.time_step)
         err = st.advance(None, sc.frame_input, half)
@@ -81,14 +115,21 @@ def main():
     err = st.advance(None, sc.frame_input, params)
     idx, rows = st.resident()
     gathered = [None] * world
-    dist.all_gather_object(gathered, (idx, rows, st.substeps, None if err is None else err.status))
+    dist.all_gather_object(gathered, (idx, rows, st.substeps, None if err is None else err.status, st.time, st.inner.allowed_time_step))
     ok = True
     if rank == 0:
         print('resident per rank', [len(g[0]) for g in gathered], 'sum', sum(len(g[0]) for g in gathered), 'of', sc.n, 'unique', len(np.unique(np.concatenate([g[0] for g in gathered]))), flush=True)
-        assert all(g[2] == steps for g in gathered), [g[2] for g in gathered]
         got = slabs.assemble(sc.n, [(g[0], g[1]) for g in gathered], sc.io_state.particles)
         single = B200State.from_io_state(sc.io_state, sc.frame_input, device=local)
         ref, _ = single.produce_next_state(None, sc.frame_input, params)
+        if adaptive:
+            # every rank took the very same steps (the clocks agree bit for bit); against the single-GPU run the limits differ in the
+            # last bits (float atomics order the grid sums differently), so its clock is only close
+            assert all(g[2] == gathered[0][2] and g[4] == gathered[0][4] and g[5] == gathered[0][5] for g in gathered), [(g[2], g[4], g[5]) for g in gathered]
+            assert gathered[0][2] == single.substeps and single.substeps < steps, (gathered[0][2], single.substeps)
+            assert abs(gathered[0][4] - single.time) <= 1e-5 * single.time and abs(gathered[0][5] - single.allowed_time_step) <= 1e-4 * single.allowed_time_step
+        else:
+            assert all(g[2] == steps for g in gathered), [g[2] for g in gathered]
         from squishy_volumes_b200.types import IoState
         h = sc.frame_input.consts.scaled_grid_node_size()
         # slab ownership after the run: every particle sits on the rank that owns its block column

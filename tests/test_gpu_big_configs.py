@@ -15,7 +15,7 @@ def test_full_size_config_properties(name, particles):
     if particles > 20_000_000 and os.environ.get("SVB_BIG_CONFIGS") != "1":
         pytest.skip("64 M particles: set SVB_BIG_CONFIGS=1 (needs ~40 GB of host memory); hand-run result in profiles/r1q_big_configs_1gpu.jsonl")
     from tests.tools import big_configs
-    out = big_configs.run(name, 1.0, steps=4, warm=2)
+    out = big_configs.run(name, 1.0, steps=10, warm=4)   # 15 substeps: the scenes start in contact and particles cross the colliders
     assert out["particles"] == particles
     assert out["tombstoned"] == 0 and out["min_det_F_sampled"] > 0.3
     assert out["collider_layers"] > 1 and out["particles_deformed"] > 0      # the run is in contact, not free fall

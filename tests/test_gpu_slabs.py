@@ -16,7 +16,7 @@ def _gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("scene,steps", [("jelly", 30), ("jelly_shear", 30), ("jelly_rebalance", 30), ("split_layers", 25), ("sand", 40)])
+@pytest.mark.parametrize("scene,steps", [("jelly", 30), ("jelly_shear", 30), ("jelly_rebalance", 30), ("split_layers", 25), ("sand", 40), ("jelly_adaptive", 40), ("energy_error", 6)])
 def test_slabs_match_single_gpu(scene, steps):
     n = _gpus()
     if n < 2:
