@@ -107,6 +107,15 @@ int32_t svb_available_devices(char* out, size_t cap);
 int32_t svb_create(const SvbConsts* consts, const SvbParticles* particles, double time, int32_t device,
                    SvbHandle** out);
 void svb_destroy(SvbHandle* h);
+/* The same, over `n_dev` GPUs of the box behind ONE handle, for a caller that drives the back end from a single thread like
+ * core/src/compute_thread.rs:100-163 does (`const int* devices, int n_dev`).  The state is cut into slabs along x
+ * inside the library (by particle count, on grid-block planes); svb_upload / svb_set_topology / svb_set_keyframes / svb_advance
+ * / svb_download / svb_destroy and the scalar getters work on the returned handle exactly as on a single-device one (download
+ * re-assembles original particle order); every call fans out to one slab rank per device for its duration.  The ranks exchange
+ * halo sums, migrating particles and the adaptive-step limits through each other's HBM (cudaDeviceEnablePeerAccess: the devices
+ * must be peers).  The introspection entry points below (grid, binning, snapshot) are single-device only. */
+int32_t svb_create_multi(const SvbConsts* consts, const SvbParticles* particles, double time, const int32_t* devices,
+                         int32_t n_dev, SvbHandle** out);
 /* Replaces the resident particle state of an existing handle (H2D of a new IoState) and restarts its clock,
  * step history and error words; constants, collider input and — on slab ranks — the communicator and the
  * peer mailboxes are kept.  The compute thread calls `from_io_state` whenever a frame is (re)loaded

@@ -69,6 +69,8 @@ def load():
     L.svb_available_devices.argtypes = [C.c_char_p, C.c_size_t]
     L.svb_create.restype = C.c_int32
     L.svb_create.argtypes = [C.POINTER(cs.SvbConsts), C.POINTER(cs.SvbParticles), C.c_double, C.c_int32, C.POINTER(vp)]
+    L.svb_create_multi.restype = C.c_int32
+    L.svb_create_multi.argtypes = [C.POINTER(cs.SvbConsts), C.POINTER(cs.SvbParticles), C.c_double, C.POINTER(C.c_int32), C.c_int32, C.POINTER(vp)]
     L.svb_destroy.restype = None
     L.svb_destroy.argtypes = [vp]
     L.svb_upload.restype = C.c_int32

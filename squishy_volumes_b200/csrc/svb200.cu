@@ -52,7 +52,9 @@ const char* const kStageNames[ST_COUNT] = {"mesh_interpolate", "collide_force_bi
 
 }  // namespace
 
+struct SvbMulti;
 struct SvbHandle {
+  SvbMulti* multi = nullptr;   // set on the front handle of svb_create_multi: every call fans out to the per-device slab ranks
   int device = 0;
   cudaStream_t stream = nullptr;
   SvbConsts consts{};
@@ -113,6 +115,7 @@ struct SvbHandle {
   uint64_t halo_tiles_sent = 0, migrated_out = 0;
   // peer-memory exchange (CUDA IPC mailboxes; the NCCL path above stays as the fallback when IPC is unavailable)
   bool p2p = false;
+  bool ipc_mapped = false;              // peer_mailbox entries are CUDA-IPC mappings (closed on destroy); false: plain peer pointers of this process
   DevBuf mig_list;                      // slots k_g2p found leaving the slab (left list, right list)
   DevBuf mailbox;                       // this rank's mailbox: SlabHeader | halo in (left, right) | rows in (left, right)
   void* peer_mailbox[16] = {};          // every rank's mailbox mapped into this process (null for self)
@@ -472,6 +475,16 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next,
 
 int halo_exchange(SvbHandle* h);
 int migrate(SvbHandle* h);
+// svb_multi.inl: a handle over several devices, its calls fan out to one slab rank per device
+int multi_upload(SvbHandle* front, const SvbParticles* p, double time);
+int multi_download(SvbHandle* front, SvbParticles* out);
+int multi_advance(SvbHandle* front, double target_time, float max_time_step, int32_t adaptive, const volatile int32_t* cancel, void (*progress)(void*, size_t), void* user);
+int multi_set_topology(SvbHandle* front, uint32_t n_colliders, const uint32_t* num_vertices, const uint32_t* num_triangles, const uint32_t* triangles);
+int multi_set_keyframes(SvbHandle* front, uint64_t frame, const SvbKeyframe* a, const SvbKeyframe* b);
+void multi_set_option(SvbHandle* front, const char* name, double value);
+void multi_destroy(SvbHandle* front);
+int mailbox_alloc(SvbHandle* h, size_t n_max);
+int mailbox_finish(SvbHandle* h);
 int substep_slab(SvbHandle* h, const StepInputs& in);
 int substep_slab_p2p(SvbHandle* h, const StepInputs& in);
 int setup_peer_mailboxes(SvbHandle* h);
@@ -958,6 +971,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
 
 void svb_destroy(SvbHandle* h) {
   if (!h) return;
+  if (h->multi) return multi_destroy(h);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& f : h->fs)
@@ -975,7 +989,7 @@ void svb_destroy(SvbHandle* h) {
     if (L.ev) cudaEventDestroy(L.ev);
   }
   for (void* pm : h->peer_mailbox)
-    if (pm) cudaIpcCloseMemHandle(pm);
+    if (pm && h->ipc_mapped) cudaIpcCloseMemHandle(pm);
   if (h->comm) ncclCommDestroy(h->comm);
   if (h->h_counts) cudaFreeHost(h->h_counts);
   for (auto& e : h->ev)
@@ -988,6 +1002,7 @@ void svb_destroy(SvbHandle* h) {
 
 int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
   if (!h || !p) return SVB_BAD_ARGUMENT;
+  if (h->multi) return multi_upload(h, p, time);
   if (p->n > 0xfffffff0ull) return SVB_BAD_ARGUMENT;
   if (int rc = set_device(h)) return rc;
   CK(cudaStreamSynchronize(h->stream));
@@ -1025,6 +1040,7 @@ int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
 
 int32_t svb_set_topology(SvbHandle* h, uint32_t n_colliders, const uint32_t* num_vertices, const uint32_t* num_triangles, const uint32_t* triangles) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return multi_set_topology(h, n_colliders, num_vertices, num_triangles, triangles);
   if (n_colliders > 16) return fail(h, SVB_TOO_MANY_COLLIDERS, "too many colliders: %u (at most 16)", n_colliders);
   if (int rc = set_device(h)) return rc;
   const std::string err = h->topo.build(n_colliders, num_vertices, num_triangles, triangles);
@@ -1052,6 +1068,7 @@ int32_t svb_set_topology(SvbHandle* h, uint32_t n_colliders, const uint32_t* num
 
 int32_t svb_set_keyframes(SvbHandle* h, uint64_t frame, const SvbKeyframe* a, const SvbKeyframe* b) {
   if (!h || !a) return SVB_BAD_ARGUMENT;
+  if (h->multi) return multi_set_keyframes(h, frame, a, b);
   if (int rc = set_device(h)) return rc;
   const auto& T = h->topo;
   const uint32_t nv = T.n_vertices, nt = T.n_triangles, n = h->n_global ? h->n_global : h->n;  // goal arrays are in (global) original order
@@ -1120,6 +1137,7 @@ int32_t svb_set_keyframes(SvbHandle* h, uint64_t frame, const SvbKeyframe* a, co
 
 int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32_t adaptive_time_steps, const volatile int32_t* cancel, void (*progress)(void*, size_t), void* user) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return multi_advance(h, target_time, max_time_step, adaptive_time_steps, cancel, progress, user);
   if (!h->have_keyframes) return fail(h, SVB_INPUT_MISSING, "At this point, interpolated input should be ready (svb_set_keyframes not called)");
   if (int rc = set_device(h)) return rc;
   const bool adaptive = adaptive_time_steps != 0;
@@ -1242,6 +1260,7 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
 
 int32_t svb_download(SvbHandle* h, SvbParticles* out) {
   if (!h || !out) return SVB_BAD_ARGUMENT;
+  if (h->multi) return multi_download(h, out);
   // slab ranks hold rows of the GLOBAL particle order (and F_GONE rows): the original-order scatter below would leave its buffers
   if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_download needs the whole particle set on one device: use svb_download_resident on a slab rank");
   if (int rc = set_device(h)) return rc;
@@ -1307,6 +1326,7 @@ static int build_node_masks(SvbHandle* h, uint32_t* total) {
 // zero-mass nodes touched one substep earlier, SURVEY.md §8g.9 — those are not emitted).
 int64_t svb_grid_count(SvbHandle* h) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "single-device introspection entry point called on a multi-device handle");
   if (int rc = set_device(h)) return rc;
   uint32_t total = 0;
   if (int rc = build_node_masks(h, &total)) return rc;
@@ -1315,6 +1335,7 @@ int64_t svb_grid_count(SvbHandle* h) {
 
 int32_t svb_download_grid(SvbHandle* h, SvbGrid* out) {
   if (!h || !out) return SVB_BAD_ARGUMENT;
+  if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "single-device introspection entry point called on a multi-device handle");
   if (int rc = set_device(h)) return rc;
   uint32_t total = 0;
   if (int rc = build_node_masks(h, &total)) return rc;
@@ -1351,6 +1372,7 @@ uint64_t svb_particle_count(const SvbHandle* h) { return h ? h->n : 0; }
 
 int32_t svb_binning(SvbHandle* h, uint32_t* sort_map, int32_t* cells) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "single-device introspection entry point called on a multi-device handle");
   if (int rc = set_device(h)) return rc;
   const uint32_t n = h->n;
   if (!n) return 0;
@@ -1370,6 +1392,7 @@ int64_t svb_active_block_count(SvbHandle* h) { return h ? (h->have_grid ? (int64
 
 int32_t svb_active_blocks(SvbHandle* h, int32_t* block_ids, uint32_t* collider_bits) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "single-device introspection entry point called on a multi-device handle");
   if (int rc = set_device(h)) return rc;
   const uint32_t na = h->have_grid ? h->n_tiles : 0;
   if (!na) return 0;
@@ -1394,16 +1417,19 @@ int32_t svb_stage_times(SvbHandle* h, const char** names, float* ms, int32_t cap
   return ST_COUNT;
 }
 void svb_enable_stage_timing(SvbHandle* h, int32_t on) {
+  if (h && h->multi) return;
   if (h) h->timing = on != 0;
 }
 void svb_set_option(SvbHandle* h, const char* name, double value) {
   if (!h || !name) return;
+  if (h->multi) return multi_set_option(h, name, value);
   if (!std::strcmp(name, "store_grid")) h->store_grid = value != 0.0;  // CpuRunParameters::store_grid
   if (!std::strcmp(name, "global_particles")) h->n_global = (uint32_t)value;  // slab ranks: size of the original-order keyframe arrays
 }
 
 int32_t svb_snapshot(SvbHandle* h) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points");
   if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points (a slab rank's row count lives on the device)");
   if (int rc = set_device(h)) return rc;
   CK(h->snap_p.ensure(h->cap * NFIELDS * 4));
@@ -1420,6 +1446,7 @@ int32_t svb_snapshot(SvbHandle* h) {
 }
 int32_t svb_restore(SvbHandle* h) {
   if (!h) return SVB_BAD_ARGUMENT;
+  if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points");
   if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points (a slab rank's row count lives on the device)");
   if (!h->have_snapshot) return fail(h, SVB_BAD_ARGUMENT, "svb_restore without svb_snapshot");
   if (int rc = set_device(h)) return rc;
@@ -1583,6 +1610,34 @@ int migrate(SvbHandle* h) {
 }
 
 
+// this rank's mailbox: header | halo entries from the left | from the right | migrating rows from the left | from the right; sized
+// from the largest slab so that every rank's mailbox has the same layout
+int mailbox_alloc(SvbHandle* h, size_t n_max) {
+  h->mb_halo_cap = n_max / 128 + 4096;
+  h->mb_mig_cap = n_max / 4 + 65536;   // room for the columns a rebalance hands over at once, not just the per-substep trickle
+  size_t off = 4096;  // header
+  for (int k = 0; k < 2; ++k) { h->mb_halo_off[k] = off; off += h->mb_halo_cap * sizeof(HaloEntry); }
+  for (int k = 0; k < 2; ++k) { h->mb_mig_off[k] = off; off += ((h->mb_mig_cap * MIG_WORDS * 4 + 255) & ~(size_t)255); }
+  CK(h->mailbox.ensure(off));
+  CK(cudaMemsetAsync(h->mailbox.p, 0, 4096, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+// once every peer's mailbox is reachable (h->peer_mailbox): device-side scratch of the exchange kernels and the row count
+int mailbox_finish(SvbHandle* h) {
+  cudaStream_t s = h->stream;
+  uint32_t* d = h->comm_counts.as<uint32_t>();
+  h->p2p_local = d + 32;   // comm_counts: words 0..15 counts, 16.. slab table, 32..47 scratch of the sending kernels, 48 row count
+  h->n_dev = d + 48;
+  CK(cudaMemsetAsync(h->p2p_local, 0, 16 * 4, s));
+  CK(cudaMemcpyAsync(h->n_dev, &h->n, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(h->n_dev + 1, 0, 4, s));   // blocks-done tick of the rebalance receive
+  CK(cudaStreamSynchronize(s));
+  h->slab_seq = 0;
+  h->dt_exchanges = 0;
+  return 0;
+}
+
 // Peer-memory mailboxes: every rank allocates one buffer, shares it with CUDA IPC (handles travel through an NCCL
 // all-gather), and maps every other rank's.  All ranks agree (all-reduce) on whether the mapping worked; if not,
 // the NCCL send/recv path above carries the exchanges.  SVB_SLAB_NCCL=1 forces that path.
@@ -1598,13 +1653,7 @@ int setup_peer_mailboxes(SvbHandle* h) {
   CK(cudaMemcpyAsync(h->h_counts, d, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   const size_t n_max = h->h_counts[0];
-  h->mb_halo_cap = n_max / 128 + 4096;
-  h->mb_mig_cap = n_max / 4 + 65536;   // room for the columns a rebalance hands over at once, not just the per-substep trickle
-  size_t off = 4096;  // header
-  for (int k = 0; k < 2; ++k) { h->mb_halo_off[k] = off; off += h->mb_halo_cap * sizeof(HaloEntry); }
-  for (int k = 0; k < 2; ++k) { h->mb_mig_off[k] = off; off += ((h->mb_mig_cap * MIG_WORDS * 4 + 255) & ~(size_t)255); }
-  CK(h->mailbox.ensure(off));
-  CK(cudaMemsetAsync(h->mailbox.p, 0, 4096, s));
+  if (int rc = mailbox_alloc(h, n_max)) return rc;
   DevBuf handles;
   CK(handles.ensure((size_t)h->n_ranks * sizeof(cudaIpcMemHandle_t)));
   cudaIpcMemHandle_t mine;
@@ -1628,15 +1677,9 @@ int setup_peer_mailboxes(SvbHandle* h) {
   CK(cudaStreamSynchronize(s));
   handles.release();
   h->p2p = h->h_counts[0] != 0;
+  h->ipc_mapped = h->p2p;
   if (!h->p2p) return 0;
-  h->p2p_local = d + 32;   // comm_counts holds 64 + 8 * n_ranks bytes... the scratch needs 12 words: see svb_comm_init
-  h->n_dev = d + 48;
-  CK(cudaMemsetAsync(h->p2p_local, 0, 16 * 4, s));
-  CK(cudaMemcpyAsync(h->n_dev, &h->n, 4, cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(h->n_dev + 1, 0, 4, s));   // blocks-done tick of the rebalance receive
-  CK(cudaStreamSynchronize(s));
-  h->slab_seq = 0;
-  return 0;
+  return mailbox_finish(h);
 }
 
 }  // namespace
@@ -1844,3 +1887,5 @@ int32_t svb_download_resident(SvbHandle* h, SvbParticles* out, uint64_t* origina
 }
 
 }  // extern "C"
+
+#include "svb_multi.inl"

@@ -67,6 +67,31 @@ class B200State:
             raise FatalError(rc, L.svb_last_error(h).decode())
         return self
 
+    @classmethod
+    def from_io_state_multi(cls, io_state: IoState, frame_input: FrameInput, devices) -> "B200State":
+        """One state over several GPUs of the box, driven from this single thread like the reference's compute thread drives a
+        back end (core/src/compute_thread.rs:100-163): `svb_create_multi` cuts the particles into slabs along x inside the
+        library, one slab rank per device; every other call of this class works unchanged (the introspection calls —
+        `grid`, `binning`, `active_blocks`, `snapshot` — are single-device only)."""
+        L = abi.load()
+        p = io_state.particles.normalized()
+        ps = cs.particles_struct(p)
+        consts = cs.consts_struct(frame_input.consts)
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = L.svb_create_multi(C.byref(consts), C.byref(ps), C.c_double(io_state.time), devs, len(devices), C.byref(h))
+        if rc != 0:
+            msg = L.svb_last_error(h).decode() if h else "svb_create_multi failed (no CUDA device?)"
+            if h:
+                L.svb_destroy(h)
+            raise FatalError(rc, msg)
+        self = cls(h, p.n, frame_input)
+        nv, nt, flat = cs.topology_arrays(frame_input)
+        rc = L.svb_set_topology(h, len(frame_input.colliders), cs.uptr(nv), cs.uptr(nt), cs.uptr(flat))
+        if rc != 0:
+            raise FatalError(rc, L.svb_last_error(h).decode())
+        return self
+
     def upload(self, io_state: IoState) -> None:
         """`from_io_state` into this (session-lived) handle: H2D of a new state, clock and step history restart;
         constants, colliders and device allocations are kept (include/svb200.h: svb_upload)."""
