@@ -354,7 +354,9 @@ def main():
         # the timed pass lasts tens of milliseconds, one nvidia-smi query a good part of a second: keep the same load on the GPU
         # (single GPU: the timed pass itself, restored from the snapshot) until the sampler has seen it a few times
         extra, t_stop = 0, time.perf_counter() + 6.0
-        while len(clocks.samples) < 3 and (time.perf_counter() < t_stop if world == 1 else extra < 10):
+        # (slab ranks cannot rewind: their extra passes must leave room for the stage pass inside the one loaded frame, 1 s at fps = 1)
+        span = (steps + 1) * dt
+        while len(clocks.samples) < 3 and (time.perf_counter() < t_stop if world == 1 else (extra < 10 and state.time + 2.2 * span < 0.95)):
             if world == 1:
                 inner.restore()
             state.advance(None, fi, run_params(state, steps))

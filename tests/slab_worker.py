@@ -142,7 +142,7 @@ def main():
         rep = parity.compare_states(IoState(0.0, got), ref, rtol=parity.RTOL_RUN, h=h)
         moved = int(np.count_nonzero(slabs.slab_of(sc.io_state.particles.positions, h, st.plan) != owner))
         print(f"[{name}] world={world} n={sc.n} substeps={steps} migrated={moved} per-rank={[len(g[0]) for g in gathered]} max err "
-              + ", ".join(f"{k}={v[0]:.2e}/{v[1]:.2e}" for k, v in rep.items()), flush=True)
+              + ", ".join(f"{k}={v[0]:.2e}/{v[1]:.2e}" for k, v in rep.items() if isinstance(v, tuple)), flush=True)
         import oracle.oracle as orc
         o = orc.OracleState.from_io_state(sc.io_state, sc.frame_input)
         oref, _ = o.produce_next_state(None, sc.frame_input, params)
@@ -172,4 +172,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        print(f"[rank {os.environ.get('RANK')}] FAILED:\n" + traceback.format_exc(), flush=True)   # on stdout: torchrun's own summary drowns stderr
+        os._exit(1)
