@@ -166,8 +166,16 @@ int32_t svb_active_blocks(SvbHandle* h, int32_t* block_ids /* n*3 */, uint32_t* 
 int32_t svb_stage_times(SvbHandle* h, const char** names, float* ms, int32_t cap);
 void svb_enable_stage_timing(SvbHandle* h, int32_t on);
 /* Options by name: "store_grid" (CpuRunParameters::store_grid: exact contributor masks for svb_download_grid),
- * "global_particles" (slab ranks: size of the original-order keyframe arrays). */
+ * "global_particles" (slab ranks: size of the original-order keyframe arrays), "murmur_table_hash" (hash the tile table with the
+ * reference's murmur node key instead of the 64-bit mixer; results do not depend on it). */
 void svb_set_option(SvbHandle* h, const char* name, double value);
+
+/* The reference's (dormant) `node_ids_to_murmur` stage, gpu/src/node_ids_to_murmur/mod.rs with the key of gpu/src/util.rs:79-100:
+ * murmur3_x86_32 over the three ordered-u32 (x ^ 0x8000_0000) little-endian coordinates of every node id, seed 0
+ * (`hashes_node_ids`) and seed = collider bits (`hashes_node_ids_and_bits`); either output may be NULL.  The same key hashes the
+ * tile table when the option "murmur_table_hash" is on (svb_set_option). */
+int32_t svb_node_ids_to_murmur(int32_t device, const int32_t* node_ids /* n*3 */, const uint32_t* collider_bits /* n or NULL */, uint64_t n,
+                               uint32_t* hashes_node_ids, uint32_t* hashes_node_ids_and_bits);
 
 /* ---- device-resident entry points (bench: inputs already in HBM) ---- */
 /* Copies the current device state into a device-side snapshot / restores it (no host traffic). */

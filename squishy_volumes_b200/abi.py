@@ -113,6 +113,8 @@ def load():
     L.svb_enable_stage_timing.argtypes = [vp, C.c_int32]
     L.svb_set_option.restype = None
     L.svb_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.svb_node_ids_to_murmur.restype = C.c_int32
+    L.svb_node_ids_to_murmur.argtypes = [C.c_int32, cs.c_i32p, cs.c_u32p, C.c_uint64, cs.c_u32p, cs.c_u32p]
     L.svb_snapshot.restype = C.c_int32
     L.svb_snapshot.argtypes = [vp]
     L.svb_restore.restype = C.c_int32

@@ -57,6 +57,8 @@ struct SvbHandle {
   SvbMulti* multi = nullptr;   // set on the front handle of svb_create_multi: every call fans out to the per-device slab ranks
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_b = nullptr;      // slab ranks: the exchange senders run here, next to P2G / G2P on `stream`
+  cudaEvent_t ev_b_start = nullptr, ev_b_end = nullptr;
   SvbConsts consts{};
   SimConsts K{};
   uint32_t n = 0;
@@ -89,6 +91,7 @@ struct SvbHandle {
   uint32_t n_ptiles = 0, n_live = 0, n_tiles = 0;
   bool have_grid = false;
   bool store_grid = false, masks_valid = false;
+  bool murmur_hash = false;   // option "murmur_table_hash"
 
   // collider input
   svbh::HostTopology topo;
@@ -234,12 +237,18 @@ int set_device(SvbHandle* h) {
   return 0;
 }
 
+// everything queued for this handle, the exchange senders on the second stream included
+cudaError_t sync_streams(SvbHandle* h) {
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && h->stream_b) e = cudaStreamSynchronize(h->stream_b);
+  return e;
+}
 StepScalars* scalars_of(SvbHandle* h, int which) { return h->scalars.as<StepScalars>() + which; }
 StepScalars* cur_scalars(SvbHandle* h) { return scalars_of(h, h->s_cur); }
 
 TileTable tile_table(SvbHandle* h, int which) {
   auto& f = h->fs[which];
-  return TileTable{f.table_slots.as<ulonglong2>(), h->table_mask, f.tile_key.as<unsigned long long>(), f.tile_slot.as<uint32_t>(), (uint32_t)h->tile_cap};
+  return TileTable{f.table_slots.as<ulonglong2>(), h->table_mask, f.tile_key.as<unsigned long long>(), f.tile_slot.as<uint32_t>(), (uint32_t)h->tile_cap, h->murmur_hash ? 1u : 0u};
 }
 TileTable tile_table(SvbHandle* h) { return tile_table(h, h->s_cur); }
 BinArrays bin_arrays(SvbHandle* h, int which) {
@@ -350,11 +359,12 @@ int enqueue_rebin(SvbHandle* h, bool prepare_next) {
 // the tiles a P2G / G2P launch works through: all particle tiles, or (peer-memory slab ranks) the boundary / interior list of k_offsets
 WorkList work_all(SvbHandle* h, int counter, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{nullptr, &S->n_ptiles, &S->work_counter[counter], tail};
+  return WorkList{nullptr, 0u, &S->n_ptiles, &S->work_counter[counter], nullptr, tail};
 }
-WorkList work_part(SvbHandle* h, int which, int counter, int tail) {
+// boundary tiles first, then the interior ones; `phase` 0 = P2G, 1 = G2P (work cursor and boundary-done counter of the scalars)
+WorkList work_ordered(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{h->work_list.as<uint32_t>() + (size_t)which * h->tile_cap, &S->n_work[which], &S->work_counter[counter], tail};
+  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_work, &S->work_counter[phase], &S->boundary_done[phase], tail};
 }
 
 int enqueue_p2g(SvbHandle* h, const StepInputs& in, const WorkList& W, uint32_t grid_cap = 148 * P2G_CTAS_PER_SM) {
@@ -674,7 +684,7 @@ int process_front_p2p(SvbHandle* h) {
     return fail(h, SVB_COMM_ERROR, r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
   if (r.sticky) {  // the previous substep failed somewhere: this one and everything queued behind it were no-ops on every rank
     h->status |= (r.sticky | r.accum) & 0xffffu;
-    CK(cudaStreamSynchronize(s));
+    CK(sync_streams(h));
     const uint64_t noops = h->lag_issued - h->lag_done;
     if (noops & 1) { h->cur ^= 1; h->s_cur ^= 1; }   // each queued G2P swapped the buffers and each front the set: undo (they wrote nothing)
     h->binned_ahead = L.was_ahead;
@@ -697,7 +707,7 @@ int process_front_p2p(SvbHandle* h) {
   h->status |= (r.status | r.accum) & 0xffffu;
   ++h->lag_done;
   if (((size_t)r.n_tiles + h->halo_margin) * 3 / 2 > h->tile_cap) {  // grow ahead of need: an overflow cannot be redone once messages are out
-    CK(cudaStreamSynchronize(s));   // (every substep queued so far completes first: they are real ones)
+    CK(sync_streams(h));   // (every substep queued so far completes first: they are real ones)
     while (h->lag_done < h->lag_issued) {
       const int rc = process_front_p2p(h);
       if (rc) return rc;
@@ -707,12 +717,15 @@ int process_front_p2p(SvbHandle* h) {
   return 0;
 }
 
-// one fixed-dt substep of a slab rank over peer memory: nothing on the data path returns to the host, and the exchanges hide
-// behind the interior tiles' work:
-//   P2G(boundary tiles) -> halo send -> P2G(interior) -> halo receive -> G2P(boundary) -> migration send -> G2P(interior) -> migration receive
-// The whole substep is queued, then the host looks at the front half of an EARLIER substep (up to two stay in flight).
+// one substep of a slab rank over peer memory: nothing on the data path returns to the host, and the exchanges hide behind the
+// interior tiles' work.  P2G and G2P take the boundary tiles first; the two SENDING kernels run on a second stream next to them,
+// wait (on the device) for the last boundary tile and ship the halo columns / the leavers while the interior is still in progress:
+//   main stream:   front | rebin | P2G [boundary, interior] | halo receive | (meld) G2P [boundary, interior] | migration receive
+//   second stream:         ......  halo send (after the boundary tiles)  ......  migration send (after the boundary tiles)
+// so both receives find the neighbour's message already there.  The whole substep is queued, then the host looks at the front half
+// of an EARLIER substep (up to two stay in flight).
 int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
-  cudaStream_t s = h->stream;
+  cudaStream_t s = h->stream, sb = h->stream_b;
   const float dt = in.dt;
   SvbHandle::FrontLag& L = h->lag[h->lag_issued % 4];
   L.time_before = h->time; L.substeps_before = h->substeps; L.was_ahead = h->binned_ahead; L.seq_before = h->slab_seq; L.dtx_before = h->dt_exchanges;
@@ -720,20 +733,20 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   const bool bin_next = !in.has_mesh;
   h->h_scalars = L.host;
   h->ev_front = L.ev;
+  CK(cudaStreamWaitEvent(s, h->ev_b_end, 0));   // the previous substep's senders are done with the scalars / buffers this one recycles
   if (int rc = enqueue_front(h, in, /*redo=*/false)) return rc;
   if (int rc = enqueue_rebin(h, bin_next)) return rc;
+  CK(cudaEventRecord(h->ev_b_start, s));
+  CK(cudaStreamWaitEvent(sb, h->ev_b_start, 0));
   StepScalars* S = cur_scalars(h);
   const TileTable T = tile_table(h);
   SlabHeader* my_hdr = h->mailbox.as<SlabHeader>();
   unsigned char* my_mb = h->mailbox.as<unsigned char>();
   const bool has[2] = {h->rank > 0, h->rank + 1 < h->n_ranks};
+  const bool concurrent = !h->timing;   // (the instrumented pass times the stages one after the other on the main stream)
+  // ---- second stream: the halo sender, gated on the device by P2G's boundary tiles
   stage_begin(h, ST_P2G);
-  if (int rc = enqueue_p2g(h, in, work_part(h, 0, 0, 0), 148 * 2)) return rc;
-  stage_end(h);
-  stage_begin(h, ST_HALO);
-  if (has[0] || has[1]) {
-    // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right; a message lands in the
-    // neighbour's slot for "from the right" (when I am its right neighbour) / "from the left"
+  if (concurrent && (has[0] || has[1])) {
     HaloPeers hp{};
     for (int side = 0; side < 2; ++side)
       if (has[side]) {
@@ -744,15 +757,29 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
         hp.count[side] = &ph->halo_count[their];
         hp.seq[side] = &ph->halo_seq[their];
       }
-    k_halo_send2<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local);
+    k_halo_send2<<<32, 256, 0, sb>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local, &S->boundary_done[0], &S->n_work[0]);
     LAUNCH_CHECK();
   }
-  stage_end(h);
-  stage_begin(h, ST_P2G);
-  if (int rc = enqueue_p2g(h, in, work_part(h, 1, 2, 0))) return rc;
+  if (int rc = enqueue_p2g(h, in, work_ordered(h, 0, 0))) return rc;
   stage_end(h);
   stage_begin(h, ST_HALO);
   if (has[0] || has[1]) {
+    if (!concurrent) {
+      // my first column goes left (the left rank holds it as halo), my halo column (== hi) goes right; a message lands in the
+      // neighbour's slot for "from the right" (when I am its right neighbour) / "from the left"
+      HaloPeers hp{};
+      for (int side = 0; side < 2; ++side)
+        if (has[side]) {
+          unsigned char* peer = static_cast<unsigned char*>(h->peer_mailbox[h->rank + (side ? 1 : -1)]);
+          SlabHeader* ph = reinterpret_cast<SlabHeader*>(peer);
+          const int their = side ? 0 : 1;
+          hp.entries[side] = reinterpret_cast<HaloEntry*>(peer + h->mb_halo_off[their]);
+          hp.count[side] = &ph->halo_count[their];
+          hp.seq[side] = &ph->halo_seq[their];
+        }
+      k_halo_send2<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local, nullptr, nullptr);
+      LAUNCH_CHECK();
+    }
     k_halo_recv2<<<148 * 2, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(), h->grid.as<float4>(), reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[0]),
                                         reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[1]), my_hdr, has[0] ? 1 : 0, has[1] ? 1 : 0, seq);
     LAUNCH_CHECK();
@@ -767,21 +794,6 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   BinNext bn{};
   if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
   DtState* D = h->dt_state.as<DtState>();
-  if (!in.adaptive) {
-    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 0, 1, 1), src_buf, &cut, 148 * 2)) return rc;
-  } else {
-    // adaptive steps: G2P with the reductions of LimitTimeStepBeforeIntegrate over all tiles, the global limits (all ranks), then
-    // the advance — which notes the leavers and bins the rest ahead — as its own pass (the step is only known now)
-    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/false, dt, false, work_all(h, 1, 1), src_buf)) return rc;
-    k_dt_integrate<<<1, 1, 0, s>>>(D, S, dt_peers(h));
-    LAUNCH_CHECK();
-    const uint32_t rows = (uint32_t)h->cap;
-    if (bin_next) k_advance<true><<<blocks_for(rows, 256), 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, h->K, rows, D, bn, cut);
-    else k_advance<false><<<blocks_for(rows, 256), 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, h->K, rows, D, bn, cut);
-    LAUNCH_CHECK();
-  }
-  stage_end(h);
-  stage_begin(h, ST_MIGRATE);
   SlabPeers peers{};
   peers.n_ranks = h->n_ranks;
   for (int side = 0; side < 2; ++side)
@@ -799,16 +811,33 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       peers.err_seq[r] = &ph->err_seq[h->rank];
       peers.err_val[r] = &ph->err_val[h->rank];
     }
-  // (the rows G2P wrote live in the OTHER buffer until `cur` is swapped below)
-  k_migrate_send_list<<<148, 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0);
-  LAUNCH_CHECK();
-  stage_end(h);
-  stage_begin(h, ST_G2P);
-  if (!in.adaptive)
-    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_part(h, 1, 3, 0), src_buf, &cut)) return rc;
+  // (the rows G2P writes live in the OTHER buffer until `cur` is swapped below)
+  const bool send_beside_g2p = concurrent && !in.adaptive;
+  if (send_beside_g2p) {   // second stream: the migration sender, gated on the device by G2P's boundary tiles
+    k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0]);
+    LAUNCH_CHECK();
+  }
+  if (!in.adaptive) {
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/true, dt, bin_next, work_ordered(h, 1, 1), src_buf, &cut)) return rc;
+  } else {
+    // adaptive steps: G2P with the reductions of LimitTimeStepBeforeIntegrate over all tiles, the global limits (all ranks), then
+    // the advance — which notes the leavers and bins the rest ahead — as its own pass (the step is only known now)
+    if (int rc = enqueue_g2p(h, in.has_mesh, /*fuse=*/false, dt, false, work_ordered(h, 1, 1), src_buf)) return rc;
+    k_dt_integrate<<<1, 1, 0, s>>>(D, S, dt_peers(h));
+    LAUNCH_CHECK();
+    const uint32_t rows = (uint32_t)h->cap;
+    if (bin_next) k_advance<true><<<blocks_for(rows, 256), 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, h->K, rows, D, bn, cut);
+    else k_advance<false><<<blocks_for(rows, 256), 256, 0, s>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, h->K, rows, D, bn, cut);
+    LAUNCH_CHECK();
+  }
   h->cur ^= 1;  // the binned buffer written by G2P is the current one from here on
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
+  if (!send_beside_g2p) {
+    k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, nullptr, nullptr);
+    LAUNCH_CHECK();
+  }
+  CK(cudaEventRecord(h->ev_b_end, sb));
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0, h->K, bn, bin_next ? 1 : 0);
   LAUNCH_CHECK();
@@ -879,7 +908,7 @@ int load_particles(SvbHandle* h, const SvbParticles* p) {
 int read_status(SvbHandle* h) {
   StepScalars* S = cur_scalars(h);
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(sync_streams(h));
   h->status |= (h->h_scalars->status | h->h_scalars->sticky | h->h_scalars->sticky_new | h->h_scalars->accum) & 0xffffu;
   if ((h->h_scalars->sticky_new & 0xffffu) && !h->adaptive.has_override) rollback_failed_substep(h);   // fixed dt: the failing substep was the last one queued
   return 0;
@@ -928,6 +957,14 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   h->time = time;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int lo_prio = 0, hi_prio = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CK(cudaStreamCreateWithPriority(&h->stream_b, cudaStreamNonBlocking, hi_prio));   // its few blocks should get an SM slot as soon as they are launched
+    CK(cudaEventCreateWithFlags(&h->ev_b_start, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_b_end, cudaEventDisableTiming));
+    CK(cudaEventRecord(h->ev_b_end, h->stream_b));
+  }
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
   for (auto& e : h->ev_adv) CK(cudaEventCreate(&e));
   for (auto& L : h->lag) {
@@ -996,6 +1033,9 @@ void svb_destroy(SvbHandle* h) {
     if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_adv)
     if (e) cudaEventDestroy(e);
+  if (h->stream_b) { cudaStreamSynchronize(h->stream_b); cudaStreamDestroy(h->stream_b); }
+  if (h->ev_b_start) cudaEventDestroy(h->ev_b_start);
+  if (h->ev_b_end) cudaEventDestroy(h->ev_b_end);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1425,6 +1465,34 @@ void svb_set_option(SvbHandle* h, const char* name, double value) {
   if (h->multi) return multi_set_option(h, name, value);
   if (!std::strcmp(name, "store_grid")) h->store_grid = value != 0.0;  // CpuRunParameters::store_grid
   if (!std::strcmp(name, "global_particles")) h->n_global = (uint32_t)value;  // slab ranks: size of the original-order keyframe arrays
+  if (!std::strcmp(name, "murmur_table_hash") && (value != 0.0) != h->murmur_hash) {
+    // another hash function sends every key to another slot: start both front sets from empty tables
+    h->murmur_hash = value != 0.0;
+    for (auto& f : h->fs) f.fresh = true;
+    h->binned_ahead = false;
+  }
+}
+
+int32_t svb_node_ids_to_murmur(int32_t device, const int32_t* node_ids, const uint32_t* collider_bits, uint64_t n, uint32_t* hashes_node_ids, uint32_t* hashes_node_ids_and_bits) {
+  if (!node_ids || n > 0x7fffffffull) return SVB_BAD_ARGUMENT;
+  if (!n) return 0;
+  SvbHandle* h = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return SVB_CUDA_ERROR;  // no CPU fallback
+  if (device < 0 || device >= count) return SVB_BAD_ARGUMENT;
+  CK(cudaSetDevice(device));
+  DevBuf ids, bits, out;
+  CK(ids.ensure(n * 12));
+  CK(bits.ensure(n * 4));
+  CK(out.ensure(n * 8));
+  CK(cudaMemcpy(ids.p, node_ids, n * 12, cudaMemcpyHostToDevice));
+  if (collider_bits) CK(cudaMemcpy(bits.p, collider_bits, n * 4, cudaMemcpyHostToDevice));
+  k_node_ids_to_murmur<<<blocks_for(n, 256), 256>>>(ids.as<int32_t>(), collider_bits ? bits.as<uint32_t>() : nullptr, (uint32_t)n, out.as<uint32_t>(), out.as<uint32_t>() + n);
+  CK(cudaGetLastError());
+  if (hashes_node_ids) CK(cudaMemcpy(hashes_node_ids, out.p, n * 4, cudaMemcpyDeviceToHost));
+  if (hashes_node_ids_and_bits) CK(cudaMemcpy(hashes_node_ids_and_bits, out.as<uint32_t>() + n, n * 4, cudaMemcpyDeviceToHost));
+  ids.release(); bits.release(); out.release();
+  return 0;
 }
 
 int32_t svb_snapshot(SvbHandle* h) {
@@ -1482,7 +1550,7 @@ namespace {
 int resize_particles(SvbHandle* h, size_t new_cap) {
   new_cap = (new_cap + 63) & ~(size_t)63;
   if (new_cap <= h->cap) return 0;
-  CK(cudaStreamSynchronize(h->stream));
+  CK(sync_streams(h));
   DevBuf nb[2], ne;
   for (int b = 0; b < 2; ++b) CK(nb[b].ensure(new_cap * NFIELDS * 4));
   CK(ne.ensure(new_cap * 4));
@@ -1808,7 +1876,7 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
       peers.err_seq[r] = &ph->err_seq[h->rank];
       peers.err_val[r] = &ph->err_val[h->rank];
     }
-  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 1);
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 1, nullptr, nullptr);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1, h->K, BinNext{}, 0);

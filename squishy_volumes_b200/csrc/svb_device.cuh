@@ -84,6 +84,7 @@ struct TileTable {
   unsigned long long* tile_key;  // [tile_cap] key of tile id
   uint32_t* tile_slot;           // [tile_cap] table slot of tile id (the next substep clears exactly the used slots)
   uint32_t tile_cap;
+  uint32_t murmur;               // hash the table with murmur3 of the ordered-u32 block coordinates, seed = layer (the reference's node key) instead of the 64-bit mixer
 };
 
 // ---- per-substep scalars that kernels read from HBM (so launches do not depend on host values)
@@ -105,6 +106,7 @@ struct StepScalars {
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];  // tile claims: [0] P2G, [1] G2P (all tiles, or a slab rank's boundary tiles), [2] / [3] the same for its interior tiles
   uint32_t n_work[2];        // slab ranks: particle tiles in the boundary / interior work list (k_offsets)
+  uint32_t boundary_done[2]; // slab ranks: boundary tiles P2G / G2P have finished (the concurrent exchange senders wait for n_work[0])
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
   uint32_t n_candidates;     // particles whose BVH leaf holds triangles within reach (k_collide_query -> k_collide_cand)
   uint32_t n_candidates_unused;

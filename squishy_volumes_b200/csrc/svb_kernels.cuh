@@ -342,9 +342,18 @@ __device__ __forceinline__ uint32_t layer_bits_of(const unsigned long long* __re
 // ------------------------------------------------------------------------------------------------
 // tile table (update_grid_nodes.rs:31-156 without the hash map rebuild: the table is cleared and
 // refilled every substep, so there are no stale nodes)
-__device__ __forceinline__ uint32_t tile_hash(unsigned long long k, uint32_t mask) {
+__device__ __forceinline__ uint32_t tile_hash_mix(unsigned long long k, uint32_t mask) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
   return (uint32_t)k & mask;
+}
+// option "murmur_table_hash": the table is hashed like the reference hashes its grid nodes (gpu/src/util.rs:79-100,
+// build_hash_table_on_cpu :102-118): murmur3_x86_32 of the ordered-u32 coordinates — here of the tile's block, seeded with its layer
+__device__ __forceinline__ uint32_t tile_hash(const TileTable& T, unsigned long long k) {
+  if (!T.murmur) return tile_hash_mix(k, T.mask);
+  int bx, by, bz;
+  uint32_t layer;
+  tile_key_unpack(k, bx, by, bz, layer);
+  return node_id_to_murmur(bx, by, bz, layer) & T.mask;
 }
 __device__ __forceinline__ ulonglong2 slot_load(const ulonglong2* p) {
   ulonglong2 v;
@@ -353,7 +362,7 @@ __device__ __forceinline__ ulonglong2 slot_load(const ulonglong2* p) {
 }
 // returns the tile id, or TILE_PENDING when the tile capacity is exhausted (status bit set)
 __device__ __forceinline__ uint32_t tile_find_or_insert(const TileTable& T, unsigned long long key, StepScalars* S) {
-  uint32_t s = tile_hash(key, T.mask);
+  uint32_t s = tile_hash(T, key);
   for (uint32_t tries = 0; tries <= T.mask; ++tries) {
     ulonglong2 cur = slot_load(&T.slots[s]);
     if (cur.x == TILE_EMPTY) {
@@ -387,7 +396,7 @@ __device__ __forceinline__ uint32_t tile_find_or_insert(const TileTable& T, unsi
 // particle-tile id and records (id -> key, slot) and slot -> id for the kernels that follow, nobody spins on it.  Particle tiles
 // count in n_ptiles AND n_tiles, so that n_tiles == n_ptiles when the binning kernel ends without any block having to publish it.
 __device__ __forceinline__ uint32_t tile_slot_find_or_insert(const TileTable& T, unsigned long long key, StepScalars* S) {
-  uint32_t s = tile_hash(key, T.mask);
+  uint32_t s = tile_hash(T, key);
   for (uint32_t tries = 0; tries <= T.mask; ++tries) {
     unsigned long long k = *(volatile unsigned long long*)&T.slots[s].x;
     if (k == TILE_EMPTY) {
@@ -413,7 +422,7 @@ __device__ __forceinline__ uint32_t tile_slot_find_or_insert(const TileTable& T,
   return ~0u;
 }
 __device__ __forceinline__ int tile_find(const TileTable& T, unsigned long long key) {
-  uint32_t s = tile_hash(key, T.mask);
+  uint32_t s = tile_hash(T, key);
   for (uint32_t tries = 0; tries <= T.mask; ++tries) {
     const ulonglong2 cur = T.slots[s];
     if (cur.x == key) return (uint32_t)cur.y >= TILE_PENDING - 1 ? -1 : (int)(uint32_t)cur.y;
@@ -585,16 +594,40 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
 // per particle-owning tile (one warp each): exclusive scan of its 64 cell counts (in place), the tile's slot range
 // [first, end) in the binned order (S->n_live ends up as the number of binned particles), and the halo: create the neighbour tiles its particles' stencils reach and record the 8 neighbour ids
 // (update_grid_nodes.rs:102-108)
-// Which particle tiles a launch of P2G / G2P works through, claimed one at a time from `cursor`.  Slab ranks split their tiles into
-// BOUNDARY tiles (block columns lo and hi - 1: the only ones that write grid nodes a neighbour rank also writes, read nodes that
-// receive a neighbour's sums, or hold particles that can leave the slab) and INTERIOR tiles, so that the exchanges overlap work:
-//   P2G(boundary) -> halo send -> P2G(interior) -> halo receive -> G2P(boundary) -> migration send -> G2P(interior) -> migration receive
+// The particle tiles a launch of P2G / G2P works through, claimed one at a time from `cursor`.  Slab ranks order their tiles:
+// BOUNDARY tiles first (block columns lo and hi - 1: the only ones that write grid nodes a neighbour rank also writes, read nodes
+// that receive a neighbour's sums, or hold particles that can leave the slab), then the INTERIOR tiles.  Every finished boundary tile
+// ticks `done`; the sending kernel of the exchange runs CONCURRENTLY on a second stream, waits for `done` to reach the number of
+// boundary tiles and ships the halo column / the leavers while the interior tiles are still being worked on — so the neighbour's
+// message is long there when the receiving kernel that follows P2G / G2P on the main stream asks for it.
 struct WorkList {
-  const uint32_t* ids;     // null: the tile ids [0, n_ptiles) themselves
-  const uint32_t* count;   // tiles in the list (a word of the scalars)
+  const uint32_t* ids;       // boundary tile ids from 0, interior tile ids from `split`; null: the tile ids [0, *count) themselves
+  uint32_t split;            // offset of the interior list inside `ids` (the tile capacity)
+  const uint32_t* count;     // ids == null: number of tiles; else count[0] = boundary tiles, count[1] = interior tiles
   uint32_t* cursor;
-  int tail;                // G2P: this launch also carries the tombstoned rows over
+  uint32_t* done;            // boundary tiles finished so far (null: nobody waits)
+  int tail;                  // G2P: this launch also carries the tombstoned rows over
 };
+// -> tile id (0xffffffff: no work left); `boundary`: the tile is one whose completion the concurrent sender counts
+__device__ __forceinline__ uint32_t work_claim(const WorkList& W, bool& boundary) {
+  const uint32_t q = atomicAdd(W.cursor, 1u);
+  boundary = false;
+  if (!W.ids) return q < W.count[0] ? q : 0xffffffffu;
+  const uint32_t nb = W.count[0];
+  if (q < nb) { boundary = true; return W.ids[q]; }
+  return q - nb < W.count[1] ? W.ids[W.split + (q - nb)] : 0xffffffffu;
+}
+// the sender's side: true once `*done` has reached `*count` (gives up after ~2 s like wait_seq)
+__device__ __forceinline__ bool wait_boundary_done(const uint32_t* done, const uint32_t* count) {
+  const uint32_t want = *count;
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
+    if (v >= want) return true;
+    __nanosleep(spin < 64 ? 64 : 400);
+  }
+  return false;
+}
 struct SlabColumns {
   int lo, hi;
   uint32_t* list;          // [2 * tile_cap]: boundary tile ids from 0, interior tile ids from tile_cap; null on a single GPU
@@ -838,7 +871,6 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
     dt = force.D->allowed;
     force.dt = force.D->dt_force; force.gx = force.D->g[0]; force.gy = force.D->g[1]; force.gz = force.D->g[2]; force.factor_b = force.D->factor_b;
   }
-  const uint32_t n_groups = *W.count;
   const float scaling = dt * 4.f / (h * h);
   // node handled by this lane in the 3x3x3 stencil (k fastest); lanes 27..31 shadow node 0 and never flush
   const bool node_lane = lane < 27;
@@ -858,11 +890,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   const float fli = (float)li, flj = (float)lj, flk = (float)lk;
   const int lane_tile_off = (li * 6 + lj) * 6 + lk;
 
+  bool ticking = false;   // thread 0: the tile just finished was a boundary tile
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) {
-      const uint32_t q = atomicAdd(W.cursor, 1u);
-      s_group = q < n_groups ? (W.ids ? W.ids[q] : q) : 0xffffffffu;
+      // the previous tile's sums are in HBM (every thread's reductions precede the barrier above; one fence of the ticking thread
+      // orders them before the tick): tell the concurrent halo sender
+      if (ticking && W.done) { __threadfence(); atomicAdd(W.done, 1u); }
+      s_group = work_claim(W, ticking);
     }
     __syncthreads();
     const uint32_t g = s_group;
@@ -1098,8 +1133,8 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     for (int q = threadIdx.x; q < 27 * 64; q += blockDim.x) s_cnt[q] = 0u;
     if (threadIdx.x < 27) { s_touch[threadIdx.x] = 0u; s_cache[threadIdx.x] = ~0u; }
   }
-  const uint32_t n_groups = *W.count;
   const float h = K.h, inv_h = 1.f / K.h;
+  bool ticking = false;   // thread 0: the tile just finished was a boundary tile
   int red_vel = INT32_MIN, red_def = INT32_MAX;
   uint32_t failed = 0;
   for (;;) {
@@ -1117,9 +1152,9 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     if (threadIdx.x < 8) {
       uint32_t g0 = 0xffffffffu;
       if (threadIdx.x == 0) {
-        const uint32_t q = atomicAdd(W.cursor, 1u);
-        if (q < n_groups) g0 = W.ids ? W.ids[q] : q;
-        s_group = g0;
+        // the previous tile's rows (and its leavers' list entries) are written: tell the concurrent migration sender
+        if (ticking && W.done) { __threadfence(); atomicAdd(W.done, 1u); }
+        s_group = g0 = work_claim(W, ticking);
       }
       g0 = __shfl_sync(0xffu, g0, 0);
       if (g0 != 0xffffffffu) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
@@ -1672,12 +1707,19 @@ struct HaloPeers {
   uint32_t* count[2]; uint32_t* seq[2];
 };
 __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid, int lo, int hi,
-                                                    HaloPeers peers, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local) {
+                                                    HaloPeers peers, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local, const uint32_t* done, const uint32_t* n_boundary) {
   // a run that was stopped by an earlier substep (sticky is the same word on every rank: error words are exchanged, stop bits come
   // from identical clocks) exchanges nothing: every rank skips the same messages, however many no-op substeps its host queued
   if (S->sticky) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  if (done && !SVB_ABORTED(S)) {
+    // launched next to P2G on a second stream: the halo columns are complete once every boundary tile has been scattered
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok && threadIdx.x == 0) atomicOr(const_cast<uint32_t*>(&S->status), ST_COMM_TIMEOUT);
+  }
   if (!SVB_ABORTED(S)) {
     const uint32_t n_tiles = min(S->n_tiles, T.tile_cap);
     for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps) {
@@ -1802,9 +1844,16 @@ struct SlabPeers {
 // Sending side, driven by the lists k_g2p<SLAB> filled (slots whose advanced position left the slab): one thread per
 // migrating row; the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
 __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, MigrateCut mc, SlabPeers peers, uint32_t cap, uint32_t seq,
-                                                           uint32_t* __restrict__ blocks_done, int between_substeps) {
+                                                           uint32_t* __restrict__ blocks_done, int between_substeps, const uint32_t* done, const uint32_t* n_boundary) {
   __shared__ uint32_t s_c[2];
   if (!between_substeps && S->sticky) return;   // stopped run: no message (see k_halo_send2)
+  if (done && !SVB_ABORTED(S)) {
+    // launched next to G2P on a second stream: only boundary tiles hold particles that can leave the slab
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_TIMEOUT);
+  }
   if (threadIdx.x < 2) s_c[threadIdx.x] = atomicAdd(&mc.counts[threadIdx.x], 0u);
   __syncthreads();
   const uint32_t c0 = s_c[0], c1 = s_c[1];
@@ -2029,6 +2078,14 @@ __global__ void k_decode_active(TileTable T, const unsigned long long* __restric
   tile_key_unpack(T.tile_key[e], bx, by, bz, layer);
   block_ids[3 * e] = bx; block_ids[3 * e + 1] = by; block_ids[3 * e + 2] = bz;
   out_bits[e] = layer_bits_of(layer_slots, layer);
+}
+// the reference's node_ids_to_murmur stage (gpu/src/node_ids_to_murmur/mod.rs; test.rs:15-96): both hashes of every (node id, bits)
+__global__ void k_node_ids_to_murmur(const int32_t* __restrict__ node_ids, const uint32_t* __restrict__ bits, uint32_t n, uint32_t* __restrict__ plain, uint32_t* __restrict__ seeded) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t x = node_ids[3 * i], y = node_ids[3 * i + 1], z = node_ids[3 * i + 2];
+  if (plain) plain[i] = node_id_to_murmur(x, y, z, 0u);
+  if (seeded) seeded[i] = node_id_to_murmur(x, y, z, bits ? bits[i] : 0u);
 }
 __global__ void k_cells(ParticleBuf P, float h, uint32_t n, int32_t* __restrict__ cells) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

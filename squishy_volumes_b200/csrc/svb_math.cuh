@@ -294,6 +294,28 @@ SVB_HD M3 recompose(const Svd3& s, V3 d) {
   return mul_nt(ud, s.v);
 }
 
+// murmur3_x86_32 of three little-endian u32 words (12 bytes, no tail) — the node key of the reference's dormant sort path
+// (gpu/src/util.rs:79-100: the node id mapped to ordered u32 with x ^ 0x8000_0000, seed 0 or the collider bits; crate murmur3 0.5.2).
+SVB_HD uint32_t ordered_u32(int32_t x) { return (uint32_t)x ^ 0x80000000u; }   // gpu/src/util.rs:71-73 (i32_to_u32_offset)
+SVB_HD uint32_t murmur3_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+SVB_HD uint32_t murmur3_32_words3(uint32_t a, uint32_t b, uint32_t c, uint32_t seed) {
+  uint32_t h = seed;
+  const uint32_t w[3] = {a, b, c};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 3; ++q) {
+    uint32_t k = w[q] * 0xcc9e2d51u;
+    k = murmur3_rotl(k, 15) * 0x1b873593u;
+    h ^= k;
+    h = murmur3_rotl(h, 13) * 5u + 0xe6546b64u;
+  }
+  h ^= 12u;   // length in bytes
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+SVB_HD uint32_t node_id_to_murmur(int32_t x, int32_t y, int32_t z, uint32_t seed) { return murmur3_32_words3(ordered_u32(x), ordered_u32(y), ordered_u32(z), seed); }
+
 // f32::total_cmp as a signed-integer key, so min/max reductions can use integer atomics
 // (cpu/src/phase/limit_time_step.rs uses total_cmp for every reduction).
 SVB_HD int32_t total_key(float f) {

@@ -6,6 +6,7 @@
 #include "../../squishy_volumes_b200/csrc/svb_host.h"
 using namespace svb;
 extern "C" {
+uint32_t shim_node_id_to_murmur(int32_t x, int32_t y, int32_t z, uint32_t seed) { return node_id_to_murmur(x, y, z, seed); }
 void shim_svd3(const float* F, float* U, float* S, float* V) {
   M3 f; std::memcpy(f.m, F, 36);
   Svd3 r = svd3(f);
