@@ -184,6 +184,22 @@ int fail(SvbHandle* h, int code, const char* fmt, ...) {
 
 inline uint32_t blocks_for(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
 
+// Launch `kernel` as a programmatic dependent of the kernel queued just before it on `s` (the kernel calls grid_dependency_wait()
+// before it touches that kernel's results): its blocks may be scheduled while the predecessor's last blocks are still running, so
+// the launch ramp overlaps the predecessor's tail.  SVB_PDL=0 in the environment turns it into an ordinary launch.
+template <class... KArgs, class... Args>
+cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  static const bool enabled = [] { const char* e = std::getenv("SVB_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 void stage_begin(SvbHandle* h, int st) {
   if (!h->timing) return;
   cudaEventRecord(h->ev[0], h->stream);
@@ -316,9 +332,14 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool redo) {
   stage_end(h);
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
-  k_offsets<<<std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8), 256, 0, s>>>(S, ahead ? S_prev : nullptr, n, h->p2p ? h->n_dev : nullptr, T, F.cell_count.as<uint32_t>(),
-                                                                                                 F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(), F.tile_touch.as<uint32_t>(), F.nbr.as<int>(),
-                                                                                                 h->p2p ? SlabColumns{h->slab_lo, h->slab_hi, h->work_list.as<uint32_t>()} : SlabColumns{0, 0, nullptr});
+  const SlabColumns cols = h->p2p ? SlabColumns{h->slab_lo, h->slab_hi, h->work_list.as<uint32_t>()} : SlabColumns{0, 0, nullptr};
+  const uint32_t offsets_grid = std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8);
+  if (ahead && !h->slabs && !h->timing)   // straight behind the previous substep's G2P: a programmatic dependent of it
+    CK(launch_dependent(k_offsets, dim3(offsets_grid), dim3(256), 0, s, S, S_prev, n, (const uint32_t*)nullptr, T, F.cell_count.as<uint32_t>(), F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(),
+                        (const uint32_t*)F.tile_touch.as<uint32_t>(), F.nbr.as<int>(), cols));
+  else
+    k_offsets<<<offsets_grid, 256, 0, s>>>(S, ahead ? S_prev : nullptr, n, h->p2p ? h->n_dev : nullptr, T, F.cell_count.as<uint32_t>(), F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(),
+                                           F.tile_touch.as<uint32_t>(), F.nbr.as<int>(), cols);
   LAUNCH_CHECK();
   CK(cudaMemcpyAsync(h->h_scalars, S, sizeof(StepScalars), cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(h->ev_front, s));
@@ -380,9 +401,11 @@ int enqueue_p2g(SvbHandle* h, const StepInputs& in, const WorkList& W, uint32_t 
     force.G.flags_b = h->has_b ? h->d_flags_b.as<uint32_t>() : force.G.flags_a;
     force.G.goal_a = h->d_goal_a.as<float>();
     force.G.goal_b = h->has_b ? h->d_goal_b.as<float>() : force.G.goal_a;
-    k_p2g<true><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force, W);
+    CK(launch_dependent(k_p2g<true>, dim3(p2g_grid), dim3(P2G_WARPS * 32), P2G_SMEM, s, h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h,
+                        in.dt, force, W));
   } else {
-    k_p2g<false><<<p2g_grid, P2G_WARPS * 32, P2G_SMEM, s>>>(h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h, in.dt, force, W);
+    CK(launch_dependent(k_p2g<false>, dim3(p2g_grid), dim3(P2G_WARPS * 32), P2G_SMEM, s, h->Pc(), h->src_of.as<uint32_t>(), F.tile_start.as<uint2>(), F.nbr.as<int>(), cur_scalars(h), h->grid.as<float4>(), h->K.h,
+                        in.dt, force, W));
   }
   LAUNCH_CHECK();
   return 0;
@@ -465,7 +488,8 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next,
   const MigrateCut mc = cut ? *cut : MigrateCut{};
   BinNext bn{};
   if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
-#define SVB_G2P(F_, R_, M_, SL_, B_) k_g2p<F_, R_, M_, SL_, B_><<<g2p_grid, G2P_THREADS, 0, s>>>(P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn, F.tile_key.as<unsigned long long>(), W)
+#define SVB_G2P(F_, R_, M_, SL_, B_) \
+  CK(launch_dependent(k_g2p<F_, R_, M_, SL_, B_>, dim3(g2p_grid), dim3(G2P_THREADS), 0, s, P, D, src_of, en, tile_start, nb, S, src, h->K, dt, mc, bn, F.tile_key.as<unsigned long long>(), W))
   if (fuse && cut) {
     if (has_mesh) SVB_G2P(true, false, true, true, false);
     else if (bin_next) SVB_G2P(true, false, false, true, true);
@@ -812,7 +836,10 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       peers.err_val[r] = &ph->err_val[h->rank];
     }
   // (the rows G2P writes live in the OTHER buffer until `cur` is swapped below)
-  const bool send_beside_g2p = concurrent && !in.adaptive;
+  // (the migration sender next to G2P — gated by G2P's boundary tiles like the halo sender is by P2G's — timed out on 2 GPUs for a
+  //  reason not yet understood; until then it follows G2P on the main stream unless SVB_MIGRATE_BESIDE_G2P=1)
+  static const bool migrate_beside = [] { const char* e = std::getenv("SVB_MIGRATE_BESIDE_G2P"); return e && e[0] == '1'; }();
+  const bool send_beside_g2p = concurrent && !in.adaptive && migrate_beside;
   if (send_beside_g2p) {   // second stream: the migration sender, gated on the device by G2P's boundary tiles
     k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0]);
     LAUNCH_CHECK();

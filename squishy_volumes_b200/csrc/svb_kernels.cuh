@@ -19,6 +19,11 @@ namespace svb {
 
 #define SVB_FULL 0xffffffffu
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may begin while the
+// previous kernel of the stream is still draining (its blocks are scheduled onto the SMs that kernel's tail has already left); it
+// must not touch anything that kernel wrote before this returns.  A no-op under an ordinary launch.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int floor_div4(int v) { return v >> 2; }
 __device__ __forceinline__ int ceil_log2_u32(uint32_t v) {  // bits needed to represent values 0..v-1
   return v <= 1 ? 0 : 32 - __clz(v - 1);
@@ -638,6 +643,7 @@ struct SlabColumns {
 __global__ void __launch_bounds__(256) k_offsets(StepScalars* S, const StepScalars* __restrict__ Sprev, uint32_t n_rows, const uint32_t* __restrict__ n_dev, TileTable T,
                                                  uint32_t* __restrict__ cell_count, uint2* __restrict__ tile_range, uint32_t* __restrict__ slot_first, const uint32_t* __restrict__ tile_touch,
                                                  int* __restrict__ nbr, SlabColumns cols) {
+  grid_dependency_wait();
   bool aborted = SVB_ABORTED(S);
   if (Sprev) {
     const uint32_t carry = Sprev->status & ST_CARRY_MASK, stop = Sprev->sticky | Sprev->sticky_new;
@@ -866,6 +872,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* my_tile = tiles + warp * TILE_NODES;
   float* stage = stage_all + warp * 32 * STAGE_STRIDE;
+  grid_dependency_wait();
   if (SVB_ABORTED(S)) return;
   if (force.D) {
     dt = force.D->allowed;
@@ -1128,11 +1135,12 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
   __shared__ uint32_t s_touch[27];
   __shared__ uint32_t s_cnt[BIN ? 27 * 64 : 1];
   __shared__ int s_block[3];
-  if (SVB_ABORTED(S)) return;
-  if (BIN) {
+  if (BIN) {   // (shared-memory set-up overlaps the previous kernel's tail under a programmatic dependent launch)
     for (int q = threadIdx.x; q < 27 * 64; q += blockDim.x) s_cnt[q] = 0u;
     if (threadIdx.x < 27) { s_touch[threadIdx.x] = 0u; s_cache[threadIdx.x] = ~0u; }
   }
+  grid_dependency_wait();
+  if (SVB_ABORTED(S)) return;
   const float h = K.h, inv_h = 1.f / K.h;
   bool ticking = false;   // thread 0: the tile just finished was a boundary tile
   int red_vel = INT32_MIN, red_def = INT32_MAX;
