@@ -378,21 +378,29 @@ int enqueue_rebin(SvbHandle* h, bool prepare_next) {
 }
 
 // the tiles a P2G / G2P launch works through: all particle tiles, or (peer-memory slab ranks) the boundary / interior list of k_offsets
-WorkList work_all(SvbHandle* h, int counter, int tail) {
+// how finely a launch cuts the tiles' particle runs into work items (svb_kernels.cuh: WorkList::parts): whole tiles once there are
+// >= 8 tiles per resident CTA slot, halves from 4, quarters below (SVB_PARTS=1|2|4 in the environment overrides, for A/B runs)
+uint32_t work_parts(SvbHandle* h, uint32_t slots_per_sm) {
+  static const int forced = [] { const char* e = std::getenv("SVB_PARTS"); return e ? std::atoi(e) : 0; }();
+  if (forced == 1 || forced == 2 || forced == 4) return (uint32_t)forced;
+  const uint32_t tiles = std::max<uint32_t>(h->n_ptiles, 1), slots = 148 * slots_per_sm;
+  return tiles >= 8 * slots ? 1u : (tiles >= 4 * slots ? 2u : 4u);
+}
+WorkList work_all(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{nullptr, 0u, &S->n_ptiles, &S->work_counter[counter], nullptr, tail};
+  return WorkList{nullptr, 0u, &S->n_ptiles, &S->work_counter[phase], nullptr, tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5)};
 }
 // boundary tiles first, then the interior ones; `phase` 0 = P2G, 1 = G2P (work cursor and boundary-done counter of the scalars)
 WorkList work_ordered(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_work, &S->work_counter[phase], &S->boundary_done[phase], tail};
+  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_work, &S->work_counter[phase], &S->boundary_done[phase], tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5)};
 }
 
 int enqueue_p2g(SvbHandle* h, const StepInputs& in, const WorkList& W, uint32_t grid_cap = 148 * P2G_CTAS_PER_SM) {
   cudaStream_t s = h->stream;
   auto& F = h->fs[h->s_cur];
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, grid_cap));
+  const uint32_t p2g_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2 * W.parts, grid_cap));
   ForceIn force{};
   force.dt = in.dt; force.gx = in.g[0]; force.gy = in.g[1]; force.gz = in.g[2]; force.factor_b = in.factor_b;
   force.D = dt_ref(h, in);
@@ -484,7 +492,7 @@ int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next,
   float* en = h->energy.as<float>();
   const int* nb = F.nbr.as<int>();
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1);
-  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2, grid_cap));
+  const uint32_t g2p_grid = std::max<uint32_t>(148, std::min<uint32_t>(lag * 2 * W.parts, grid_cap));
   const MigrateCut mc = cut ? *cut : MigrateCut{};
   BinNext bn{};
   if (bin_next) bn = BinNext{scalars_of(h, h->s_cur ^ 1), tile_table(h, h->s_cur ^ 1), bin_arrays(h, h->s_cur ^ 1)};
@@ -781,7 +789,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
         hp.count[side] = &ph->halo_count[their];
         hp.seq[side] = &ph->halo_seq[their];
       }
-    k_halo_send2<<<32, 256, 0, sb>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local, &S->boundary_done[0], &S->n_work[0]);
+    k_halo_send2<<<32, 256, 0, sb>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local, &S->boundary_done[0], &S->n_work[0], work_parts(h, P2G_CTAS_PER_SM));
     LAUNCH_CHECK();
   }
   if (int rc = enqueue_p2g(h, in, work_ordered(h, 0, 0))) return rc;
@@ -801,7 +809,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
           hp.count[side] = &ph->halo_count[their];
           hp.seq[side] = &ph->halo_seq[their];
         }
-      k_halo_send2<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local, nullptr, nullptr);
+      k_halo_send2<<<148, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->grid.as<float4>(), h->slab_lo, h->slab_hi, hp, (uint32_t)h->mb_halo_cap, seq, h->p2p_local, nullptr, nullptr, 1u);
       LAUNCH_CHECK();
     }
     k_halo_recv2<<<148 * 2, 256, 0, s>>>(S, T, h->layer_slots.as<unsigned long long>(), h->layer_list.as<uint32_t>(), h->grid.as<float4>(), reinterpret_cast<const HaloEntry*>(my_mb + h->mb_halo_off[0]),
@@ -841,7 +849,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   static const bool migrate_beside = [] { const char* e = std::getenv("SVB_MIGRATE_BESIDE_G2P"); return e && e[0] == '1'; }();
   const bool send_beside_g2p = concurrent && !in.adaptive && migrate_beside;
   if (send_beside_g2p) {   // second stream: the migration sender, gated on the device by G2P's boundary tiles
-    k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0]);
+    k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0], work_parts(h, 5));
     LAUNCH_CHECK();
   }
   if (!in.adaptive) {
@@ -861,7 +869,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   stage_end(h);
   stage_begin(h, ST_MIGRATE);
   if (!send_beside_g2p) {
-    k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, nullptr, nullptr);
+    k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, nullptr, nullptr, 1u);
     LAUNCH_CHECK();
   }
   CK(cudaEventRecord(h->ev_b_end, sb));
@@ -1903,7 +1911,7 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
       peers.err_seq[r] = &ph->err_seq[h->rank];
       peers.err_val[r] = &ph->err_val[h->rank];
     }
-  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 1, nullptr, nullptr);
+  k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 1, nullptr, nullptr, 1u);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
                                      has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1, h->K, BinNext{}, 0);

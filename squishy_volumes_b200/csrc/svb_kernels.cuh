@@ -610,21 +610,35 @@ struct WorkList {
   uint32_t split;            // offset of the interior list inside `ids` (the tile capacity)
   const uint32_t* count;     // ids == null: number of tiles; else count[0] = boundary tiles, count[1] = interior tiles
   uint32_t* cursor;
-  uint32_t* done;            // boundary tiles finished so far (null: nobody waits)
+  uint32_t* done;            // boundary work items finished so far (null: nobody waits)
   int tail;                  // G2P: this launch also carries the tombstoned rows over
+  // A work item is a tile, or 1 / `parts` of its particle run (parts = 1, 2 or 4: particles [k, k + 1) * 512 / parts of the run, the
+  // last part up to the run's end): at 1 M particles a GPU holds only ~2.6 tiles per resident P2G CTA, so whole-tile items leave
+  // most SMs idle while the last CTAs finish their third tile; finer items fill that tail (at 8 M particles whole tiles are best).
+  uint32_t parts;
 };
-// -> tile id (0xffffffff: no work left); `boundary`: the tile is one whose completion the concurrent sender counts
-__device__ __forceinline__ uint32_t work_claim(const WorkList& W, bool& boundary) {
-  const uint32_t q = atomicAdd(W.cursor, 1u);
+// -> tile id (0xffffffff: no work left) and which part of its run; `boundary`: an item whose completion the concurrent sender counts
+__device__ __forceinline__ uint32_t work_claim(const WorkList& W, bool& boundary, uint32_t& part) {
+  const uint32_t item = atomicAdd(W.cursor, 1u);
+  const uint32_t q = item / W.parts;
+  part = item - q * W.parts;
   boundary = false;
   if (!W.ids) return q < W.count[0] ? q : 0xffffffffu;
   const uint32_t nb = W.count[0];
   if (q < nb) { boundary = true; return W.ids[q]; }
   return q - nb < W.count[1] ? W.ids[W.split + (q - nb)] : 0xffffffffu;
 }
-// the sender's side: true once `*done` has reached `*count` (gives up after ~2 s like wait_seq)
-__device__ __forceinline__ bool wait_boundary_done(const uint32_t* done, const uint32_t* count) {
-  const uint32_t want = *count;
+// the particle sub-range of a work item
+__device__ __forceinline__ uint2 work_range(const WorkList& W, uint2 run, uint32_t part) {
+  if (W.parts == 1) return run;
+  const uint32_t span = 512u / W.parts;
+  const uint32_t s = run.x + part * span;
+  const uint32_t e = part + 1 == W.parts ? run.y : min(run.y, s + span);
+  return make_uint2(min(s, run.y), max(e, min(s, run.y)));
+}
+// the sender's side: true once `*done` has reached `*count * parts` (gives up after ~2 s like wait_seq)
+__device__ __forceinline__ bool wait_boundary_done(const uint32_t* done, const uint32_t* count, uint32_t parts) {
+  const uint32_t want = *count * parts;
   for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
@@ -868,7 +882,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   float* stage_all = reinterpret_cast<float*>(smem_raw + P2G_WARPS * TILE_NODES * 16);
-  __shared__ uint32_t s_group;
+  __shared__ uint32_t s_group, s_part;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* my_tile = tiles + warp * TILE_NODES;
   float* stage = stage_all + warp * 32 * STAGE_STRIDE;
@@ -904,13 +918,14 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
       // the previous tile's sums are in HBM (every thread's reductions precede the barrier above; one fence of the ticking thread
       // orders them before the tick): tell the concurrent halo sender
       if (ticking && W.done) { __threadfence(); atomicAdd(W.done, 1u); }
-      s_group = work_claim(W, ticking);
+      s_group = work_claim(W, ticking, s_part);
     }
     __syncthreads();
     const uint32_t g = s_group;
     if (g == 0xffffffffu) break;
-    const uint2 range = group_range[g];
+    const uint2 range = work_range(W, group_range[g], s_part);
     const uint32_t start = range.x, end = range.y;
+    if (start >= end) continue;   // (a short run has no particles for this part)
     for (int q = threadIdx.x; q < P2G_WARPS * TILE_NODES; q += blockDim.x) tiles[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
@@ -1126,7 +1141,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
                                                         const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn,
                                                         const unsigned long long* __restrict__ tile_key, WorkList W) {
   __shared__ float4 tile[TILE_NODES];
-  __shared__ uint32_t s_group;
+  __shared__ uint32_t s_group, s_part;
   __shared__ int s_nbr[8];
   // BIN: a particle moves less than a cell per substep, so its next tile is one of the 27 blocks around this CTA's tile: their table
   // slots (in the NEXT substep's set) are cached, the cell counts and touch masks of the tile's particles are collected in shared
@@ -1162,7 +1177,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       if (threadIdx.x == 0) {
         // the previous tile's rows (and its leavers' list entries) are written: tell the concurrent migration sender
         if (ticking && W.done) { __threadfence(); atomicAdd(W.done, 1u); }
-        s_group = g0 = work_claim(W, ticking);
+        s_group = g0 = work_claim(W, ticking, s_part);
       }
       g0 = __shfl_sync(0xffu, g0, 0);
       if (g0 != 0xffffffffu) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
@@ -1177,8 +1192,9 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     if (BIN && threadIdx.x >= 32 && threadIdx.x < 32 + 27) s_cache[threadIdx.x - 32] = ~0u;   // (the flush above has read the old slots)
     const uint32_t g = s_group;
     if (g == 0xffffffffu) break;
-    const uint2 range = group_range[g];
+    const uint2 range = work_range(W, group_range[g], s_part);
     const uint32_t start = range.x, end = range.y;
+    if (start >= end) continue;   // (a short run has no particles for this part)
     for (int t = threadIdx.x; t < TILE_NODES; t += blockDim.x) {
       const int ti = t / 36, tj = (t / 6) % 6, tk = t % 6;
       const int nb = s_nbr[(ti >> 2) | ((tj >> 2) << 1) | ((tk >> 2) << 2)];
@@ -1715,7 +1731,7 @@ struct HaloPeers {
   uint32_t* count[2]; uint32_t* seq[2];
 };
 __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restrict__ S, TileTable T, const unsigned long long* __restrict__ layer_slots, const float4* __restrict__ grid, int lo, int hi,
-                                                    HaloPeers peers, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local, const uint32_t* done, const uint32_t* n_boundary) {
+                                                    HaloPeers peers, uint32_t cap, uint32_t seq, uint32_t* __restrict__ local, const uint32_t* done, const uint32_t* n_boundary, uint32_t parts) {
   // a run that was stopped by an earlier substep (sticky is the same word on every rank: error words are exchanged, stop bits come
   // from identical clocks) exchanges nothing: every rank skips the same messages, however many no-op substeps its host queued
   if (S->sticky) return;
@@ -1724,7 +1740,7 @@ __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restric
   if (done && !SVB_ABORTED(S)) {
     // launched next to P2G on a second stream: the halo columns are complete once every boundary tile has been scattered
     __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary) ? 1 : 0;
+    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary, parts) ? 1 : 0;
     __syncthreads();
     if (!s_ok && threadIdx.x == 0) atomicOr(const_cast<uint32_t*>(&S->status), ST_COMM_TIMEOUT);
   }
@@ -1852,13 +1868,13 @@ struct SlabPeers {
 // Sending side, driven by the lists k_g2p<SLAB> filled (slots whose advanced position left the slab): one thread per
 // migrating row; the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
 __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, MigrateCut mc, SlabPeers peers, uint32_t cap, uint32_t seq,
-                                                           uint32_t* __restrict__ blocks_done, int between_substeps, const uint32_t* done, const uint32_t* n_boundary) {
+                                                           uint32_t* __restrict__ blocks_done, int between_substeps, const uint32_t* done, const uint32_t* n_boundary, uint32_t parts) {
   __shared__ uint32_t s_c[2];
   if (!between_substeps && S->sticky) return;   // stopped run: no message (see k_halo_send2)
   if (done && !SVB_ABORTED(S)) {
     // launched next to G2P on a second stream: only boundary tiles hold particles that can leave the slab
     __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary) ? 1 : 0;
+    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary, parts) ? 1 : 0;
     __syncthreads();
     if (!s_ok && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_TIMEOUT);
   }
