@@ -378,13 +378,13 @@ int enqueue_rebin(SvbHandle* h, bool prepare_next) {
 }
 
 // the tiles a P2G / G2P launch works through: all particle tiles, or (peer-memory slab ranks) the boundary / interior list of k_offsets
-// how finely a launch cuts the tiles' particle runs into work items (svb_kernels.cuh: WorkList::parts): whole tiles once there are
-// >= 8 tiles per resident CTA slot, halves from 4, quarters below (SVB_PARTS=1|2|4 in the environment overrides, for A/B runs)
-uint32_t work_parts(SvbHandle* h, uint32_t slots_per_sm) {
+// how finely a launch cuts the tiles' particle runs into work items (svb_kernels.cuh: WorkList::parts).  Whole tiles: measured on
+// B200 (profiles/README.md r2i) halves and quarters are SLOWER at 1 M and at 8 M particles (G2P 78 -> 88 -> 112 us at 1 M) — every
+// work item pays ~3 us of dependent round trips (claim, neighbour ids, velocity tile, row indices) that more items only multiply,
+// which outweighs the fuller tail.  SVB_PARTS=2|4 in the environment keeps the experiment reproducible.
+uint32_t work_parts(SvbHandle*, uint32_t) {
   static const int forced = [] { const char* e = std::getenv("SVB_PARTS"); return e ? std::atoi(e) : 0; }();
-  if (forced == 1 || forced == 2 || forced == 4) return (uint32_t)forced;
-  const uint32_t tiles = std::max<uint32_t>(h->n_ptiles, 1), slots = 148 * slots_per_sm;
-  return tiles >= 8 * slots ? 1u : (tiles >= 4 * slots ? 2u : 4u);
+  return forced == 2 || forced == 4 ? (uint32_t)forced : 1u;
 }
 WorkList work_all(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
