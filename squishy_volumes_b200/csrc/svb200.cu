@@ -1132,7 +1132,7 @@ int32_t svb_set_topology(SvbHandle* h, uint32_t n_colliders, const uint32_t* num
   CK(h->d_vpos.ensure((size_t)T.n_vertices * 12 + 4));
   CK(h->d_vnormal.ensure((size_t)T.n_vertices * 12 + 4));
   CK(h->d_tnormal.ensure((size_t)T.n_triangles * 12 + 4));
-  CK(h->d_tbox.ensure((size_t)T.n_triangles * 24 + 4));
+  CK(h->d_tbox.ensure((size_t)T.n_triangles * 32 + 16));
   CK(h->d_tfric.ensure((size_t)T.n_triangles * 4 + 4));
   CK(h->d_tdamp.ensure((size_t)T.n_triangles * 4 + 4));
   CK(cudaStreamSynchronize(h->stream));

@@ -172,7 +172,7 @@ struct MeshDev {
   const float* damp_a; const float* damp_b;
   // interpolated per substep
   float* vpos; float* vnormal; float* tnormal; float* tfric; float* tdamp;
-  float* tbox;                  // 6 per triangle: bounding box (min, max) of the interpolated triangle, a cheap reject before the exact distance
+  float* tbox;                  // 8 per triangle (two float4: min, max) bounding box of the interpolated triangle, a cheap reject before the exact distance
   // BVH
   int32_t bvh_level;
   int32_t bvh_nodes;

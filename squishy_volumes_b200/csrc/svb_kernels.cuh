@@ -86,17 +86,17 @@ __global__ void k_mesh_tri_normals(MeshDev M) {
   const V3 a = ld3(M.vpos, M.tri[3 * t]), b = ld3(M.vpos, M.tri[3 * t + 1]), c = ld3(M.vpos, M.tri[3 * t + 2]);
   const V3 n = normalize_or_zero(cross(b - a, c - a), SVB_NORMALIZATION_EPS);
   M.tnormal[3 * t] = n.x; M.tnormal[3 * t + 1] = n.y; M.tnormal[3 * t + 2] = n.z;
-  float* box = M.tbox + 6 * t;
-  box[0] = fminf(a.x, fminf(b.x, c.x)); box[1] = fminf(a.y, fminf(b.y, c.y)); box[2] = fminf(a.z, fminf(b.z, c.z));
-  box[3] = fmaxf(a.x, fmaxf(b.x, c.x)); box[4] = fmaxf(a.y, fmaxf(b.y, c.y)); box[5] = fmaxf(a.z, fmaxf(b.z, c.z));
+  float4* box = reinterpret_cast<float4*>(M.tbox) + 2 * t;   // (min, -) and (max, -): two 16-byte loads per test
+  box[0] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.f);
+  box[1] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.f);
 }
 // true when the triangle's bounding box is farther from p than `reach`: its exact distance is then >= reach as well, so
 // skipping it cannot change which triangle is closest within the forget distance (reach carries a 0.1 % rounding margin)
 __device__ __forceinline__ bool triangle_out_of_reach(const MeshDev& M, uint32_t t, V3 p, float reach) {
-  const float* box = M.tbox + 6 * t;
-  const float dx = fmaxf(fmaxf(box[0] - p.x, p.x - box[3]), 0.f);
-  const float dy = fmaxf(fmaxf(box[1] - p.y, p.y - box[4]), 0.f);
-  const float dz = fmaxf(fmaxf(box[2] - p.z, p.z - box[5]), 0.f);
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(M.tbox) + 2 * t), hi = __ldg(reinterpret_cast<const float4*>(M.tbox) + 2 * t + 1);
+  const float dx = fmaxf(fmaxf(lo.x - p.x, p.x - hi.x), 0.f);
+  const float dy = fmaxf(fmaxf(lo.y - p.y, p.y - hi.y), 0.f);
+  const float dz = fmaxf(fmaxf(lo.z - p.z, p.z - hi.z), 0.f);
   return dx * dx + dy * dy + dz * dz > reach * reach;
 }
 __global__ void k_mesh_vertex_normals(MeshDev M) {
@@ -285,16 +285,26 @@ __global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepS
   if (D) dt = D->dt_force;
   const uint32_t n_cand = S->n_candidates;
   const float reach = K.forget_distance * 1.001f;
-  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
-    const uint32_t i = candidates[q];
-    const V3 p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-    int first, count;
-    bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
-    uint32_t closest[NC];
-    float min_dist[NC];
+  // FOUR lanes per candidate share the leaf's triangle run (entries sub, sub + 4, ...): the scan is a chain of dependent loads
+  // (run entry -> bounding box -> vertices), and a particle resting on a mesh sees 40-100 triangles — one thread per candidate
+  // left the SMs at 14 % active warps.  Each lane keeps, per collider, the closest triangle of ITS entries as the key
+  // (distance bits << 32 | position in the run); distances are >= 0, so the unsigned order of the keys is the numeric order and ties
+  // go to the earlier entry: the minimum over the four lanes is the FIRST minimum of the reference's sequential scan (collide.rs:82).
+  const uint32_t lane = threadIdx.x & 31, sub = lane & 3u;
+  const uint32_t groups = (gridDim.x * blockDim.x) >> 2;
+  for (uint32_t q0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; q0 < ((n_cand + 7u) & ~7u); q0 += groups) {   // warp-uniform trip count (8 candidates per warp)
+    const bool have = q0 < n_cand;
+    const uint32_t i = have ? candidates[q0] : 0u;
+    V3 p = V3{0.f, 0.f, 0.f};
+    int first = 0, count = 0;
+    if (have) {
+      p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+      bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
+    }
+    unsigned long long best[NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { closest[c] = 0xffffffffu; min_dist[c] = 3.402823466e+38f; }
-    for (int r = 0; r < count; ++r) {
+    for (int c = 0; c < NC; ++c) best[c] = ~0ull;
+    for (int r = (int)sub; r < count; r += 4) {
       const uint32_t t = M.tri_indices[first + r];
       if (triangle_out_of_reach(M, t, p, reach)) continue;
       const V3 n = ld3(M.tnormal, t);
@@ -302,14 +312,28 @@ __global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepS
       const float d = triangle_distance(p, ld3(M.vpos, M.tri[3 * t]), ld3(M.vpos, M.tri[3 * t + 1]), ld3(M.vpos, M.tri[3 * t + 2]), n);
       if (!(d < K.forget_distance)) continue;   // (also drops a NaN distance, which the reference's `d < min` never selects)
       const uint32_t c = M.tri_collider[t] & 15u;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)r;
 #pragma unroll
       for (int k = 0; k < NC; ++k)
-        if ((uint32_t)k == c && d < min_dist[k]) { min_dist[k] = d; closest[k] = t; }
+        if ((uint32_t)k == c && key < best[k]) best[k] = key;
     }
-    V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-    const uint32_t bits = collide_respond<NC>(M, K, dt, p, vel, P.u(PBITS)[i], closest);
-    P.u(PBITS)[i] = bits;
-    P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
+    uint32_t closest[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      unsigned long long b = best[c];
+#pragma unroll
+      for (int o = 1; o < 4; o <<= 1) {
+        const unsigned long long other = __shfl_xor_sync(SVB_FULL, b, o);
+        b = other < b ? other : b;
+      }
+      closest[c] = b != ~0ull ? M.tri_indices[first + (uint32_t)b] : 0xffffffffu;
+    }
+    if (have && sub == 0) {
+      V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+      const uint32_t bits = collide_respond<NC>(M, K, dt, p, vel, P.u(PBITS)[i], closest);
+      P.u(PBITS)[i] = bits;
+      P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
+    }
   }
 }
 
@@ -1549,8 +1573,11 @@ __global__ void k_dt_tail(DtState* D, StepScalars* S, DtPeers peers) {
 // advance + cull as its own pass (adaptive time stepping: dt is only known after the G2P reductions).  Also — it holds the advanced
 // position and F — the binning of the next substep (BIN, scenes without a collider mesh) and the per-particle limits of the next
 // substep's LimitTimeStepBeforeForce (limit_time_step.rs:35-182).  One thread per row of the binned buffer, tombstoned rows included.
+#ifndef SVB_ADVANCE_BLOCKS
+#define SVB_ADVANCE_BLOCKS 3   // 85 registers: 24 warps per SM for a kernel that streams 176 B per particle
+#endif
 template <bool BIN>
-__global__ void __launch_bounds__(256) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn, MigrateCut mc) {
+__global__ void __launch_bounds__(256, SVB_ADVANCE_BLOCKS) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn, MigrateCut mc) {
   if (SVB_ABORTED(S)) return;
   n = min(n, S->n_live + S->n_tomb);
   const float dt = D->allowed;

@@ -282,6 +282,42 @@ SVB_HD Svd3 svd3(const M3& F) {
   r.u.m[6] = u2.x; r.u.m[7] = u2.y; r.u.m[8] = u2.z;
   return r;
 }
+// singular values only (sorted descending): the same rotations as svd3 applied to B alone — bit-identical values without carrying V
+// and without forming U (the time-step limits need nothing else, cpu/src/phase/limit_time_step.rs:45: svd(false, false))
+SVB_HD void jacobi_pair_values(M3& b, int p, int q) {
+  const float a0 = b.m[p * 3], a1 = b.m[p * 3 + 1], a2 = b.m[p * 3 + 2];
+  const float c0 = b.m[q * 3], c1 = b.m[q * 3 + 1], c2 = b.m[q * 3 + 2];
+  const float alpha = a0 * a0 + a1 * a1 + a2 * a2;
+  const float beta = c0 * c0 + c1 * c1 + c2 * c2;
+  const float gamma = a0 * c0 + a1 * c1 + a2 * c2;
+  if (gamma * gamma <= SVD_ORTHOGONAL * alpha * beta) return;
+  const float zeta = (beta - alpha) / (2.f * gamma);
+  const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
+  const float c = 1.f / sqrtf(1.f + t * t);
+  const float s = c * t;
+  b.m[p * 3] = c * a0 - s * c0; b.m[p * 3 + 1] = c * a1 - s * c1; b.m[p * 3 + 2] = c * a2 - s * c2;
+  b.m[q * 3] = s * a0 + c * c0; b.m[q * 3 + 1] = s * a1 + c * c1; b.m[q * 3 + 2] = s * a2 + c * c2;
+}
+SVB_HD V3 singular_values3(const M3& F) {
+  M3 b = F;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int sweep = 0; sweep < 8; ++sweep) {
+    jacobi_pair_values(b, 0, 1);
+    jacobi_pair_values(b, 0, 2);
+    jacobi_pair_values(b, 1, 2);
+    const V3 b0 = col(b, 0), b1 = col(b, 1), b2 = col(b, 2);
+    const float n0 = dot(b0, b0), n1 = dot(b1, b1), n2 = dot(b2, b2);
+    const float g01 = dot(b0, b1), g02 = dot(b0, b2), g12 = dot(b1, b2);
+    if (g01 * g01 <= SVD_ORTHOGONAL * n0 * n1 && g02 * g02 <= SVD_ORTHOGONAL * n0 * n2 && g12 * g12 <= SVD_ORTHOGONAL * n1 * n2) break;
+  }
+  float s0 = norm(col(b, 0)), s1 = norm(col(b, 1)), s2 = norm(col(b, 2));
+  if (s0 < s1) { const float t = s0; s0 = s1; s1 = t; }
+  if (s0 < s2) { const float t = s0; s0 = s2; s2 = t; }
+  if (s1 < s2) { const float t = s1; s1 = s2; s2 = t; }
+  return V3{s0, s1, s2};
+}
 // U diag(d) V^T
 SVB_HD M3 recompose(const Svd3& s, V3 d) {
   M3 ud;
@@ -345,8 +381,7 @@ struct ParticleLimits {
 };
 SVB_HD ParticleLimits particle_time_step_limits(bool is_fluid, float p0, float p1, float mass, float initial_volume,
                                                 const M3& F, float h) {
-  const Svd3 svd = svd3(F);
-  const V3 s = svd.s;
+  const V3 s = singular_values3(F);
   const float j = s.x * s.y * s.z;
   const bool xy_close = fabsf(s.x - s.y) < SVB_SINGULAR_VALUE_SEPARATION;
   const bool yz_close = fabsf(s.y - s.z) < SVB_SINGULAR_VALUE_SEPARATION;
