@@ -319,7 +319,12 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool redo) {
       k_collide_query<<<blocks, 256, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, n);
       LAUNCH_CHECK();
       const uint32_t nc = h->M.n_colliders;
-#define SVB_CAND(NC) k_collide_cand<NC><<<148 * 16, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, in.dt, dt_ref(h, in))
+#define SVB_CAND(NC)                                                                                                                    \
+  do {                                                                                                                                \
+    k_collide_cand<NC, 1, false><<<148 * 8, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, in.dt, dt_ref(h, in)); \
+    k_collide_cand<NC, 4, true><<<148 * 16, 128, 0, s>>>(h->Pc(), S, h->K, h->M, candidates, (uint32_t)h->cap, in.dt, dt_ref(h, in)); \
+    ++h->launches;                                                                                                                    \
+  } while (0)
       if (nc <= 1) SVB_CAND(1); else if (nc <= 2) SVB_CAND(2); else if (nc <= 4) SVB_CAND(4); else SVB_CAND(16);
 #undef SVB_CAND
       LAUNCH_CHECK();

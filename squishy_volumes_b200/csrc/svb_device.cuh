@@ -108,8 +108,8 @@ struct StepScalars {
   uint32_t n_work[2];        // slab ranks: particle tiles in the boundary / interior work list (k_offsets)
   uint32_t boundary_done[2]; // slab ranks: boundary tiles P2G / G2P have finished (the concurrent exchange senders wait for n_work[0])
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
-  uint32_t n_candidates;     // particles whose BVH leaf holds triangles within reach (k_collide_query -> k_collide_cand)
-  uint32_t n_candidates_unused;
+  uint32_t n_candidates;     // particles whose BVH leaf holds a few triangles within reach (k_collide_query -> k_collide_cand, one thread each)
+  uint32_t n_candidates_big; // ... whose leaf holds a long triangle run (back of the candidate array, four lanes each)
   // adaptive time step reductions (f32::total_cmp keys)
   int32_t min_sound_key, min_isolated_key, max_velocity_key, min_deformation_key;
   uint32_t live_count;

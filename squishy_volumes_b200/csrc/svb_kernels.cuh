@@ -253,48 +253,59 @@ __global__ void __launch_bounds__(256) k_collide_query(ParticleBuf P, StepScalar
   if (S->sticky) return;
   n = min(n, S->n);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool cand = false;
+  int kind = 0;   // 1: a short triangle run (front of the list, one thread each), 2: a long one (back of the list, four lanes each)
   if (i < n) {
     const uint32_t flags = P.u(PFLAGS)[i];
     const float x0 = P.f(PX)[i], x1 = P.f(PX + 1)[i], x2 = P.f(PX + 2)[i];
     if (!(flags & (F_TOMBSTONED | F_GONE))) {
       int first, count;
       bvh_query(M, (int)floorf(x0 / K.leaf_size), (int)floorf(x1 / K.leaf_size), (int)floorf(x2 / K.leaf_size), first, count);
-      if (count > COLLIDE_SMALL_MAX) cand = true;
+      if (count > COLLIDE_SMALL_MAX) kind = 2;
       else {
         // a leaf with few triangles (a coarse mesh: the whole box collider of a dam break is ONE leaf) — look for any triangle
         // whose bounding box is within reach; with none, every collider ends "not near": the same bits as an empty leaf
         const V3 p = V3{x0, x1, x2};
         const float reach = K.forget_distance * 1.001f;
-        for (int r = 0; r < count && !cand; ++r)
-          if (!triangle_out_of_reach(M, M.tri_indices[first + r], p, reach)) cand = true;
+        for (int r = 0; r < count && kind == 0; ++r)
+          if (!triangle_out_of_reach(M, M.tri_indices[first + r], p, reach)) kind = 1;
       }
-      if (!cand) P.u(PBITS)[i] = 0u;
+      if (kind == 0) P.u(PBITS)[i] = 0u;
     }
   }
   const uint32_t lane = threadIdx.x & 31;
-  const unsigned ms = __ballot_sync(SVB_FULL, cand);
-  uint32_t base_s = 0;
-  if (lane == 0 && ms) base_s = atomicAdd(&S->n_candidates, (uint32_t)__popc(ms));
+  const unsigned ms = __ballot_sync(SVB_FULL, kind == 1), mb = __ballot_sync(SVB_FULL, kind == 2);
+  uint32_t base_s = 0, base_b = 0;
+  if (lane == 0) {
+    if (ms) base_s = atomicAdd(&S->n_candidates, (uint32_t)__popc(ms));
+    if (mb) base_b = atomicAdd(&S->n_candidates_big, (uint32_t)__popc(mb));
+  }
   base_s = __shfl_sync(SVB_FULL, base_s, 0);
-  if (cand) candidates[base_s + __popc(ms & ((1u << lane) - 1u))] = i;   // <= n <= cap entries
+  base_b = __shfl_sync(SVB_FULL, base_b, 0);
+  const unsigned below = (1u << lane) - 1u;
+  if (kind == 1) candidates[base_s + __popc(ms & below)] = i;                    // the two lists cannot meet: together they hold <= n <= cap entries
+  if (kind == 2) candidates[cap - 1 - (base_b + __popc(mb & below))] = i;
 }
-template <int NC>
-__global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, float dt, const DtState* __restrict__ D) {
+// LANES lanes (1 or 4) per candidate share the leaf's triangle run (entries sub, sub + LANES, ...).  The scan is a chain of dependent
+// loads (run entry -> bounding box -> vertices): a particle resting on a finely meshed collider sees 40-100 triangles, and one thread
+// per candidate left the SMs at 14 % active warps (105 us for 1 M sand particles on a torus; 62 us with four lanes) — while the
+// candidates of a coarse mesh (the 12-triangle box of a dam break is ONE leaf) have a handful of triangles and are dominated by the
+// response, which only one lane of a group computes (four lanes there: 113 -> 131 us).  Hence two lists.  Each lane keeps, per
+// collider, the closest triangle of ITS entries as the key (distance bits << 32 | position in the run); distances are >= 0, so the
+// unsigned order of the keys is the numeric order and ties go to the earlier entry: the minimum over the lanes is the FIRST minimum
+// of the reference's sequential scan (collide.rs:82).  BIG: the list of long runs (back of the candidate array).
+template <int NC, int LANES, bool BIG>
+__global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepScalars* __restrict__ S, SimConsts K, MeshDev M, const uint32_t* __restrict__ candidates, uint32_t cap, float dt,
+                                                      const DtState* __restrict__ D) {
   if (S->sticky) return;
   if (D) dt = D->dt_force;
-  const uint32_t n_cand = S->n_candidates;
+  const uint32_t n_cand = BIG ? S->n_candidates_big : S->n_candidates;
   const float reach = K.forget_distance * 1.001f;
-  // FOUR lanes per candidate share the leaf's triangle run (entries sub, sub + 4, ...): the scan is a chain of dependent loads
-  // (run entry -> bounding box -> vertices), and a particle resting on a mesh sees 40-100 triangles — one thread per candidate
-  // left the SMs at 14 % active warps.  Each lane keeps, per collider, the closest triangle of ITS entries as the key
-  // (distance bits << 32 | position in the run); distances are >= 0, so the unsigned order of the keys is the numeric order and ties
-  // go to the earlier entry: the minimum over the four lanes is the FIRST minimum of the reference's sequential scan (collide.rs:82).
-  const uint32_t lane = threadIdx.x & 31, sub = lane & 3u;
-  const uint32_t groups = (gridDim.x * blockDim.x) >> 2;
-  for (uint32_t q0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; q0 < ((n_cand + 7u) & ~7u); q0 += groups) {   // warp-uniform trip count (8 candidates per warp)
+  const uint32_t lane = threadIdx.x & 31, sub = lane & (LANES - 1);
+  const uint32_t groups = (gridDim.x * blockDim.x) / LANES;
+  constexpr uint32_t PER_WARP = 32 / LANES;
+  for (uint32_t q0 = (blockIdx.x * blockDim.x + threadIdx.x) / LANES; q0 < ((n_cand + PER_WARP - 1) / PER_WARP) * PER_WARP; q0 += groups) {   // warp-uniform trip count
     const bool have = q0 < n_cand;
-    const uint32_t i = have ? candidates[q0] : 0u;
+    const uint32_t i = have ? candidates[BIG ? cap - 1 - q0 : q0] : 0u;
     V3 p = V3{0.f, 0.f, 0.f};
     int first = 0, count = 0;
     if (have) {
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepS
     unsigned long long best[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) best[c] = ~0ull;
-    for (int r = (int)sub; r < count; r += 4) {
+    for (int r = (int)sub; r < count; r += LANES) {
       const uint32_t t = M.tri_indices[first + r];
       if (triangle_out_of_reach(M, t, p, reach)) continue;
       const V3 n = ld3(M.tnormal, t);
@@ -322,7 +333,7 @@ __global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepS
     for (int c = 0; c < NC; ++c) {
       unsigned long long b = best[c];
 #pragma unroll
-      for (int o = 1; o < 4; o <<= 1) {
+      for (int o = 1; o < LANES; o <<= 1) {
         const unsigned long long other = __shfl_xor_sync(SVB_FULL, b, o);
         b = other < b ? other : b;
       }
@@ -1574,7 +1585,7 @@ __global__ void k_dt_tail(DtState* D, StepScalars* S, DtPeers peers) {
 // position and F — the binning of the next substep (BIN, scenes without a collider mesh) and the per-particle limits of the next
 // substep's LimitTimeStepBeforeForce (limit_time_step.rs:35-182).  One thread per row of the binned buffer, tombstoned rows included.
 #ifndef SVB_ADVANCE_BLOCKS
-#define SVB_ADVANCE_BLOCKS 3   // 85 registers: 24 warps per SM for a kernel that streams 176 B per particle
+#define SVB_ADVANCE_BLOCKS 2   // (3 blocks / SM = 80 registers with 30 bytes of spills: measured the same, 0.288 vs 0.286 ms per adaptive substep)
 #endif
 template <bool BIN>
 __global__ void __launch_bounds__(256, SVB_ADVANCE_BLOCKS) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn, MigrateCut mc) {
