@@ -340,6 +340,14 @@ def main():
     state, inner = make_state(scene.io_state)
     if warmup:
         state.advance(None, fi, run_params(state, warmup))   # contact has begun, buffers have settled
+    rebalanced = None
+    if world > 1:
+        # the cuts were planned on the initial particle positions; material has moved since ("rebalanced by particle
+        # count every K substeps" — here once, between the warm-up and the timed region, like a frame loop would between frames)
+        try:
+            rebalanced = bool(state.rebalance(dist))
+        except Exception as exc:   # a refused plan (e.g. a cut that would leave its neighbour slabs) is not an error of the run
+            rebalanced = f"not done: {exc}"
     if world == 1:
         inner.snapshot()                                      # device-side copy: the extra passes below repeat exactly the timed one
     launches0 = inner.kernel_launches
@@ -410,6 +418,7 @@ def main():
             "clocks": clocks.summary()}
     if slab_parity is not None or world > 1:
         line["slab_parity"] = slab_parity
+        line["config"]["rebalanced_after_warmup"] = rebalanced
 
     # ---------------- end to end through the public API with host buffers (page-locked, as the contract asks)
     if not args.no_e2e:
