@@ -1326,8 +1326,12 @@ int32_t svb_advance(SvbHandle* h, double target_time, float max_time_step, int32
   if (int rc = read_status(h)) return rc;
   if (h->p2p) {  // the row count lived on the device during the loop
     CK(cudaMemcpy(&h->n, h->n_dev, 4, cudaMemcpyDeviceToHost));
-    if (h->h_scalars->status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))
-      return fail(h, SVB_COMM_ERROR, h->h_scalars->status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
+    if (h->h_scalars->status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW)) {
+      const StepScalars& r = *h->h_scalars;
+      return fail(h, SVB_COMM_ERROR, "%s (rank %d, message %u; boundary tiles %u, interior %u, ticks P2G %u G2P %u, status 0x%x)",
+                  r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room", h->rank, h->slab_seq, r.n_work[0],
+                  r.n_work[1], r.boundary_done[0], r.boundary_done[1], r.status);
+    }
   }
   CK(cudaEventElapsedTime(&h->last_advance_ms, h->ev_adv[0], h->ev_adv[1]));
   if (h->status) {

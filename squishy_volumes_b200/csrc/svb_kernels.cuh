@@ -1069,6 +1069,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
           o.x += acc_xy.x; o.y += acc_xy.y; o.z += acc_z; o.w += acc_m;
           my_tile[t] = o;
         }
+        __syncwarp();   // the next run's flush reads nodes another lane has just written (neighbouring cells share 18 of their 27 nodes)
       }
       __syncwarp();
     }
@@ -1361,6 +1362,8 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
           if (b0 < -lim || b0 > lim || b1 < -lim || b1 > lim || b2 < -lim || b2 > lim) atomicOr(&bn.S->status, ST_KEY_RANGE);
           else if ((unsigned)d0 < 3u && (unsigned)d1 < 3u && (unsigned)d2 < 3u) {
             const int at = (d0 * 3 + d1) * 3 + d2;
+            // (deliberately unsynchronised: every thread that finds ~0u looks the tile up itself and all of them store the same slot —
+            //  compute-sanitizer's racecheck reports this read / write pair, profiles/README.md)
             uint32_t slot = ((volatile uint32_t*)s_cache)[at];
             if (slot == ~0u) {   // the first particle(s) of this tile that reach the block look its tile up (or create it)
               slot = tile_slot_find_or_insert(bn.T, tile_key_pack(b0, b1, b2, 0u), bn.S);
