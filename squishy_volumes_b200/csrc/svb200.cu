@@ -253,6 +253,27 @@ int set_device(SvbHandle* h) {
   return 0;
 }
 
+// CUDA loads a kernel's code lazily, at its first launch, and that load synchronises with the kernels that are running — a deadlock
+// when the running kernel is an exchange sender spinning on a counter that only the kernel being loaded will tick (observed: the
+// first G2P of a slab run never started while the migration sender waited for its boundary tiles, until the sender's 2 s timeout).
+// Every kernel that can be launched next to a waiting one is therefore loaded up front.
+int preload_kernels(SvbHandle* h) {
+  cudaFuncAttributes a;
+#define SVB_PRELOAD(fn) CK(cudaFuncGetAttributes(&a, fn))
+  SVB_PRELOAD(k_begin); SVB_PRELOAD(k_bin<false>); SVB_PRELOAD(k_bin<true>); SVB_PRELOAD(k_offsets); SVB_PRELOAD(k_invert_zero); SVB_PRELOAD(k_touch_nodes);
+  SVB_PRELOAD(k_collide_query); SVB_PRELOAD(k_meld); SVB_PRELOAD(k_mesh_lerp); SVB_PRELOAD(k_mesh_tri_normals); SVB_PRELOAD(k_mesh_vertex_normals);
+  SVB_PRELOAD((k_collide_cand<1, 1, false>)); SVB_PRELOAD((k_collide_cand<1, 4, true>)); SVB_PRELOAD((k_collide_cand<2, 1, false>)); SVB_PRELOAD((k_collide_cand<2, 4, true>));
+  SVB_PRELOAD((k_collide_cand<4, 1, false>)); SVB_PRELOAD((k_collide_cand<4, 4, true>)); SVB_PRELOAD((k_collide_cand<16, 1, false>)); SVB_PRELOAD((k_collide_cand<16, 4, true>));
+  SVB_PRELOAD(k_p2g<false>); SVB_PRELOAD(k_p2g<true>);
+  SVB_PRELOAD((k_g2p<true, false, true, true, false>)); SVB_PRELOAD((k_g2p<true, false, false, true, true>)); SVB_PRELOAD((k_g2p<true, false, false, true, false>));
+  SVB_PRELOAD((k_g2p<true, false, true, false, false>)); SVB_PRELOAD((k_g2p<true, false, false, false, true>)); SVB_PRELOAD((k_g2p<true, false, false, false, false>));
+  SVB_PRELOAD((k_g2p<false, true, true, false, false>)); SVB_PRELOAD((k_g2p<false, true, false, false, false>));
+  SVB_PRELOAD(k_advance<true>); SVB_PRELOAD(k_advance<false>); SVB_PRELOAD(k_limit_force); SVB_PRELOAD(k_dt_open); SVB_PRELOAD(k_dt_integrate); SVB_PRELOAD(k_dt_tail);
+  SVB_PRELOAD(k_halo_send2); SVB_PRELOAD(k_halo_recv2); SVB_PRELOAD(k_migrate_send_list); SVB_PRELOAD(k_migrate_recv); SVB_PRELOAD(k_note_outside); SVB_PRELOAD(k_column_histogram);
+#undef SVB_PRELOAD
+  return 0;
+}
+
 // everything queued for this handle, the exchange senders on the second stream included
 cudaError_t sync_streams(SvbHandle* h) {
   cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -717,8 +738,17 @@ int process_front_p2p(SvbHandle* h) {
   const StepScalars& r = *L.host;
   if (r.status & ST_KEY_RANGE) return fail(h, SVB_KEY_RANGE, "a live particle lies outside the +-2^18 grid-cell range of the tile keys (or crossed more than one slab in a substep)");
   if (r.status & ST_TILE_OVERFLOW) return fail(h, SVB_COMM_ERROR, "tile capacity exceeded on a slab rank (%u tiles > %zu)", r.n_tiles, h->tile_cap);
-  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW))   // raised by an earlier substep's back half and carried forward
-    return fail(h, SVB_COMM_ERROR, r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room");
+  if (r.status & (ST_COMM_TIMEOUT | ST_COMM_OVERFLOW)) {   // raised by an earlier substep's back half and carried forward
+    StepScalars both[2];
+    uint32_t tr[16] = {};
+    sync_streams(h);
+    cudaMemcpy(both, h->scalars.p, sizeof both, cudaMemcpyDeviceToHost);
+    cudaMemcpyFromSymbol(tr, g_exchange_trace, sizeof tr);
+    return fail(h, SVB_COMM_ERROR, "%s (rank %d, message %u; last message numbers seen by halo send in/waited/published %u %u %u, halo recv in/got %u %u, migrate send in/waited/published %u %u %u, migrate recv in/got %u %u; scalars halves: boundary tiles %u / %u, interior %u / %u, ticks P2G %u / %u, G2P %u / %u, status 0x%x / 0x%x)",
+                r.status & ST_COMM_TIMEOUT ? "a neighbour slab's message did not arrive" : "a slab mailbox or the particle buffer ran out of room", h->rank, h->slab_seq, tr[0], tr[1], tr[2], tr[3],
+                tr[4], tr[5], tr[6], tr[7], tr[8], tr[9], both[0].n_work[0], both[1].n_work[0], both[0].n_work[1], both[1].n_work[1], both[0].boundary_done[0], both[1].boundary_done[0], both[0].boundary_done[1], both[1].boundary_done[1], both[0].status,
+                both[1].status);
+  }
   if (r.sticky) {  // the previous substep failed somewhere: this one and everything queued behind it were no-ops on every rank
     h->status |= (r.sticky | r.accum) & 0xffffu;
     CK(sync_streams(h));
@@ -849,9 +879,8 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
       peers.err_val[r] = &ph->err_val[h->rank];
     }
   // (the rows G2P writes live in the OTHER buffer until `cur` is swapped below)
-  // (the migration sender next to G2P — gated by G2P's boundary tiles like the halo sender is by P2G's — timed out on 2 GPUs for a
-  //  reason not yet understood; until then it follows G2P on the main stream unless SVB_MIGRATE_BESIDE_G2P=1)
-  static const bool migrate_beside = [] { const char* e = std::getenv("SVB_MIGRATE_BESIDE_G2P"); return e && e[0] == '1'; }();
+  // (SVB_MIGRATE_BESIDE_G2P=0 puts the migration sender back behind G2P on the main stream, for A/B runs)
+  static const bool migrate_beside = [] { const char* e = std::getenv("SVB_MIGRATE_BESIDE_G2P"); return !(e && e[0] == '0'); }();
   const bool send_beside_g2p = concurrent && !in.adaptive && migrate_beside;
   if (send_beside_g2p) {   // second stream: the migration sender, gated on the device by G2P's boundary tiles
     k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0], work_parts(h, 5));
@@ -1016,6 +1045,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(cudaMallocHost(&h->h_dt, sizeof(DtState)));
   CK(h->dt_state.ensure(sizeof(DtState)));
   CK(cudaMemsetAsync(h->dt_state.p, 0, sizeof(DtState), h->stream));
+  if (int rc = preload_kernels(h)) return rc;
   CK(cudaFuncSetAttribute(k_p2g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
   CK(cudaFuncSetAttribute(k_p2g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2G_SMEM));
   const uint32_t n = (uint32_t)p->n;

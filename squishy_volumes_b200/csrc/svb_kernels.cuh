@@ -1694,6 +1694,10 @@ __global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, DtState* D, 
   }
 }
 
+// progress markers of the exchange kernels (message numbers), read by the host when an exchange times out (diagnostics only)
+__device__ uint32_t g_exchange_trace[16];
+#define SVB_TRACE(k, v) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_exchange_trace[k] = (v); } while (0)
+
 // ------------------------------------------------------------------------------------------------
 // multi-GPU slabs (no reference counterpart).  A rank owns the particles whose base
 // node lies in block columns [lo, hi) along x.
@@ -1776,6 +1780,7 @@ __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restric
   // a run that was stopped by an earlier substep (sticky is the same word on every rank: error words are exchanged, stop bits come
   // from identical clocks) exchanges nothing: every rank skips the same messages, however many no-op substeps its host queued
   if (S->sticky) return;
+  SVB_TRACE(0, seq);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   if (done && !SVB_ABORTED(S)) {
@@ -1785,6 +1790,7 @@ __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restric
     __syncthreads();
     if (!s_ok && threadIdx.x == 0) atomicOr(const_cast<uint32_t*>(&S->status), ST_COMM_TIMEOUT);
   }
+  SVB_TRACE(1, seq);
   if (!SVB_ABORTED(S)) {
     const uint32_t n_tiles = min(S->n_tiles, T.tile_cap);
     for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles; t += warps) {
@@ -1824,12 +1830,14 @@ __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restric
       local[side] = 0;
     }
     local[2] = 0;
+    g_exchange_trace[2] = seq;
   }
 }
 __global__ void __launch_bounds__(256) k_halo_recv2(StepScalars* S, TileTable T, unsigned long long* layer_slots, uint32_t* layer_list, float4* __restrict__ grid, const HaloEntry* __restrict__ in_left,
                                                     const HaloEntry* __restrict__ in_right, const SlabHeader* __restrict__ hdr, int has_left, int has_right, uint32_t seq) {
   __shared__ uint32_t s_count[2];
   if (S->sticky) return;   // stopped run: nothing was sent (see k_halo_send2)
+  SVB_TRACE(3, seq);
   if (threadIdx.x == 0) {
     const int has[2] = {has_left, has_right};
     for (int side = 0; side < 2; ++side) {
@@ -1845,6 +1853,7 @@ __global__ void __launch_bounds__(256) k_halo_recv2(StepScalars* S, TileTable T,
   }
   __syncthreads();
   const uint32_t cl = s_count[0], total = cl + s_count[1];
+  SVB_TRACE(4, seq);
   if (SVB_ABORTED(S)) return;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -1912,6 +1921,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
                                                            uint32_t* __restrict__ blocks_done, int between_substeps, const uint32_t* done, const uint32_t* n_boundary, uint32_t parts) {
   __shared__ uint32_t s_c[2];
   if (!between_substeps && S->sticky) return;   // stopped run: no message (see k_halo_send2)
+  SVB_TRACE(5, seq);
   if (done && !SVB_ABORTED(S)) {
     // launched next to G2P on a second stream: only boundary tiles hold particles that can leave the slab
     __shared__ int s_ok;
@@ -1919,6 +1929,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
     __syncthreads();
     if (!s_ok && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_TIMEOUT);
   }
+  SVB_TRACE(6, seq);
   if (threadIdx.x < 2) s_c[threadIdx.x] = atomicAdd(&mc.counts[threadIdx.x], 0u);
   __syncthreads();
   const uint32_t c0 = s_c[0], c1 = s_c[1];
@@ -1953,6 +1964,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
     for (int r = 0; r < peers.n_ranks; ++r)
       if (peers.err_val[r]) { st_sys(peers.err_val[r], err); st_sys(peers.err_seq[r], seq); }
     *blocks_done = 0;
+    g_exchange_trace[7] = seq;
   }
 }
 // receiving side: append the neighbours' rows behind this rank's rows, publish the new row count on the device,
@@ -1962,6 +1974,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
                                                       int between_substeps, SimConsts K, BinNext bn, int bin) {
   __shared__ uint32_t s_c[2];
   if (!between_substeps && S->sticky) return;   // stopped run: nothing was sent (see k_halo_send2)
+  SVB_TRACE(8, seq);
   if (threadIdx.x == 0) {
     uint32_t c[2] = {0, 0};
     const int has[2] = {has_left, has_right};
@@ -1984,6 +1997,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
     }
   }
   __syncthreads();
+  SVB_TRACE(9, seq);
   const uint32_t cl = s_c[0], cr = s_c[1];
   // after a substep the rows are the re-binned ones; a rebalance between substeps appends behind whatever is resident
   const uint32_t base = between_substeps ? *n_dev : S->n_live + S->n_tomb;
