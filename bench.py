@@ -39,7 +39,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from squishy_volumes_b200 import scenes  # noqa: E402
+from squishy_volumes_b200 import abi as _abi, scenes  # noqa: E402
 from squishy_volumes_b200.types import RunParameters  # noqa: E402
 
 METRIC = "particle-substeps/sec"
@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--adaptive", action="store_true", help="adaptive time steps (the reference's default mode); max_time_step = 4 x the scene's fixed dt")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (development A/B runs)")
+    ap.add_argument("--length", type=int, default=0, help="development: jelly_collision stretched along x like the weak-scaling scene of that many GPUs, whatever N is")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
@@ -277,7 +278,7 @@ def main():
     # N > 1.  jelly_collision (the default workload): weak scaling — the blocks grow along x with the GPU count, 1.02 M particles
     # per GPU.  Every other scene, or --strong: ONE scene of the named size is cut into N slabs (BASELINE configs 4 and 5).
     weak = world_env > 1 and args.scene == "jelly_collision" and not args.strong
-    scene = make_scene(args.scene, args.scale, length=world_env if weak else 1)
+    scene = make_scene(args.scene, args.scale, length=args.length or (world_env if weak else 1))
     scene.frame_input.consts.frames_per_second = 1  # one long frame: the bench never crosses a keyframe boundary
     dt = scene.time_step
     max_dt = 4.0 * dt if args.adaptive else dt
@@ -352,11 +353,17 @@ def main():
         inner.snapshot()                                      # device-side copy: the extra passes below repeat exactly the timed one
     launches0 = inner.kernel_launches
     sub0 = state.substeps
+    if world > 1:
+        inner.exchange_waits(reset=True)
     barrier(dist, local)
+    waits = None
     with ClockSampler(local) as clocks:
         state.advance(None, fi, run_params(state, steps))
         ms = inner.last_advance_ms
         done = state.substeps - sub0
+        if world > 1:
+            waits = {k: round(v / max(done, 1), 5) for k, v in inner.exchange_waits().items()}
+            waits["resident_rows_at_end"] = int(_abi.load().svb_particle_count(inner._h))
         barrier(dist, local)
         gpu_launches = inner.kernel_launches - launches0
         # the timed pass lasts tens of milliseconds, one nvidia-smi query a good part of a second: keep the same load on the GPU
@@ -411,6 +418,11 @@ def main():
                 "stage_ms_per_substep": stages, "stage_note": "rank 0, instrumented pass (one event pair and a sync per stage)"}
     if stages_by_rank is not None:
         roofline["stage_ms_per_substep_by_rank"] = stages_by_rank   # exchange stages include the wait for the neighbour
+        gathered = [None] * world
+        dist.all_gather_object(gathered, waits)
+        # the timed region itself: time the exchange kernels spent waiting, per substep, by device-side clocks.  The two "send_for_*_boundary"
+        # waits run on the second stream beside the interior tiles; the "recv" waits are the ones that stall a rank
+        roofline["exchange_wait_ms_per_substep_by_rank"] = gathered
     state.close()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": int(done), "warmup": warmup, "ms_per_step": ms_max / done, "higher_is_better": True,

@@ -165,6 +165,12 @@ int32_t svb_active_blocks(SvbHandle* h, int32_t* block_ids /* n*3 */, uint32_t* 
  * gpu/src/profiler_output.rs:93-192).  Returns the number of stages; names are static strings. */
 int32_t svb_stage_times(SvbHandle* h, const char** names, float* ms, int32_t cap);
 void svb_enable_stage_timing(SvbHandle* h, int32_t on);
+/* Slab ranks: milliseconds the exchange kernels of this rank's device have spent WAITING since the last reset, measured on the device
+ * (%globaltimer around the spin loops): [0] halo sender for P2G's boundary tiles, [1] halo receiver for the neighbours' columns,
+ * [2] migration sender for G2P's boundary tiles, [3] migration receiver for the neighbours' rows, [4] ... for every rank's error
+ * word, [5] adaptive steps: the other ranks' limit reductions.  [0] and [2] are waits of the second stream (hidden behind the interior
+ * tiles); [1], [3], [4], [5] stall the main stream.  Synchronises.  Returns the number of entries (6).  No reference counterpart. */
+int32_t svb_exchange_waits(SvbHandle* h, double* ms, int32_t cap, int32_t reset);
 /* Options by name: "store_grid" (CpuRunParameters::store_grid: exact contributor masks for svb_download_grid),
  * "global_particles" (slab ranks: size of the original-order keyframe arrays), "murmur_table_hash" (hash the tile table with the
  * reference's murmur node key instead of the 64-bit mixer; results do not depend on it). */

@@ -109,6 +109,8 @@ def load():
     L.svb_active_blocks.argtypes = [vp, cs.c_i32p, cs.c_u32p]
     L.svb_stage_times.restype = C.c_int32
     L.svb_stage_times.argtypes = [vp, C.POINTER(C.c_char_p), cs.c_f32p, C.c_int32]
+    L.svb_exchange_waits.restype = C.c_int32
+    L.svb_exchange_waits.argtypes = [vp, C.POINTER(C.c_double), C.c_int32, C.c_int32]
     L.svb_enable_stage_timing.restype = None
     L.svb_enable_stage_timing.argtypes = [vp, C.c_int32]
     L.svb_set_option.restype = None

@@ -239,7 +239,7 @@ int ensure_tile_capacity(SvbHandle* h, size_t tiles) {
     f.fresh = true;  // new allocations: the next use memsets them instead of undoing the previous one
   }
   CK(h->grid.ensure(c * 64 * 16));
-  CK(h->work_list.ensure(2 * c * 4));
+  CK(h->work_list.ensure((size_t)WORK_CLASSES * c * 4));
   CK(h->node_mask.ensure(c * 8));
   CK(h->node_offset.ensure((c + 1) * 4));
   h->tile_cap = c;
@@ -260,7 +260,7 @@ int set_device(SvbHandle* h) {
 int preload_kernels(SvbHandle* h) {
   cudaFuncAttributes a;
 #define SVB_PRELOAD(fn) CK(cudaFuncGetAttributes(&a, fn))
-  SVB_PRELOAD(k_begin); SVB_PRELOAD(k_bin<false>); SVB_PRELOAD(k_bin<true>); SVB_PRELOAD(k_offsets); SVB_PRELOAD(k_invert_zero); SVB_PRELOAD(k_touch_nodes);
+  SVB_PRELOAD(k_begin); SVB_PRELOAD(k_bin<false>); SVB_PRELOAD(k_bin<true>); SVB_PRELOAD(k_offsets); SVB_PRELOAD(k_invert_zero<1>); SVB_PRELOAD(k_invert_zero<4>); SVB_PRELOAD(k_touch_nodes);
   SVB_PRELOAD(k_collide_query); SVB_PRELOAD(k_meld); SVB_PRELOAD(k_mesh_lerp); SVB_PRELOAD(k_mesh_tri_normals); SVB_PRELOAD(k_mesh_vertex_normals);
   SVB_PRELOAD((k_collide_cand<1, 1, false>)); SVB_PRELOAD((k_collide_cand<1, 4, true>)); SVB_PRELOAD((k_collide_cand<2, 1, false>)); SVB_PRELOAD((k_collide_cand<2, 4, true>));
   SVB_PRELOAD((k_collide_cand<4, 1, false>)); SVB_PRELOAD((k_collide_cand<4, 4, true>)); SVB_PRELOAD((k_collide_cand<16, 1, false>)); SVB_PRELOAD((k_collide_cand<16, 4, true>));
@@ -358,7 +358,8 @@ int enqueue_front(SvbHandle* h, const StepInputs& in, bool redo) {
   stage_end(h);
   stage_begin(h, ST_OFFSETS);
   const uint32_t lag = std::max<uint32_t>(h->n_ptiles, 1024);
-  const SlabColumns cols = h->p2p ? SlabColumns{h->slab_lo, h->slab_hi, h->work_list.as<uint32_t>()} : SlabColumns{0, 0, nullptr};
+  static const bool by_size = [] { const char* e = std::getenv("SVB_WORK_ORDER"); return !(e && e[0] == '0'); }();
+  const SlabColumns cols{h->slab_lo, h->slab_hi, h->work_list.as<uint32_t>(), h->p2p ? 1 : 0, by_size ? 1 : 0};
   const uint32_t offsets_grid = std::min<uint32_t>(blocks_for((uint64_t)lag * 32 * 2, 256), 148 * 8);
   if (ahead && !h->slabs && !h->timing)   // straight behind the previous substep's G2P: a programmatic dependent of it
     CK(launch_dependent(k_offsets, dim3(offsets_grid), dim3(256), 0, s, S, S_prev, n, (const uint32_t*)nullptr, T, F.cell_count.as<uint32_t>(), F.tile_start.as<uint2>(), F.slot_first.as<uint32_t>(),
@@ -389,9 +390,14 @@ int enqueue_rebin(SvbHandle* h, bool prepare_next) {
     prep = PrepareNext{scalars_of(h, nx), tile_table(h, nx), N.cell_count.as<uint32_t>(), N.tile_touch.as<uint32_t>(), n, h->p2p ? h->n_dev : nullptr, N.fresh ? 1 : 0, 74u};
     N.fresh = false;
   }
-  const uint32_t invert_blocks = blocks_for(n, 256);
-  k_invert_zero<<<invert_blocks + 148 * 2 + prep.blocks, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), F.cell_count.as<uint32_t>(), F.slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n,
-                                                                      invert_blocks, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap, prep);
+  static const int rows_per_thread = [] { const char* e = std::getenv("SVB_INVERT_ROWS"); return e && e[0] == '1' ? 1 : 4; }();
+  const uint32_t invert_blocks = blocks_for(n, 256 * rows_per_thread);
+  if (rows_per_thread == 4)
+    k_invert_zero<4><<<invert_blocks + 148 * 2 + prep.blocks, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), F.cell_count.as<uint32_t>(), F.slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n,
+                                                                          invert_blocks, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap, prep);
+  else
+    k_invert_zero<1><<<invert_blocks + 148 * 2 + prep.blocks, 256, 0, s>>>(S, h->pcell.as<uint32_t>(), F.cell_count.as<uint32_t>(), F.slot_first.as<uint32_t>(), h->src_of.as<uint32_t>(), n,
+                                                                          invert_blocks, h->grid.as<float4>(), h->store_grid ? h->node_mask.as<unsigned long long>() : nullptr, (uint32_t)h->tile_cap, prep);
   LAUNCH_CHECK();
   h->masks_valid = false;
   if (h->store_grid) {
@@ -412,14 +418,23 @@ uint32_t work_parts(SvbHandle*, uint32_t) {
   static const int forced = [] { const char* e = std::getenv("SVB_PARTS"); return e ? std::atoi(e) : 0; }();
   return forced == 2 || forced == 4 ? (uint32_t)forced : 1u;
 }
+// ... and how many of the last tiles of a launch are cut that way: SVB_SPLIT_LAST (tiles; "all" = every tile)
+uint32_t work_split_last(int phase) {
+  static const uint32_t v = [] {
+    const char* e = std::getenv("SVB_SPLIT_LAST");
+    if (!e) return 0u;
+    return e[0] == 'a' ? 0xffffffffu : (uint32_t)std::atoi(e);
+  }();
+  return v ? v : 148u * (phase == 0 ? P2G_CTAS_PER_SM : 5);   // default: as many tiles as CTAs are resident = the launch's final wave
+}
 WorkList work_all(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{nullptr, 0u, &S->n_ptiles, &S->work_counter[phase], nullptr, tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5)};
+  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_class, &S->work_counter[phase], nullptr, tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5), work_split_last(phase)};
 }
 // boundary tiles first, then the interior ones; `phase` 0 = P2G, 1 = G2P (work cursor and boundary-done counter of the scalars)
 WorkList work_ordered(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_work, &S->work_counter[phase], &S->boundary_done[phase], tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5)};
+  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_class, &S->work_counter[phase], &S->boundary_done[phase], tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5), work_split_last(phase)};
 }
 
 int enqueue_p2g(SvbHandle* h, const StepInputs& in, const WorkList& W, uint32_t grid_cap = 148 * P2G_CTAS_PER_SM) {
@@ -1529,6 +1544,20 @@ int32_t svb_stage_times(SvbHandle* h, const char** names, float* ms, int32_t cap
     if (ms) ms[i] = h->stage_ms[i];
   }
   return ST_COUNT;
+}
+int32_t svb_exchange_waits(SvbHandle* h, double* ms, int32_t cap, int32_t reset) {
+  if (!h || h->multi) return SVB_BAD_ARGUMENT;
+  CK(cudaSetDevice(h->device));
+  if (int rc = sync_streams(h)) return rc;
+  unsigned long long ns[8] = {};
+  CK(cudaMemcpyFromSymbol(ns, g_wait_ns, sizeof ns));
+  for (int i = 0; i < 6 && i < cap; ++i)
+    if (ms) ms[i] = (double)ns[i] * 1e-6;
+  if (reset) {
+    unsigned long long zero[8] = {};
+    CK(cudaMemcpyToSymbol(g_wait_ns, zero, sizeof zero));
+  }
+  return 6;
 }
 void svb_enable_stage_timing(SvbHandle* h, int32_t on) {
   if (h && h->multi) return;

@@ -94,6 +94,7 @@ constexpr uint32_t ST_COMM_TIMEOUT = 0x20000000u;   // slab ranks: a neighbour's
 constexpr uint32_t ST_COMM_OVERFLOW = 0x10000000u;  // slab ranks: a mailbox or the particle buffer ran out of room
 constexpr uint32_t ST_ZERO_DT = 0x08000000u;        // adaptive steps: the allowed time step became 0 inside a substep (the rest of it must not run)
 constexpr uint32_t ST_ABORT_MASK = ST_KEY_RANGE | ST_TILE_OVERFLOW | ST_COMM_TIMEOUT | ST_COMM_OVERFLOW | ST_ZERO_DT;
+constexpr int WORK_CLASSES = 16;
 struct StepScalars {
   uint32_t n;          // resident particles (incl. tombstoned)
   uint32_t n_live;     // particles with a bin (not tombstoned)
@@ -106,6 +107,8 @@ struct StepScalars {
   uint32_t status;     // SVB_* simulation-level bits | ST_*
   uint32_t work_counter[4];  // tile claims: [0] P2G, [1] G2P (all tiles, or a slab rank's boundary tiles), [2] / [3] the same for its interior tiles
   uint32_t n_work[2];        // slab ranks: particle tiles in the boundary / interior work list (k_offsets)
+  uint32_t n_class[WORK_CLASSES];   // particle tiles by work class (k_offsets): boundary tiles in classes [0, 8), the others in [8, 16), inside
+                             // each half by falling particle count (class = 7 - min(7, count / 128)): P2G / G2P claim the heavy tiles first
   uint32_t boundary_done[2]; // slab ranks: boundary tiles P2G / G2P have finished (the concurrent exchange senders wait for n_work[0])
   uint32_t bin_blocks_done;  // k_bin blocks finished: the last one publishes n_ptiles
   uint32_t n_candidates;     // particles whose BVH leaf holds a few triangles within reach (k_collide_query -> k_collide_cand, one thread each)

@@ -24,6 +24,21 @@ namespace svb {
 // must not touch anything that kernel wrote before this returns.  A no-op under an ordinary launch.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// nanoseconds the exchange kernels of this device spent waiting, by kind (svb_exchange_waits): [0] halo sender for P2G's boundary tiles,
+// [1] halo receiver for the neighbours' columns, [2] migration sender for G2P's boundary tiles, [3] migration receiver for the
+// neighbours' rows, [4] ... for every rank's error word, [5] time-step reductions of the other ranks
+__device__ unsigned long long g_wait_ns[8];
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct WaitClock {   // block 0 accounts for the whole kernel: its waiting thread sees the same counters as every other block's
+  unsigned long long t0;
+  int kind;
+  __device__ __forceinline__ WaitClock(int k) : t0(blockIdx.x == 0 ? global_timer_ns() : 0ull), kind(k) {}
+  __device__ __forceinline__ void stop() { if (blockIdx.x == 0) atomicAdd(&g_wait_ns[kind], global_timer_ns() - t0); }
+};
 __device__ __forceinline__ int floor_div4(int v) { return v >> 2; }
 __device__ __forceinline__ int ceil_log2_u32(uint32_t v) {  // bits needed to represent values 0..v-1
   return v <= 1 ? 0 : 32 - __clz(v - 1);
@@ -641,34 +656,63 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
 // boundary tiles and ships the halo column / the leavers while the interior tiles are still being worked on — so the neighbour's
 // message is long there when the receiving kernel that follows P2G / G2P on the main stream asks for it.
 struct WorkList {
-  const uint32_t* ids;       // boundary tile ids from 0, interior tile ids from `split`; null: the tile ids [0, *count) themselves
-  uint32_t split;            // offset of the interior list inside `ids` (the tile capacity)
-  const uint32_t* count;     // ids == null: number of tiles; else count[0] = boundary tiles, count[1] = interior tiles
+  const uint32_t* ids;       // WORK_CLASSES lists of tile ids, list c from c * split
+  uint32_t split;            // the tile capacity
+  const uint32_t* count;     // n_class[WORK_CLASSES] of the substep's scalars: final before P2G starts
   uint32_t* cursor;
   uint32_t* done;            // boundary work items finished so far (null: nobody waits)
   int tail;                  // G2P: this launch also carries the tombstoned rows over
   // A work item is a tile, or 1 / `parts` of its particle run (parts = 1, 2 or 4: particles [k, k + 1) * 512 / parts of the run, the
-  // last part up to the run's end): at 1 M particles a GPU holds only ~2.6 tiles per resident P2G CTA, so whole-tile items leave
-  // most SMs idle while the last CTAs finish their third tile; finer items fill that tail (at 8 M particles whole tiles are best).
-  uint32_t parts;
+  // last part up to the run's end): at 1 M particles a GPU holds only ~3.5 tiles per resident P2G CTA and a tile keeps a CTA busy for
+  // ~17 us, so whole-tile items leave SMs idle while the last CTAs finish; every item also pays ~3 us of dependent round trips, so
+  // only the LAST `split_last` tiles a launch hands out are cut (its final wave), the others stay whole.
+  uint32_t parts, split_last;
 };
+// Items are handed out class by class: boundary tiles first (the concurrent sender waits for them), and inside both halves the
+// heaviest tiles first — longest-processing-time-first list scheduling, so the last items a launch hands out are its lightest and
+// the CTAs finish together (a compressed region holds tiles of 700+ particles next to surface tiles of 64: in arrival order one
+// heavy tile claimed last cost a slab rank at the collision interface 45 % more P2G / G2P time for 13 % more particles).
+// `ends`: shared memory, inclusive prefix sums of the class counts (work_prefix, before the first claim).
+__device__ __forceinline__ void work_prefix(const WorkList& W, uint32_t* ends) {
+  if (threadIdx.x == 0) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < WORK_CLASSES; ++c) { acc += W.count[c]; ends[c] = acc; }
+  }
+}
 // -> tile id (0xffffffff: no work left) and which part of its run; `boundary`: an item whose completion the concurrent sender counts
-__device__ __forceinline__ uint32_t work_claim(const WorkList& W, bool& boundary, uint32_t& part) {
+// `part` = which part | number of parts << 8; `tick`: what the item's completion adds to W.done when it belongs to a boundary tile (a
+// whole tile counts `parts`, a part 1: the sender waits for boundary tiles * parts), 0 for an interior item
+__device__ __forceinline__ uint32_t work_claim(const WorkList& W, const uint32_t* ends, uint32_t& tick, uint32_t& part) {
   const uint32_t item = atomicAdd(W.cursor, 1u);
-  const uint32_t q = item / W.parts;
-  part = item - q * W.parts;
-  boundary = false;
-  if (!W.ids) return q < W.count[0] ? q : 0xffffffffu;
-  const uint32_t nb = W.count[0];
-  if (q < nb) { boundary = true; return W.ids[q]; }
-  return q - nb < W.count[1] ? W.ids[W.split + (q - nb)] : 0xffffffffu;
+  const uint32_t total = ends[WORK_CLASSES - 1];
+  const uint32_t n_whole = total - min(W.parts > 1 ? W.split_last : 0u, total);
+  uint32_t q = item, nparts = 1;
+  part = 1u << 8;
+  if (item >= n_whole) {
+    const uint32_t r = item - n_whole;
+    q = n_whole + r / W.parts;
+    nparts = W.parts;
+    part = (r - (q - n_whole) * W.parts) | (W.parts << 8);
+  }
+  tick = 0;
+  if (q >= total) return 0xffffffffu;
+  uint32_t cls = 0, base = 0;
+#pragma unroll
+  for (int c = 0; c < WORK_CLASSES - 1; ++c) {
+    const uint32_t e = ends[c];
+    if (q >= e) { cls = c + 1; base = e; }
+  }
+  if (cls < WORK_CLASSES / 2) tick = nparts == 1 ? W.parts : 1u;
+  return W.ids[(size_t)cls * W.split + (q - base)];
 }
 // the particle sub-range of a work item
-__device__ __forceinline__ uint2 work_range(const WorkList& W, uint2 run, uint32_t part) {
-  if (W.parts == 1) return run;
-  const uint32_t span = 512u / W.parts;
-  const uint32_t s = run.x + part * span;
-  const uint32_t e = part + 1 == W.parts ? run.y : min(run.y, s + span);
+__device__ __forceinline__ uint2 work_range(uint2 run, uint32_t part) {
+  const uint32_t nparts = part >> 8, k = part & 0xffu;
+  if (nparts == 1) return run;
+  const uint32_t span = 512u / nparts;
+  const uint32_t s = run.x + k * span;
+  const uint32_t e = k + 1 == nparts ? run.y : min(run.y, s + span);
   return make_uint2(min(s, run.y), max(e, min(s, run.y)));
 }
 // the sender's side: true once `*done` has reached `*count * parts` (gives up after ~2 s like wait_seq)
@@ -684,7 +728,9 @@ __device__ __forceinline__ bool wait_boundary_done(const uint32_t* done, const u
 }
 struct SlabColumns {
   int lo, hi;
-  uint32_t* list;          // [2 * tile_cap]: boundary tile ids from 0, interior tile ids from tile_cap; null on a single GPU
+  uint32_t* list;          // [WORK_CLASSES * tile_cap]: the work lists (WorkList)
+  int slab;                // peer-memory slab rank: tiles of block columns lo and hi - 1 are boundary tiles
+  int by_size;             // 0: one class per half, tiles in arrival order (SVB_WORK_ORDER=0, for A/B runs)
 };
 // `Sprev` != null: this substep's set was filled ahead of time by the previous substep's G2P, so this is the FIRST kernel of the substep
 // and it folds what the previous substep's back half raised (a FAILED particle, table status bits, exchange errors) into this
@@ -734,13 +780,16 @@ __global__ void __launch_bounds__(256) k_offsets(StepScalars* S, const StepScala
       const uint32_t first = atomicAdd(&S->n_live, inc);
       tile_range[t] = make_uint2(first, first + inc);
       slot_first[slot] = first;
-      if (cols.list) {
+      int which = 1;
+      if (cols.slab) {
         int bx, by, bz;
         uint32_t layer;
         tile_key_unpack(T.tile_key[t], bx, by, bz, layer);
-        const int which = (bx == cols.lo || bx == cols.hi - 1) ? 0 : 1;
-        cols.list[(size_t)which * T.tile_cap + atomicAdd(&S->n_work[which], 1u)] = t;
+        which = (bx == cols.lo || bx == cols.hi - 1) ? 0 : 1;
+        atomicAdd(&S->n_work[which], 1u);
       }
+      const uint32_t cls = (uint32_t)which * (WORK_CLASSES / 2) + (cols.by_size ? 7u - min(7u, inc >> 7) : 0u);
+      cols.list[(size_t)cls * T.tile_cap + atomicAdd(&S->n_class[cls], 1u)] = t;
     }
     if (lane < 8) nbr[(size_t)t * 8 + lane] = r;
   }
@@ -800,6 +849,7 @@ struct PrepareNext {
   StepScalars* S; TileTable T; uint32_t* cell_count; uint32_t* tile_touch;
   uint32_t n; const uint32_t* n_dev; int tables_fresh; uint32_t blocks;
 };
+template <int R>
 __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S, const uint32_t* __restrict__ pcell, uint32_t* __restrict__ cell_offset,
                                                      const uint32_t* __restrict__ slot_first, uint32_t* __restrict__ src_of, uint32_t n, uint32_t invert_blocks, float4* __restrict__ grid,
                                                      unsigned long long* __restrict__ node_mask, uint32_t tile_cap, PrepareNext prep) {
@@ -819,21 +869,35 @@ __global__ void __launch_bounds__(256) k_invert_zero(StepScalars* __restrict__ S
     return;
   }
   // the rank of a particle inside its cell is handed out HERE, from the cell's offset used as a cursor (one atomic per distinct
-  // cell per warp: consecutive rows share cells) — the binning itself only counted, so the kernels that bin never wait on an atomic
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // cell per warp: consecutive rows share cells) — the binning itself only counted, so the kernels that bin never wait on an atomic.
+  // Every row is a chain of three dependent round trips (cell word -> cursor atomic -> the tile's first slot): a thread carries R
+  // rows through it side by side, so that one wave of CTAs covers the rows instead of R.
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t ci = i < min(n, S->n) ? pcell[i] : 0xfffffffeu;
-  const bool binned = ci < 0xfffffffdu, tomb = ci == 0xffffffffu;
-  const unsigned peers = __match_any_sync(SVB_FULL, ci);
-  const int leader = __ffs(peers) - 1;
-  uint32_t base = 0;
-  if ((int)lane == leader) {
-    if (binned) base = atomicAdd(&cell_offset[ci], (uint32_t)__popc(peers));
-    else if (tomb) base = atomicAdd(&S->tomb_cursor, (uint32_t)__popc(peers));
+  const uint32_t n_rows = min(n, S->n);
+  uint32_t row[R], ci[R], base[R];
+  unsigned peers[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    row[k] = (blockIdx.x * R + k) * blockDim.x + threadIdx.x;
+    ci[k] = row[k] < n_rows ? pcell[row[k]] : 0xfffffffeu;
   }
-  base = __shfl_sync(SVB_FULL, base, leader) + __popc(peers & ((1u << lane) - 1u));
-  if (binned) src_of[slot_first[ci >> 6] + base] = i;
-  else if (tomb) src_of[S->n_live + base] = i;   // (migrated away, or unbinned after an abort: no slot)
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    peers[k] = __match_any_sync(SVB_FULL, ci[k]);
+    base[k] = 0;
+    if ((int)lane == __ffs(peers[k]) - 1) {
+      if (ci[k] < 0xfffffffdu) base[k] = atomicAdd(&cell_offset[ci[k]], (uint32_t)__popc(peers[k]));
+      else if (ci[k] == 0xffffffffu) base[k] = atomicAdd(&S->tomb_cursor, (uint32_t)__popc(peers[k]));
+    }
+  }
+  uint32_t first[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) first[k] = ci[k] < 0xfffffffdu ? slot_first[ci[k] >> 6] : S->n_live;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t r = __shfl_sync(SVB_FULL, base[k], __ffs(peers[k]) - 1) + __popc(peers[k] & ((1u << lane) - 1u));
+    if (ci[k] < 0xfffffffdu || ci[k] == 0xffffffffu) src_of[first[k] + r] = row[k];   // (migrated away, or unbinned after an abort: no slot)
+  }
 }
 // ------------------------------------------------------------------------------------------------
 // P2G (scatter_momentum.rs:22-93).  One CTA per (block, layer) run of particles, claimed from a
@@ -917,12 +981,13 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tiles = reinterpret_cast<float4*>(smem_raw);
   float* stage_all = reinterpret_cast<float*>(smem_raw + P2G_WARPS * TILE_NODES * 16);
-  __shared__ uint32_t s_group, s_part;
+  __shared__ uint32_t s_group, s_part, s_ends[WORK_CLASSES];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* my_tile = tiles + warp * TILE_NODES;
   float* stage = stage_all + warp * 32 * STAGE_STRIDE;
   grid_dependency_wait();
   if (SVB_ABORTED(S)) return;
+  work_prefix(W, s_ends);
   if (force.D) {
     dt = force.D->allowed;
     force.dt = force.D->dt_force; force.gx = force.D->g[0]; force.gy = force.D->g[1]; force.gz = force.D->g[2]; force.factor_b = force.D->factor_b;
@@ -946,19 +1011,19 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   const float fli = (float)li, flj = (float)lj, flk = (float)lk;
   const int lane_tile_off = (li * 6 + lj) * 6 + lk;
 
-  bool ticking = false;   // thread 0: the tile just finished was a boundary tile
+  uint32_t ticking = 0;   // thread 0: the item just finished belonged to a boundary tile (its weight in W.done)
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) {
       // the previous tile's sums are in HBM (every thread's reductions precede the barrier above; one fence of the ticking thread
       // orders them before the tick): tell the concurrent halo sender
-      if (ticking && W.done) { __threadfence(); atomicAdd(W.done, 1u); }
-      s_group = work_claim(W, ticking, s_part);
+      if (ticking && W.done) { __threadfence(); atomicAdd(W.done, ticking); }
+      s_group = work_claim(W, s_ends, ticking, s_part);
     }
     __syncthreads();
     const uint32_t g = s_group;
     if (g == 0xffffffffu) break;
-    const uint2 range = work_range(W, group_range[g], s_part);
+    const uint2 range = work_range(group_range[g], s_part);
     const uint32_t start = range.x, end = range.y;
     if (start >= end) continue;   // (a short run has no particles for this part)
     for (int q = threadIdx.x; q < P2G_WARPS * TILE_NODES; q += blockDim.x) tiles[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1177,7 +1242,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
                                                         const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn,
                                                         const unsigned long long* __restrict__ tile_key, WorkList W) {
   __shared__ float4 tile[TILE_NODES];
-  __shared__ uint32_t s_group, s_part;
+  __shared__ uint32_t s_group, s_part, s_ends[WORK_CLASSES];
   __shared__ int s_nbr[8];
   // BIN: a particle moves less than a cell per substep, so its next tile is one of the 27 blocks around this CTA's tile: their table
   // slots (in the NEXT substep's set) are cached, the cell counts and touch masks of the tile's particles are collected in shared
@@ -1192,8 +1257,9 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
   }
   grid_dependency_wait();
   if (SVB_ABORTED(S)) return;
+  work_prefix(W, s_ends);
   const float h = K.h, inv_h = 1.f / K.h;
-  bool ticking = false;   // thread 0: the tile just finished was a boundary tile
+  uint32_t ticking = 0;   // thread 0: the item just finished belonged to a boundary tile (its weight in W.done)
   int red_vel = INT32_MIN, red_def = INT32_MAX;
   uint32_t failed = 0;
   for (;;) {
@@ -1212,8 +1278,8 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       uint32_t g0 = 0xffffffffu;
       if (threadIdx.x == 0) {
         // the previous tile's rows (and its leavers' list entries) are written: tell the concurrent migration sender
-        if (ticking && W.done) { __threadfence(); atomicAdd(W.done, 1u); }
-        s_group = g0 = work_claim(W, ticking, s_part);
+        if (ticking && W.done) { __threadfence(); atomicAdd(W.done, ticking); }
+        s_group = g0 = work_claim(W, s_ends, ticking, s_part);
       }
       g0 = __shfl_sync(0xffu, g0, 0);
       if (g0 != 0xffffffffu) s_nbr[threadIdx.x] = nbr[(size_t)g0 * 8 + threadIdx.x];
@@ -1228,7 +1294,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     if (BIN && threadIdx.x >= 32 && threadIdx.x < 32 + 27) s_cache[threadIdx.x - 32] = ~0u;   // (the flush above has read the old slots)
     const uint32_t g = s_group;
     if (g == 0xffffffffu) break;
-    const uint2 range = work_range(W, group_range[g], s_part);
+    const uint2 range = work_range(group_range[g], s_part);
     const uint32_t start = range.x, end = range.y;
     if (start >= end) continue;   // (a short run has no particles for this part)
     for (int t = threadIdx.x; t < TILE_NODES; t += blockDim.x) {
@@ -1464,6 +1530,7 @@ __device__ __forceinline__ bool dt_exchange(const DtPeers& P, int32_t& a, int32_
       st_sys(P.post_seq[r] + slot * stride_seq, P.exchange);
     }
   bool ok = true;
+  const unsigned long long t0 = global_timer_ns();
   for (int r = 0; r < P.n_ranks; ++r)
     if (r != P.rank) {
       if (!wait_seq(&P.mine->dt_seq[slot][r], P.exchange)) { ok = false; continue; }
@@ -1473,6 +1540,7 @@ __device__ __forceinline__ bool dt_exchange(const DtPeers& P, int32_t& a, int32_
       c = max(c, (int32_t)ld_sys((const uint32_t*)(v + 2)));
       d = max(d, (int32_t)ld_sys((const uint32_t*)(v + 3)));
     }
+  atomicAdd(&g_wait_ns[5], global_timer_ns() - t0);
   return ok;
 }
 
@@ -1786,7 +1854,7 @@ __global__ void __launch_bounds__(256) k_halo_send2(const StepScalars* __restric
   if (done && !SVB_ABORTED(S)) {
     // launched next to P2G on a second stream: the halo columns are complete once every boundary tile has been scattered
     __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary, parts) ? 1 : 0;
+    if (threadIdx.x == 0) { WaitClock wc(0); s_ok = wait_boundary_done(done, n_boundary, parts) ? 1 : 0; wc.stop(); }
     __syncthreads();
     if (!s_ok && threadIdx.x == 0) atomicOr(const_cast<uint32_t*>(&S->status), ST_COMM_TIMEOUT);
   }
@@ -1840,6 +1908,7 @@ __global__ void __launch_bounds__(256) k_halo_recv2(StepScalars* S, TileTable T,
   SVB_TRACE(3, seq);
   if (threadIdx.x == 0) {
     const int has[2] = {has_left, has_right};
+    WaitClock wc(1);
     for (int side = 0; side < 2; ++side) {
       uint32_t c = 0;
       if (has[side]) {
@@ -1850,6 +1919,7 @@ __global__ void __launch_bounds__(256) k_halo_recv2(StepScalars* S, TileTable T,
       }
       s_count[side] = c;
     }
+    wc.stop();
   }
   __syncthreads();
   const uint32_t cl = s_count[0], total = cl + s_count[1];
@@ -1925,7 +1995,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
   if (done && !SVB_ABORTED(S)) {
     // launched next to G2P on a second stream: only boundary tiles hold particles that can leave the slab
     __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = wait_boundary_done(done, n_boundary, parts) ? 1 : 0;
+    if (threadIdx.x == 0) { WaitClock wc(2); s_ok = wait_boundary_done(done, n_boundary, parts) ? 1 : 0; wc.stop(); }
     __syncthreads();
     if (!s_ok && threadIdx.x == 0) atomicOr(&S->status, ST_COMM_TIMEOUT);
   }
@@ -1978,6 +2048,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
   if (threadIdx.x == 0) {
     uint32_t c[2] = {0, 0};
     const int has[2] = {has_left, has_right};
+    WaitClock wc(3);
     for (int side = 0; side < 2; ++side)
       if (has[side]) {
         if (wait_seq(&hdr->mig_seq[side], seq)) {
@@ -1985,8 +2056,10 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
           if (c[side] & SLAB_OVERFLOW) { atomicOr(&S->status, ST_COMM_OVERFLOW); c[side] &= ~SLAB_OVERFLOW; }
         } else atomicOr(&S->status, ST_COMM_TIMEOUT);
       }
+    wc.stop();
     s_c[0] = c[0]; s_c[1] = c[1];
     if (blockIdx.x == 0) {
+      WaitClock we(4);
       uint32_t err = 0;
       for (int r = 0; r < n_ranks; ++r)
         if (r != rank) {
@@ -1994,6 +2067,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
           else atomicOr(&S->status, ST_COMM_TIMEOUT);
         }
       if (err) atomicOr(&S->sticky_new, err);
+      we.stop();
     }
   }
   __syncthreads();

@@ -207,6 +207,18 @@ class B200State:
         k = L.svb_stage_times(self._h, names, cs.fptr(ms), 32)
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
+    EXCHANGE_WAITS = ("halo_send_for_p2g_boundary", "halo_recv_for_neighbours", "migrate_send_for_g2p_boundary", "migrate_recv_for_neighbours",
+                      "migrate_recv_for_error_words", "time_step_reductions")
+
+    def exchange_waits(self, reset: bool = False) -> Dict[str, float]:
+        """Slab ranks: milliseconds this rank's exchange kernels have spent waiting since the last reset (device-side clocks)."""
+        L = abi.load()
+        ms = (C.c_double * 8)()
+        k = L.svb_exchange_waits(self._h, ms, 8, int(reset))
+        if k < 0:
+            raise FatalError(k, L.svb_last_error(self._h).decode())
+        return {self.EXCHANGE_WAITS[i]: float(ms[i]) for i in range(k)}
+
     def snapshot(self) -> None:
         rc = abi.load().svb_snapshot(self._h)
         if rc != 0:
