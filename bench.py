@@ -362,7 +362,7 @@ def main():
         ms = inner.last_advance_ms
         done = state.substeps - sub0
         if world > 1:
-            waits = {k: round(v / max(done, 1), 5) for k, v in inner.exchange_waits().items()}
+            waits = {k: (round(v / max(done, 1), 5) if not k.endswith("_tiles") else int(v)) for k, v in inner.exchange_waits().items()}
             waits["resident_rows_at_end"] = int(_abi.load().svb_particle_count(inner._h))
         barrier(dist, local)
         gpu_launches = inner.kernel_launches - launches0

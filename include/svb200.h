@@ -169,7 +169,8 @@ void svb_enable_stage_timing(SvbHandle* h, int32_t on);
  * (%globaltimer around the spin loops): [0] halo sender for P2G's boundary tiles, [1] halo receiver for the neighbours' columns,
  * [2] migration sender for G2P's boundary tiles, [3] migration receiver for the neighbours' rows, [4] ... for every rank's error
  * word, [5] adaptive steps: the other ranks' limit reductions.  [0] and [2] are waits of the second stream (hidden behind the interior
- * tiles); [1], [3], [4], [5] stall the main stream.  Synchronises.  Returns the number of entries (6).  No reference counterpart. */
+ * tiles); [1], [3], [4], [5] stall the main stream.  With cap >= 8 also [6] the number of particle tiles and [7] of active grid tiles
+ * of the last substep the host has looked at (plain counts).  Synchronises.  Returns the number of entries.  No reference counterpart. */
 int32_t svb_exchange_waits(SvbHandle* h, double* ms, int32_t cap, int32_t reset);
 /* Options by name: "store_grid" (CpuRunParameters::store_grid: exact contributor masks for svb_download_grid),
  * "global_particles" (slab ranks: size of the original-order keyframe arrays), "murmur_table_hash" (hash the tile table with the

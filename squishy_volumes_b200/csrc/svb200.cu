@@ -923,7 +923,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   }
   CK(cudaEventRecord(h->ev_b_end, sb));
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
-                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0, h->K, bn, bin_next ? 1 : 0);
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/0, h->K, bn, bin_next ? 1 : 0, peers);
   LAUNCH_CHECK();
   if (in.adaptive) {   // the clock moves on every rank alike (after the error words of this substep have been folded in)
     k_dt_tail<<<1, 1, 0, s>>>(D, S, dt_peers(h));
@@ -1553,11 +1553,12 @@ int32_t svb_exchange_waits(SvbHandle* h, double* ms, int32_t cap, int32_t reset)
   CK(cudaMemcpyFromSymbol(ns, g_wait_ns, sizeof ns));
   for (int i = 0; i < 6 && i < cap; ++i)
     if (ms) ms[i] = (double)ns[i] * 1e-6;
+  if (ms && cap >= 8) { ms[6] = (double)h->n_ptiles; ms[7] = (double)h->n_tiles; }   // (as of the last front half the host has looked at)
   if (reset) {
     unsigned long long zero[8] = {};
     CK(cudaMemcpyToSymbol(g_wait_ns, zero, sizeof zero));
   }
-  return 6;
+  return cap >= 8 ? 8 : 6;
 }
 void svb_enable_stage_timing(SvbHandle* h, int32_t on) {
   if (h && h->multi) return;
@@ -1982,7 +1983,7 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
   k_migrate_send_list<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 1, nullptr, nullptr, 1u);
   LAUNCH_CHECK();
   k_migrate_recv<<<148, 256, 0, s>>>(h->Pc(), h->energy.as<float>(), S, my_hdr, reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[0]), reinterpret_cast<const uint32_t*>(my_mb + h->mb_mig_off[1]),
-                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1, h->K, BinNext{}, 0);
+                                     has[0] ? 1 : 0, has[1] ? 1 : 0, h->rank, h->n_ranks, seq, h->n_dev, /*between_substeps=*/1, h->K, BinNext{}, 0, peers);
   h->binned_ahead = false;   // rows left and arrived: the bins made ahead describe another row set
   LAUNCH_CHECK();
   if (int rc = read_status(h)) return rc;

@@ -1978,7 +1978,7 @@ __global__ void __launch_bounds__(256) k_migrate_unpack(ParticleBuf P, float* __
   energy[i] = __uint_as_float(row[NFIELDS]);
 }
 // migration over peer memory.  Sending side: rows that left [lo, hi) go straight into the neighbour's mailbox;
-// the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
+// the last block publishes both counts and the sequence numbers.
 struct SlabPeers {
   uint32_t* rows[2];                     // neighbour mailbox: migrating rows (left / right neighbour), null at the domain ends
   uint32_t* count[2]; uint32_t* seq[2];
@@ -1986,7 +1986,8 @@ struct SlabPeers {
   int n_ranks;
 };
 // Sending side, driven by the lists k_g2p<SLAB> filled (slots whose advanced position left the slab): one thread per
-// migrating row; the last block publishes both counts, the sequence numbers and this rank's sticky error word (to every rank).
+// migrating row; the last block publishes both counts and the sequence numbers.  (This rank's error word is posted by
+// k_migrate_recv, which follows G2P on the main stream: this kernel may run BESIDE G2P, whose interior tiles can still raise one.)
 __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const float* __restrict__ energy, StepScalars* S, MigrateCut mc, SlabPeers peers, uint32_t cap, uint32_t seq,
                                                            uint32_t* __restrict__ blocks_done, int between_substeps, const uint32_t* done, const uint32_t* n_boundary, uint32_t parts) {
   __shared__ uint32_t s_c[2];
@@ -2030,21 +2031,24 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
       }
       mc.counts[side] = 0;
     }
-    const uint32_t err = (S->sticky | atomicOr(&S->sticky_new, 0u)) & 0xffffu;   // simulation-level errors only: stop bits are every rank's own
-    for (int r = 0; r < peers.n_ranks; ++r)
-      if (peers.err_val[r]) { st_sys(peers.err_val[r], err); st_sys(peers.err_seq[r], seq); }
     *blocks_done = 0;
     g_exchange_trace[7] = seq;
   }
 }
-// receiving side: append the neighbours' rows behind this rank's rows, publish the new row count on the device,
+// receiving side: post this rank's sticky error word to every rank (G2P / the advance of this substep are complete: this kernel
+// follows them on the main stream), append the neighbours' rows behind this rank's rows, publish the new row count on the device,
 // and fold every rank's error word into this rank's (a FAILED particle anywhere stops every rank after this substep)
 __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __restrict__ energy, StepScalars* S, const SlabHeader* __restrict__ hdr, const uint32_t* __restrict__ rows_left,
                                                       const uint32_t* __restrict__ rows_right, int has_left, int has_right, int rank, int n_ranks, uint32_t seq, uint32_t* __restrict__ n_dev,
-                                                      int between_substeps, SimConsts K, BinNext bn, int bin) {
+                                                      int between_substeps, SimConsts K, BinNext bn, int bin, SlabPeers peers) {
   __shared__ uint32_t s_c[2];
   if (!between_substeps && S->sticky) return;   // stopped run: nothing was sent (see k_halo_send2)
   SVB_TRACE(8, seq);
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)n_ranks && peers.err_val[threadIdx.x]) {
+    const uint32_t err = (S->sticky | S->sticky_new) & 0xffffu;   // simulation-level errors only: stop bits are every rank's own
+    st_sys(peers.err_val[threadIdx.x], err);
+    st_sys(peers.err_seq[threadIdx.x], seq);
+  }
   if (threadIdx.x == 0) {
     uint32_t c[2] = {0, 0};
     const int has[2] = {has_left, has_right};

@@ -208,7 +208,7 @@ class B200State:
         return {names[i].decode(): float(ms[i]) for i in range(k)}
 
     EXCHANGE_WAITS = ("halo_send_for_p2g_boundary", "halo_recv_for_neighbours", "migrate_send_for_g2p_boundary", "migrate_recv_for_neighbours",
-                      "migrate_recv_for_error_words", "time_step_reductions")
+                      "migrate_recv_for_error_words", "time_step_reductions", "particle_tiles", "grid_tiles")
 
     def exchange_waits(self, reset: bool = False) -> Dict[str, float]:
         """Slab ranks: milliseconds this rank's exchange kernels have spent waiting since the last reset (device-side clocks)."""
