@@ -924,6 +924,9 @@ __device__ __forceinline__ void quad_weights(float shifted, float* w) {
   w[1] = 0.75f - a1 * a1;
   w[2] = 0.5f * a2 * a2;
 }
+#ifndef SVB_P2G_WALK
+#define SVB_P2G_WALK 2   // 1: per-lane constants in registers (ptxas rematerialises them in every run), 2: constants from a shared-memory table per chunk
+#endif
 #ifndef SVB_P2G_CTAS_PER_SM
 #define SVB_P2G_CTAS_PER_SM 7   // 71 registers, 24 KB of shared memory per CTA; measured: 6 -> 81 us, 7 -> 79 us, 8 (spills) -> 88 us at 1 M
 #endif
@@ -968,6 +971,27 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Shared memory through 32-bit window addresses (P2G's walk): the address arithmetic of a run is one integer add, and an `opaque`
+// value cannot be rematerialised — ptxas otherwise recomputes cheap per-lane constants (and the shared window base) inside every run
+// of the walk to keep them out of the prologue's register budget: 25 of the 66 instructions a run cost besides its particles.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm volatile("mov.b32 %0, %0;" : "+r"(v)); return v; }
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // The external force (external_force.rs:17-50) is applied here, in registers: v + dt g, or (goal - x) / dt for a goal particle.  The
 // forced velocity is only ever read by the scatter (collect_velocity.rs overwrites v), so it is never stored.
 struct ForceIn {
@@ -1010,6 +1034,19 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   const float kp2_z = lk == 1 ? -1.f : 0.5f, kp1_z = lk == 0 ? -1.5f : lk == 1 ? 2.f : -0.5f, kp0_z = lk == 0 ? 1.125f : lk == 1 ? -0.25f : 0.125f;
   const float fli = (float)li, flj = (float)lj, flk = (float)lk;
   const int lane_tile_off = (li * 6 + lj) * 6 + lk;
+#if SVB_P2G_WALK == 2
+  // the lane's polynomial coefficients and stencil offsets live in shared memory and are fetched after each chunk's prologue (three
+  // LDS.128 per 32 particles), so they never compete with the prologue for registers
+  __shared__ float4 s_lane_k[3 * 32];
+  if (warp == 0) {
+    s_lane_k[lane] = make_float4(kp2_xy.x, kp2_xy.y, kp2_z, fli);
+    s_lane_k[32 + lane] = make_float4(kp1_xy.x, kp1_xy.y, kp1_z, flj);
+    s_lane_k[64 + lane] = make_float4(kp0_xy.x, kp0_xy.y, kp0_z, flk);
+  }
+  const uint32_t lane_k_s = opaque(smem_addr(s_lane_k) + lane * 16);
+  const uint32_t stage_s = opaque(smem_addr(stage));
+  const uint32_t tile_s = opaque(smem_addr(my_tile) + (uint32_t)lane_tile_off * 16u);   // the lane's node of cell (0,0,0) in the warp's tile
+#endif
 
   uint32_t ticking = 0;   // thread 0: the item just finished belonged to a boundary tile (its weight in W.done)
   for (;;) {
@@ -1093,11 +1130,63 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
       float4* row = reinterpret_cast<float4*>(stage + lane * STAGE_STRIDE);
 #pragma unroll
       for (int q = 0; q < 4; ++q) row[q] = st[q];
+#if SVB_P2G_WALK == 2
+      stage[lane * STAGE_STRIDE + 16] = __int_as_float((((cell >> 4) * 6 + ((cell >> 2) & 3)) * 6 + (cell & 3)) * 16);   // byte offset of the cell's first node in a tile
+#else
       stage[lane * STAGE_STRIDE + 16] = __int_as_float(cell);
+#endif
       __syncwarp();
 
       // ---- cooperative walk: lane = stencil node, one register accumulator per run of equal cells
       const int count = __popc(valid);
+#if SVB_P2G_WALK == 2
+      {
+        const float4 k2 = lds128<0>(lane_k_s), k1 = lds128<512>(lane_k_s), k0 = lds128<1024>(lane_k_s);
+        const float2 c2_xy = make_float2(k2.x, k2.y), c1_xy = make_float2(k1.x, k1.y), c0_xy = make_float2(k0.x, k0.y);
+        while (heads) {
+          const int first = __ffs(heads) - 1;
+          heads &= heads - 1;
+          const int last = heads ? __ffs(heads) - 1 : count;
+          float2 acc_xy = make_float2(0.f, 0.f);
+          float acc_z = 0.f, acc_m = 0.f;
+          const uint32_t run_s = stage_s + (uint32_t)first * (STAGE_STRIDE * 4);
+          uint32_t sp = run_s;
+          auto node_update = [&](const float4 q0, const float4 q1, const float4 q2, const float4 q3) {
+            const float2 t_xy = make_float2(q0.x, q0.y);
+            const float2 w_xy = ffma2(ffma2(c2_xy, t_xy, c1_xy), t_xy, c0_xy);
+            const float w_z = fmaf(fmaf(k2.z, q0.z, k1.z), q0.z, k0.z);
+            const float wgt = w_xy.x * w_xy.y * w_z;
+            const float2 m_xy = ffma2(make_float2(q2.z, q2.w), k0.w, ffma2(make_float2(q2.x, q2.y), k1.w, ffma2(make_float2(q1.z, q1.w), k2.w, make_float2(q1.x, q1.y))));
+            const float m_z = fmaf(q3.w, k0.w, fmaf(q3.z, k1.w, fmaf(q3.y, k2.w, q3.x)));
+            acc_xy = ffma2(m_xy, wgt, acc_xy);
+            acc_z = fmaf(wgt, m_z, acc_z);
+            acc_m = fmaf(wgt, q0.w, acc_m);
+          };
+          constexpr int RB = STAGE_STRIDE * 4;   // bytes per staged row
+          int left = last - first;
+          for (; left >= 4; left -= 4) {   // whole groups of four without a trip test in between
+            node_update(lds128<0>(sp), lds128<16>(sp), lds128<32>(sp), lds128<48>(sp));
+            node_update(lds128<RB>(sp), lds128<RB + 16>(sp), lds128<RB + 32>(sp), lds128<RB + 48>(sp));
+            node_update(lds128<2 * RB>(sp), lds128<2 * RB + 16>(sp), lds128<2 * RB + 32>(sp), lds128<2 * RB + 48>(sp));
+            node_update(lds128<3 * RB>(sp), lds128<3 * RB + 16>(sp), lds128<3 * RB + 32>(sp), lds128<3 * RB + 48>(sp));
+            sp += 4 * RB;
+          }
+          if (left & 2) {
+            node_update(lds128<0>(sp), lds128<16>(sp), lds128<32>(sp), lds128<48>(sp));
+            node_update(lds128<RB>(sp), lds128<RB + 16>(sp), lds128<RB + 32>(sp), lds128<RB + 48>(sp));
+            sp += 2 * RB;
+          }
+          if (left & 1) node_update(lds128<0>(sp), lds128<16>(sp), lds128<32>(sp), lds128<48>(sp));
+          if (node_lane) {
+            const uint32_t a = tile_s + lds32<64>(run_s);
+            float4 o = lds128<0>(a);
+            o.x += acc_xy.x; o.y += acc_xy.y; o.z += acc_z; o.w += acc_m;
+            sts128(a, o);
+          }
+          __syncwarp();   // the next run's flush reads nodes another lane has just written (neighbouring cells share 18 of their 27 nodes)
+        }
+      }
+#else
       while (heads) {
         const int first = __ffs(heads) - 1;
         heads &= heads - 1;
@@ -1136,6 +1225,7 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
         }
         __syncwarp();   // the next run's flush reads nodes another lane has just written (neighbouring cells share 18 of their 27 nodes)
       }
+#endif
       __syncwarp();
     }
     __syncthreads();
