@@ -924,9 +924,6 @@ __device__ __forceinline__ void quad_weights(float shifted, float* w) {
   w[1] = 0.75f - a1 * a1;
   w[2] = 0.5f * a2 * a2;
 }
-#ifndef SVB_P2G_WALK
-#define SVB_P2G_WALK 2   // 1: per-lane constants in registers (ptxas rematerialises them in every run), 2: constants from a shared-memory table per chunk
-#endif
 #ifndef SVB_P2G_CTAS_PER_SM
 #define SVB_P2G_CTAS_PER_SM 7   // 71 registers, 24 KB of shared memory per CTA; measured: 6 -> 81 us, 7 -> 79 us, 8 (spills) -> 88 us at 1 M
 #endif
@@ -1034,7 +1031,6 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   const float kp2_z = lk == 1 ? -1.f : 0.5f, kp1_z = lk == 0 ? -1.5f : lk == 1 ? 2.f : -0.5f, kp0_z = lk == 0 ? 1.125f : lk == 1 ? -0.25f : 0.125f;
   const float fli = (float)li, flj = (float)lj, flk = (float)lk;
   const int lane_tile_off = (li * 6 + lj) * 6 + lk;
-#if SVB_P2G_WALK == 2
   // the lane's polynomial coefficients and stencil offsets live in shared memory and are fetched after each chunk's prologue (three
   // LDS.128 per 32 particles), so they never compete with the prologue for registers
   __shared__ float4 s_lane_k[3 * 32];
@@ -1046,7 +1042,6 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
   const uint32_t lane_k_s = opaque(smem_addr(s_lane_k) + lane * 16);
   const uint32_t stage_s = opaque(smem_addr(stage));
   const uint32_t tile_s = opaque(smem_addr(my_tile) + (uint32_t)lane_tile_off * 16u);   // the lane's node of cell (0,0,0) in the warp's tile
-#endif
 
   uint32_t ticking = 0;   // thread 0: the item just finished belonged to a boundary tile (its weight in W.done)
   for (;;) {
@@ -1130,16 +1125,11 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
       float4* row = reinterpret_cast<float4*>(stage + lane * STAGE_STRIDE);
 #pragma unroll
       for (int q = 0; q < 4; ++q) row[q] = st[q];
-#if SVB_P2G_WALK == 2
       stage[lane * STAGE_STRIDE + 16] = __int_as_float((((cell >> 4) * 6 + ((cell >> 2) & 3)) * 6 + (cell & 3)) * 16);   // byte offset of the cell's first node in a tile
-#else
-      stage[lane * STAGE_STRIDE + 16] = __int_as_float(cell);
-#endif
       __syncwarp();
 
       // ---- cooperative walk: lane = stencil node, one register accumulator per run of equal cells
       const int count = __popc(valid);
-#if SVB_P2G_WALK == 2
       {
         const float4 k2 = lds128<0>(lane_k_s), k1 = lds128<512>(lane_k_s), k0 = lds128<1024>(lane_k_s);
         const float2 c2_xy = make_float2(k2.x, k2.y), c1_xy = make_float2(k1.x, k1.y), c0_xy = make_float2(k0.x, k0.y);
@@ -1186,46 +1176,6 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
           __syncwarp();   // the next run's flush reads nodes another lane has just written (neighbouring cells share 18 of their 27 nodes)
         }
       }
-#else
-      while (heads) {
-        const int first = __ffs(heads) - 1;
-        heads &= heads - 1;
-        const int last = heads ? __ffs(heads) - 1 : count;
-        float2 acc_xy = make_float2(0.f, 0.f);
-        float acc_z = 0.f, acc_m = 0.f;
-        const float4* sp = reinterpret_cast<const float4*>(stage + first * STAGE_STRIDE);
-        auto node_update = [&](const float4* row) {
-          const float4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
-          const float2 t_xy = make_float2(q0.x, q0.y);
-          const float2 w_xy = ffma2(ffma2(kp2_xy, t_xy, kp1_xy), t_xy, kp0_xy);
-          const float w_z = fmaf(fmaf(kp2_z, q0.z, kp1_z), q0.z, kp0_z);
-          const float wgt = w_xy.x * w_xy.y * w_z;
-          const float2 m_xy = ffma2(make_float2(q2.z, q2.w), flk, ffma2(make_float2(q2.x, q2.y), flj, ffma2(make_float2(q1.z, q1.w), fli, make_float2(q1.x, q1.y))));
-          const float m_z = fmaf(q3.w, flk, fmaf(q3.z, flj, fmaf(q3.y, fli, q3.x)));
-          acc_xy = ffma2(m_xy, wgt, acc_xy);
-          acc_z = fmaf(wgt, m_z, acc_z);
-          acc_m = fmaf(wgt, q0.w, acc_m);
-        };
-        int p = first;
-        for (; p + 4 <= last; p += 4) {   // whole groups of four without a trip test in between
-#pragma unroll
-          for (int u = 0; u < 4; ++u) node_update(sp + u * (STAGE_STRIDE / 4));
-          sp += 4 * (STAGE_STRIDE / 4);
-        }
-        for (; p < last; ++p) {
-          node_update(sp);
-          sp += STAGE_STRIDE / 4;
-        }
-        if (node_lane) {
-          const int c = __float_as_int(stage[first * STAGE_STRIDE + 16]);
-          const int t = ((c >> 4) * 6 + ((c >> 2) & 3)) * 6 + (c & 3) + lane_tile_off;
-          float4 o = my_tile[t];
-          o.x += acc_xy.x; o.y += acc_xy.y; o.z += acc_z; o.w += acc_m;
-          my_tile[t] = o;
-        }
-        __syncwarp();   // the next run's flush reads nodes another lane has just written (neighbouring cells share 18 of their 27 nodes)
-      }
-#endif
       __syncwarp();
     }
     __syncthreads();
@@ -1396,11 +1346,12 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     }
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t base = start + (threadIdx.x & ~31u); base < end; base += blockDim.x) {   // warp-uniform trip count (bin_warp is warp-collective)
+    // a warp's 32 slots start on a 128-byte line of the destination arrays: every store of a warp is one line, not two (G2P 80 -> 77 us at 1 M)
+    for (uint32_t base = (start & ~31u) + (threadIdx.x & ~31u); base < end; base += blockDim.x) {   // warp-uniform trip count (bin_warp is warp-collective)
       const uint32_t i = base + lane;
       int bin_state = 2;
       V3 bin_x = V3{0.f, 0.f, 0.f};
-      if (i < end) {
+      if (i >= start && i < end) {
       const uint32_t si = src_of[i];   // (fetching the next iteration's row index one iteration ahead: measured neutral, r1n)
       V3 x = V3{P.f(PX)[si], P.f(PX + 1)[si], P.f(PX + 2)[si]};
       // issue the loads of everything this thread carries / updates before the gather needs them
@@ -1501,7 +1452,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
       D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
       }
-      if (BIN && i < end) {
+      if (BIN && i >= start && i < end) {
         uint32_t ci = bin_state == 1 ? 0xffffffffu : 0xfffffffdu;
         if (bin_state == 1) atomicAdd(&bn.S->n_tomb, 1u);   // culled just now (rare)
         if (bin_state == 0) {
