@@ -959,22 +959,19 @@ int load_particles(SvbHandle* h, const SvbParticles* p) {
   ParticleBuf P = h->Pc();
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();
   const uint32_t blocks = blocks_for(n, 256);
-  auto scalar = [&](const void* src, int field) -> int {
-    if (!src) return 0;
-    CK(cudaMemcpyAsync(P.u(field), src, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-    return 0;
-  };
-  size_t stage_off = 0;  // every wire array gets its own region of the spare buffer (24 n words <= 34 cap): no sync in between
-  auto vec = [&](const float* src, int field, int k) -> int {
+  size_t stage_off = 0;  // every wire array gets its own region of the spare buffer (33 n words <= 36 cap): no sync in between
+  auto vec = [&](const void* src, int field, int k) -> int {
     if (!src) return 0;
     float* st = stagef + stage_off;
     stage_off += (size_t)h->cap * k;
     CK(cudaMemcpyAsync(st, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
-    if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
-    else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(st, P.f(field), h->cap, n);
+    if (k == 1) k_wire_to_soa<1><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(st), P, field, n);
+    else if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(st), P, field, n);
+    else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(st), P, field, n);
     LAUNCH_CHECK();
     return 0;
   };
+  auto scalar = [&](const void* src, int field) -> int { return vec(src, field, 1); };
   int rc = 0;
   if ((rc = scalar(p->flags, PFLAGS)) || (rc = scalar(p->mass, PMASS)) || (rc = scalar(p->initial_volume, PVOL)) || (rc = scalar(p->mu_or_bulk_modulus, PP0)) ||
       (rc = scalar(p->lambda_or_exponent, PP1)) || (rc = scalar(p->sand_alpha, PALPHA)) || (rc = scalar(p->viscosity_dynamic, PVD)) || (rc = scalar(p->viscosity_bulk, PVB)) ||
@@ -982,7 +979,7 @@ int load_particles(SvbHandle* h, const SvbParticles* p) {
       (rc = vec(p->position_gradients, PF, 9)))
     return rc;
   if (p->elastic_energies) CK(cudaMemcpyAsync(h->energy.p, p->elastic_energies, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-  k_iota<<<blocks, 256, 0, h->stream>>>(P.u(PORIG), n, 0);
+  k_iota_orig<<<blocks, 256, 0, h->stream>>>(P, n, 0);
   LAUNCH_CHECK();
   h->initial_positions.assign((size_t)n * 3, 0.f);
   if (p->initial_positions) std::memcpy(h->initial_positions.data(), p->initial_positions, (size_t)n * 12);
@@ -1067,7 +1064,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   h->n = n;
   h->cap = ((size_t)std::max<uint32_t>(n, 1) + 63) & ~(size_t)63;
   for (int b = 0; b < 2; ++b) {
-    CK(h->pbuf[b].ensure(h->cap * NFIELDS * 4));
+    CK(h->pbuf[b].ensure(h->cap * NWORDS * 4));
   }
   CK(h->energy.ensure(h->cap * 4));
   CK(h->scalars.ensure(2 * sizeof(StepScalars)));
@@ -1079,7 +1076,7 @@ int32_t svb_create(const SvbConsts* consts, const SvbParticles* p, double time, 
   CK(h->layer_slots.ensure(LAYER_SLOTS * 8));
   CK(h->layer_list.ensure(LAYER_SLOTS * 4));
   CK(cudaMemsetAsync(h->layer_slots.p, 0, LAYER_SLOTS * 8, h->stream));
-  for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->pbuf[b].p, 0, h->cap * NFIELDS * 4, h->stream));
+  for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->pbuf[b].p, 0, h->cap * NWORDS * 4, h->stream));
   CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
   if (int rc = ensure_tile_capacity(h, (size_t)n / 96 + 2048)) return rc;
 
@@ -1135,7 +1132,7 @@ int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
   const size_t need = h->slabs ? (size_t)n * 3 / 2 + 65536 : (size_t)std::max<uint32_t>(n, 1);
   if (int rc = resize_particles(h, need)) return rc;
   h->n = n;
-  for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->pbuf[b].p, 0, h->cap * NFIELDS * 4, h->stream));
+  for (int b = 0; b < 2; ++b) CK(cudaMemsetAsync(h->pbuf[b].p, 0, h->cap * NWORDS * 4, h->stream));
   CK(cudaMemsetAsync(h->energy.p, 0, h->cap * 4, h->stream));
   if (int rc = load_particles(h, p)) return rc;
   // a new state starts a new run: clock, step history, error words, per-substep tables
@@ -1154,7 +1151,7 @@ int32_t svb_upload(SvbHandle* h, const SvbParticles* p, double time) {
   h->have_snapshot = false;
   if (h->slabs) {
     if (n && h->orig_offset) {
-      k_add_u32<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->Pc().u(PORIG), n, (uint32_t)h->orig_offset);
+      k_add_orig<<<blocks_for(n, 256), 256, 0, h->stream>>>(h->Pc(), n, (uint32_t)h->orig_offset);
       LAUNCH_CHECK();
     }
     if (h->p2p) CK(cudaMemcpyAsync(h->n_dev, &h->n, 4, cudaMemcpyHostToDevice, h->stream));
@@ -1397,32 +1394,31 @@ int32_t svb_download(SvbHandle* h, SvbParticles* out) {
   out->n = n;
   if (!n) return 0;
   ParticleBuf P = h->Pc();
-  const uint32_t* orig = P.u(PORIG);
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();  // the spare buffer is free between substeps
   const uint32_t blocks = blocks_for(n, 256);
-  size_t stage_off = 0;  // one region per field (34 n words in total): all gathers and copies queue back to back
-  auto field = [&](void* dst, const float* src_field, int k) -> int {
+  size_t stage_off = 0;  // one region per field (33 n words in total): all gathers and copies queue back to back
+  auto field = [&](void* dst, int word, int k) -> int {
     if (!dst) return 0;
     float* st = stagef + stage_off;
     stage_off += (size_t)h->cap * k;
-    if (k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, st, n);
-    else if (k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, st, n);
-    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(src_field, h->cap, orig, st, n);
+    if (k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(P, word, reinterpret_cast<uint32_t*>(st), n);
+    else if (k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(P, word, reinterpret_cast<uint32_t*>(st), n);
+    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(P, word, reinterpret_cast<uint32_t*>(st), n);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(dst, st, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
     return 0;
   };
   int rc = 0;
-  if ((rc = field(out->flags, P.f(PFLAGS), 1)) || (rc = field(out->mass, P.f(PMASS), 1)) || (rc = field(out->initial_volume, P.f(PVOL), 1)) ||
-      (rc = field(out->mu_or_bulk_modulus, P.f(PP0), 1)) || (rc = field(out->lambda_or_exponent, P.f(PP1), 1)) || (rc = field(out->sand_alpha, P.f(PALPHA), 1)) ||
-      (rc = field(out->viscosity_dynamic, P.f(PVD), 1)) || (rc = field(out->viscosity_bulk, P.f(PVB), 1)) || (rc = field(out->collider_bits, P.f(PBITS), 1)) ||
-      (rc = field(out->positions, P.f(PX), 3)) || (rc = field(out->velocities, P.f(PV), 3)) || (rc = field(out->velocity_gradients, P.f(PC), 9)) ||
-      (rc = field(out->position_gradients, P.f(PF), 9)))
+  if ((rc = field(out->flags, PFLAGS, 1)) || (rc = field(out->mass, PMASS, 1)) || (rc = field(out->initial_volume, PVOL, 1)) ||
+      (rc = field(out->mu_or_bulk_modulus, PP0, 1)) || (rc = field(out->lambda_or_exponent, PP1, 1)) || (rc = field(out->sand_alpha, PALPHA, 1)) ||
+      (rc = field(out->viscosity_dynamic, PVD, 1)) || (rc = field(out->viscosity_bulk, PVB, 1)) || (rc = field(out->collider_bits, PBITS, 1)) ||
+      (rc = field(out->positions, PX, 3)) || (rc = field(out->velocities, PV, 3)) || (rc = field(out->velocity_gradients, PC, 9)) ||
+      (rc = field(out->position_gradients, PF, 9)))
     return rc;
-  // energies are the 35th word: park them in the node-mask scratch if the spare buffer is full
+  // energies live in their own array: park them in the node-mask scratch
   if (out->elastic_energies) {
     CK(h->scratch.ensure((size_t)h->cap * 4));
-    k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(h->energy.as<float>(), h->cap, orig, h->scratch.as<float>(), n);
+    k_array_to_wire<<<blocks, 256, 0, h->stream>>>(h->energy.as<float>(), P, h->scratch.as<float>(), n);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(out->elastic_energies, h->scratch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   }
@@ -1506,7 +1502,12 @@ int32_t svb_binning(SvbHandle* h, uint32_t* sort_map, int32_t* cells) {
   const uint32_t n = h->n;
   if (!n) return 0;
   ParticleBuf P = h->Pc();
-  if (sort_map) CK(cudaMemcpyAsync(sort_map, P.u(PORIG), (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (sort_map) {
+    uint32_t* d = h->pbuf[h->cur ^ 1].as<uint32_t>() + (size_t)3 * h->cap;   // behind the cells
+    k_soa_to_wire_plain<<<blocks_for(n, 256), 256, 0, h->stream>>>(P, PORIG, d, n);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(sort_map, d, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
   if (cells) {
     int32_t* d = h->pbuf[h->cur ^ 1].as<int32_t>();
     k_cells<<<blocks_for(n, 256), 256, 0, h->stream>>>(P, h->K.h, n, d);
@@ -1604,9 +1605,9 @@ int32_t svb_snapshot(SvbHandle* h) {
   if (h->multi) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points");
   if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points (a slab rank's row count lives on the device)");
   if (int rc = set_device(h)) return rc;
-  CK(h->snap_p.ensure(h->cap * NFIELDS * 4));
+  CK(h->snap_p.ensure(h->cap * NWORDS * 4));
   CK(h->snap_e.ensure(h->cap * 4));
-  CK(cudaMemcpyAsync(h->snap_p.p, h->pbuf[h->cur].p, h->cap * NFIELDS * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->snap_p.p, h->pbuf[h->cur].p, h->cap * NWORDS * 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->snap_e.p, h->energy.p, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->snap_time = h->time;
@@ -1622,7 +1623,7 @@ int32_t svb_restore(SvbHandle* h) {
   if (h->slabs) return fail(h, SVB_BAD_ARGUMENT, "svb_snapshot / svb_restore are single-device entry points (a slab rank's row count lives on the device)");
   if (!h->have_snapshot) return fail(h, SVB_BAD_ARGUMENT, "svb_restore without svb_snapshot");
   if (int rc = set_device(h)) return rc;
-  CK(cudaMemcpyAsync(h->pbuf[h->cur].p, h->snap_p.p, h->cap * NFIELDS * 4, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->pbuf[h->cur].p, h->snap_p.p, h->cap * NWORDS * 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(h->energy.p, h->snap_e.p, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->time = h->snap_time;
@@ -1650,16 +1651,16 @@ namespace {
     if (r_ != ncclSuccess) return fail(h, SVB_COMM_ERROR, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 
-// re-stride the particle buffers to a larger per-field capacity (field f of row i = base[f*cap + i])
+// re-stride the particle buffers to a larger per-quad capacity (quad q of row i = ((float4*)base)[q*cap + i])
 int resize_particles(SvbHandle* h, size_t new_cap) {
   new_cap = (new_cap + 63) & ~(size_t)63;
   if (new_cap <= h->cap) return 0;
   CK(sync_streams(h));
   DevBuf nb[2], ne;
-  for (int b = 0; b < 2; ++b) CK(nb[b].ensure(new_cap * NFIELDS * 4));
+  for (int b = 0; b < 2; ++b) CK(nb[b].ensure(new_cap * NWORDS * 4));
   CK(ne.ensure(new_cap * 4));
-  for (int f = 0; f < NFIELDS; ++f)
-    CK(cudaMemcpyAsync(nb[h->cur].as<uint32_t>() + (size_t)f * new_cap, h->pbuf[h->cur].as<uint32_t>() + (size_t)f * h->cap, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
+  for (int q = 0; q < NQUADS; ++q)
+    CK(cudaMemcpyAsync(nb[h->cur].as<uint32_t>() + (size_t)q * new_cap * 4, h->pbuf[h->cur].as<uint32_t>() + (size_t)q * h->cap * 4, h->cap * 16, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaMemcpyAsync(ne.p, h->energy.p, h->cap * 4, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int b = 0; b < 2; ++b) { h->pbuf[b].release(); h->pbuf[b] = nb[b]; }
@@ -1892,7 +1893,7 @@ int32_t svb_comm_init(SvbHandle* h, const uint8_t unique_id[128], int32_t rank, 
   h->reach_hi = rank + 1 < n_ranks ? all[2 * (rank + 1) + 1] : slab_hi_block_x;
   // global original indices travel with the particles
   if (h->n && original_offset) {
-    k_add_u32<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->Pc().u(PORIG), h->n, (uint32_t)original_offset);
+    k_add_orig<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->Pc(), h->n, (uint32_t)original_offset);
     LAUNCH_CHECK();
   }
   h->orig_offset = original_offset;
@@ -2001,7 +2002,12 @@ int32_t svb_slab_rebalance(SvbHandle* h, int32_t new_lo, int32_t new_hi) {
 int32_t svb_set_original_indices(SvbHandle* h, const uint32_t* original_index, uint64_t n) {
   if (!h || !original_index || n != h->n) return SVB_BAD_ARGUMENT;
   if (int rc = set_device(h)) return rc;
-  if (n) CK(cudaMemcpyAsync(h->Pc().u(PORIG), original_index, n * 4, cudaMemcpyHostToDevice, h->stream));
+  if (n) {
+    uint32_t* st = h->pbuf[h->cur ^ 1].as<uint32_t>();   // the spare buffer is free between substeps
+    CK(cudaMemcpyAsync(st, original_index, n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_wire_to_soa<1><<<blocks_for((uint32_t)n, 256), 256, 0, h->stream>>>(st, h->Pc(), PORIG, (uint32_t)n);
+    LAUNCH_CHECK();
+  }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -2027,28 +2033,28 @@ int32_t svb_download_resident(SvbHandle* h, SvbParticles* out, uint64_t* origina
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();
   const uint32_t blocks = blocks_for(m, 256);
   size_t stage_off = 0;
-  auto field = [&](void* dst, const float* src_field, int k) -> int {
+  auto field = [&](void* dst, int word, int k) -> int {
     if (!dst) return 0;
     float* st = stagef + stage_off;
     stage_off += (size_t)h->cap * k;
-    if (k == 1) k_rows_to_wire<1><<<blocks, 256, 0, s>>>(src_field, h->cap, rows, st, m);
-    else if (k == 3) k_rows_to_wire<3><<<blocks, 256, 0, s>>>(src_field, h->cap, rows, st, m);
-    else k_rows_to_wire<9><<<blocks, 256, 0, s>>>(src_field, h->cap, rows, st, m);
+    if (k == 1) k_rows_to_wire<1><<<blocks, 256, 0, s>>>(P, word, rows, reinterpret_cast<uint32_t*>(st), m);
+    else if (k == 3) k_rows_to_wire<3><<<blocks, 256, 0, s>>>(P, word, rows, reinterpret_cast<uint32_t*>(st), m);
+    else k_rows_to_wire<9><<<blocks, 256, 0, s>>>(P, word, rows, reinterpret_cast<uint32_t*>(st), m);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(dst, st, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
     return 0;
   };
   int rc = 0;
   std::vector<uint32_t> orig32(original_index ? m : 0);
-  if ((rc = field(out->flags, P.f(PFLAGS), 1)) || (rc = field(out->mass, P.f(PMASS), 1)) || (rc = field(out->initial_volume, P.f(PVOL), 1)) ||
-      (rc = field(out->mu_or_bulk_modulus, P.f(PP0), 1)) || (rc = field(out->lambda_or_exponent, P.f(PP1), 1)) || (rc = field(out->sand_alpha, P.f(PALPHA), 1)) ||
-      (rc = field(out->viscosity_dynamic, P.f(PVD), 1)) || (rc = field(out->viscosity_bulk, P.f(PVB), 1)) || (rc = field(out->collider_bits, P.f(PBITS), 1)) ||
-      (rc = field(out->positions, P.f(PX), 3)) || (rc = field(out->velocities, P.f(PV), 3)) || (rc = field(out->velocity_gradients, P.f(PC), 9)) ||
-      (rc = field(out->position_gradients, P.f(PF), 9)) || (rc = field(original_index ? orig32.data() : nullptr, P.f(PORIG), 1)))
+  if ((rc = field(out->flags, PFLAGS, 1)) || (rc = field(out->mass, PMASS, 1)) || (rc = field(out->initial_volume, PVOL, 1)) ||
+      (rc = field(out->mu_or_bulk_modulus, PP0, 1)) || (rc = field(out->lambda_or_exponent, PP1, 1)) || (rc = field(out->sand_alpha, PALPHA, 1)) ||
+      (rc = field(out->viscosity_dynamic, PVD, 1)) || (rc = field(out->viscosity_bulk, PVB, 1)) || (rc = field(out->collider_bits, PBITS, 1)) ||
+      (rc = field(out->positions, PX, 3)) || (rc = field(out->velocities, PV, 3)) || (rc = field(out->velocity_gradients, PC, 9)) ||
+      (rc = field(out->position_gradients, PF, 9)) || (rc = field(original_index ? orig32.data() : nullptr, PORIG, 1)))
     return rc;
   if (out->elastic_energies) {
     CK(h->node_offset.ensure((size_t)m * 4));
-    k_rows_to_wire<1><<<blocks, 256, 0, s>>>(h->energy.as<float>(), h->cap, rows, h->node_offset.as<float>(), m);
+    k_array_rows_to_wire<<<blocks, 256, 0, s>>>(h->energy.as<float>(), rows, h->node_offset.as<float>(), m);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(out->elastic_energies, h->node_offset.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
   }

@@ -61,25 +61,37 @@ __device__ __forceinline__ int base_node_fast(float x, float h, float inv_h) {
 
 // ------------------------------------------------------------------------------------------------
 // wire <-> SoA
+// (all words as u32: a flag / bit word must not pass through a float register as a signalling NaN pattern would still be preserved
+// by LDG / STG, but typed loads keep this obvious)
 template <int K>
-__global__ void k_wire_to_soa(const float* __restrict__ src, float* __restrict__ dst, size_t cap, uint32_t n) {
+__global__ void k_wire_to_soa(const uint32_t* __restrict__ src, ParticleBuf P, int field, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
 #pragma unroll
-  for (int k = 0; k < K; ++k) dst[(size_t)k * cap + i] = src[(size_t)i * K + k];
+  for (int k = 0; k < K; ++k) P.u(field + k)[i] = src[(size_t)i * K + k];
 }
-// out[(original index)*K + k] = field[k][i]   (to_io_state, cpu/src/cpu_state.rs:84-93)
+// out[(original index)*K + k] = word[field + k][i]   (to_io_state, cpu/src/cpu_state.rs:84-93)
 template <int K>
-__global__ void k_soa_to_wire(const float* __restrict__ src, size_t cap, const uint32_t* __restrict__ orig, float* __restrict__ dst, uint32_t n) {
+__global__ void k_soa_to_wire(ParticleBuf P, int field, uint32_t* __restrict__ dst, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const size_t o = orig ? orig[i] : i;
+  const size_t o = P.u(PORIG)[i];
 #pragma unroll
-  for (int k = 0; k < K; ++k) dst[o * K + k] = src[(size_t)k * cap + i];
+  for (int k = 0; k < K; ++k) dst[o * K + k] = P.u(field + k)[i];
 }
-__global__ void k_iota(uint32_t* a, uint32_t n, uint32_t offset) {
+// ... in row order (no scatter by original index)
+__global__ void k_soa_to_wire_plain(ParticleBuf P, int field, uint32_t* __restrict__ dst, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = i + offset;
+  if (i < n) dst[i] = P.u(field)[i];
+}
+// a plain per-row array (the elastic energies) into original order
+__global__ void k_array_to_wire(const float* __restrict__ src, ParticleBuf P, float* __restrict__ dst, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[P.u(PORIG)[i]] = src[i];
+}
+__global__ void k_iota_orig(ParticleBuf P, uint32_t n, uint32_t offset) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) P.u(PORIG)[i] = i + offset;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1067,15 +1079,18 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
       int cell = -1;
       if (chunk + lane < end) {
         const uint32_t i = src_of[chunk + lane];  // row of this particle in the pre-bin order
-        const float x0 = P.f(PX)[i], x1 = P.f(PX + 1)[i], x2 = P.f(PX + 2)[i];
+        // the particle's nine quads (svb_device.cuh: Field): 16-byte gathers, consecutive slots come from (nearly) consecutive rows
+        const float4 pq0 = P.q(0)[i], pq1 = P.q(1)[i], pq2 = P.q(2)[i], pq3 = P.q(3)[i], pq4 = P.q(4)[i], pq5 = P.q(5)[i], pq6 = P.q(6)[i], pq7 = P.q(7)[i];
+        const float2 pq8 = *reinterpret_cast<const float2*>(P.q(8) + i);
+        const float x0 = pq0.x, x1 = pq0.y, x2 = pq0.z;
         const float n0 = __fdiv_rn(x0, h), n1 = __fdiv_rn(x1, h), n2 = __fdiv_rn(x2, h);
         const int s0 = (int)floorf(__fsub_rn(n0, 0.5f)), s1 = (int)floorf(__fsub_rn(n1, 0.5f)), s2 = (int)floorf(__fsub_rn(n2, 0.5f));
         cell = ((s0 & 3) << 4) | ((s1 & 3) << 2) | (s2 & 3);
         M3 C, F;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) { C.m[q] = P.f(PC + q)[i]; F.m[q] = P.f(PF + q)[i]; }
-        const float mass = P.f(PMASS)[i], vol = P.f(PVOL)[i], p0 = P.f(PP0)[i], p1 = P.f(PP1)[i];
-        const uint32_t flags = P.u(PFLAGS)[i];
+        F.m[0] = pq1.x; F.m[1] = pq1.y; F.m[2] = pq1.z; F.m[3] = pq1.w; F.m[4] = pq2.x; F.m[5] = pq2.y; F.m[6] = pq2.z; F.m[7] = pq2.w; F.m[8] = pq3.x;
+        C.m[0] = pq6.y; C.m[1] = pq6.z; C.m[2] = pq6.w; C.m[3] = pq7.x; C.m[4] = pq7.y; C.m[5] = pq7.z; C.m[6] = pq7.w; C.m[7] = pq8.x; C.m[8] = pq8.y;
+        const float mass = pq3.y, vol = pq3.z, p0 = pq3.w, p1 = pq4.x;
+        const uint32_t flags = __float_as_uint(pq0.w);
         const M3 stress = (flags & F_IS_FLUID) ? first_piola_inviscid(p0, (int)p1, F) : first_piola_neo_hookean(p0, p1, F);
         const M3 pft = mul_nt(stress, F);
         const float sv = scaling * vol;
@@ -1083,16 +1098,16 @@ __global__ void __launch_bounds__(P2G_WARPS * 32, P2G_CTAS_PER_SM) k_p2g(Particl
 #pragma unroll
         for (int q = 0; q < 9; ++q) A.m[q] = mass * C.m[q] - sv * pft.m[q];
         if (flags & F_USE_VISCOSITY) {
-          const M3 cauchy = viscous_cauchy(P.f(PVD)[i], P.f(PVB)[i], C);
+          const M3 cauchy = viscous_cauchy(pq4.z, pq4.w, C);
           const float sj = scaling * det(F) * vol;
 #pragma unroll
           for (int q = 0; q < 9; ++q) A.m[q] -= sj * cauchy.m[q];
         }
-        V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+        V3 v = V3{pq5.z, pq5.w, pq6.x};
         {   // ExternalForce, after the collide pass of the same substep like phase/mod.rs:27-41
           bool goal = false;
           if (HAS_GOALS) {
-            const uint32_t o = P.u(PORIG)[i];
+            const uint32_t o = __float_as_uint(pq5.y);
             if ((force.G.flags_a[o] & F_HAS_GOAL) && (force.G.flags_b[o] & F_HAS_GOAL)) {
               const float fa = 1.f - force.factor_b;
               const V3 target = fa * ld3(force.G.goal_a, o) + force.factor_b * ld3(force.G.goal_b, o);
@@ -1353,16 +1368,15 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
       V3 bin_x = V3{0.f, 0.f, 0.f};
       if (i >= start && i < end) {
       const uint32_t si = src_of[i];   // (fetching the next iteration's row index one iteration ahead: measured neutral, r1n)
-      V3 x = V3{P.f(PX)[si], P.f(PX + 1)[si], P.f(PX + 2)[si]};
-      // issue the loads of everything this thread carries / updates before the gather needs them
-      uint32_t flags = P.u(PFLAGS)[si];
+      // quads 0..5 of the particle (svb_device.cuh: Field): position, flags, F and the words this thread merely carries — six 16-byte
+      // gathers instead of thirty 4-byte ones (v and C are replaced, quads 6..8 are not read)
+      const float4 pq0 = P.q(0)[si], pq1 = P.q(1)[si], pq2 = P.q(2)[si], pq3 = P.q(3)[si], pq4 = P.q(4)[si];
+      const float2 pq5 = *reinterpret_cast<const float2*>(P.q(5) + si);
+      V3 x = V3{pq0.x, pq0.y, pq0.z};
+      uint32_t flags = __float_as_uint(pq0.w);
       M3 F;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) F.m[q] = P.f(PF + q)[si];
-      float carry[7];
-#pragma unroll
-      for (int q = 0; q < 7; ++q) carry[q] = P.f(PMASS + q)[si];
-      const uint32_t bits = P.u(PBITS)[si], orig = P.u(PORIG)[si];
+      F.m[0] = pq1.x; F.m[1] = pq1.y; F.m[2] = pq1.z; F.m[3] = pq1.w; F.m[4] = pq2.x; F.m[5] = pq2.y; F.m[6] = pq2.z; F.m[7] = pq2.w; F.m[8] = pq3.x;
+      const float carry[7] = {pq3.y, pq3.z, pq3.w, pq4.x, pq4.y, pq4.z, pq4.w};   // mass, V0, mu | K, lambda | gamma, alpha, eta, zeta
       // (deriving the base node from the binned cell id instead of three IEEE divisions was measured slower:
       // the extra gathered 4-byte load costs more than the divisions)
       const V3 nrm = V3{__fdiv_rn(x.x, h), __fdiv_rn(x.y, h), __fdiv_rn(x.z, h)};
@@ -1444,13 +1458,15 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
         bin_state = leaving ? 2 : ((flags & F_TOMBSTONED) ? 1 : 0);
         bin_x = x;
       }
-      D.f(PX)[i] = x.x; D.f(PX + 1)[i] = x.y; D.f(PX + 2)[i] = x.z;
-      D.f(PV)[i] = v.x; D.f(PV + 1)[i] = v.y; D.f(PV + 2)[i] = v.z;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) { D.f(PC + q)[i] = C.m[q]; D.f(PF + q)[i] = F.m[q]; }
-#pragma unroll
-      for (int q = 0; q < 7; ++q) D.f(PMASS + q)[i] = carry[q];
-      D.u(PFLAGS)[i] = flags; D.u(PBITS)[i] = bits; D.u(PORIG)[i] = orig;
+      D.q(0)[i] = make_float4(x.x, x.y, x.z, __uint_as_float(flags));
+      D.q(1)[i] = make_float4(F.m[0], F.m[1], F.m[2], F.m[3]);
+      D.q(2)[i] = make_float4(F.m[4], F.m[5], F.m[6], F.m[7]);
+      D.q(3)[i] = make_float4(F.m[8], carry[0], carry[1], carry[2]);
+      D.q(4)[i] = make_float4(carry[3], carry[4], carry[5], carry[6]);
+      D.q(5)[i] = make_float4(pq5.x, pq5.y, v.x, v.y);   // collider bits, original index
+      D.q(6)[i] = make_float4(v.z, C.m[0], C.m[1], C.m[2]);
+      D.q(7)[i] = make_float4(C.m[3], C.m[4], C.m[5], C.m[6]);
+      D.q(8)[i] = make_float4(C.m[7], C.m[8], 0.f, 0.f);
       }
       if (BIN && i >= start && i < end) {
         uint32_t ci = bin_state == 1 ? 0xffffffffu : 0xfffffffdu;
@@ -1500,7 +1516,7 @@ __global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleB
     for (uint32_t j = n_live + blockIdx.x * blockDim.x + threadIdx.x; j < n_end; j += gridDim.x * blockDim.x) {
       const uint32_t i = src_of[j];
 #pragma unroll 1
-      for (int f = 0; f < NFIELDS; ++f) D.base[(size_t)f * D.cap + j] = P.base[(size_t)f * P.cap + i];
+      for (int q = 0; q < NQUADS; ++q) D.q(q)[j] = P.q(q)[i];
       if (BIN) {   // stays tombstoned: behind the live rows of the next substep as well
         bn.B.pcell[j] = 0xffffffffu;
         atomicAdd(&bn.S->n_tomb, 1u);
@@ -2005,7 +2021,7 @@ __global__ void __launch_bounds__(256) k_migrate_pack(ParticleBuf P, const float
   if (slot >= cap) return;
   uint32_t* row = (side ? out_right : out_left) + (size_t)slot * MIG_WORDS;
 #pragma unroll
-  for (int f = 0; f < NFIELDS; ++f) row[f] = P.base[(size_t)f * P.cap + i];
+  for (int f = 0; f < NFIELDS; ++f) row[f] = P.u(f)[i];
   row[PFLAGS] = flags;  // the row travels without the local F_GONE mark
   row[NFIELDS] = __float_as_uint(energy[i]);
 }
@@ -2015,7 +2031,7 @@ __global__ void __launch_bounds__(256) k_migrate_unpack(ParticleBuf P, float* __
   const uint32_t* row = in + (size_t)q * MIG_WORDS;
   const uint32_t i = base + q;
 #pragma unroll
-  for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
+  for (int f = 0; f < NFIELDS; ++f) P.u(f)[i] = row[f];
   energy[i] = __uint_as_float(row[NFIELDS]);
 }
 // migration over peer memory.  Sending side: rows that left [lo, hi) go straight into the neighbour's mailbox;
@@ -2056,7 +2072,7 @@ __global__ void __launch_bounds__(256) k_migrate_send_list(ParticleBuf P, const 
       if (!peers.rows[side]) continue;
       uint32_t* row = peers.rows[side] + (size_t)slot * MIG_WORDS;
 #pragma unroll
-      for (int f = 0; f < NFIELDS; ++f) row[f] = P.base[(size_t)f * P.cap + i];
+      for (int f = 0; f < NFIELDS; ++f) row[f] = P.u(f)[i];
       row[PFLAGS] = flags;  // the row travels without the local F_GONE mark
       row[NFIELDS] = __float_as_uint(energy[i]);
     }
@@ -2134,7 +2150,7 @@ __global__ void __launch_bounds__(256) k_migrate_recv(ParticleBuf P, float* __re
       const uint32_t* row = q < cl ? rows_left + (size_t)q * MIG_WORDS : rows_right + (size_t)(q - cl) * MIG_WORDS;
       const uint32_t i = base + q;
 #pragma unroll
-      for (int f = 0; f < NFIELDS; ++f) P.base[(size_t)f * P.cap + i] = row[f];
+      for (int f = 0; f < NFIELDS; ++f) P.u(f)[i] = row[f];
       energy[i] = __uint_as_float(row[NFIELDS]);
       x = V3{__uint_as_float(row[PX]), __uint_as_float(row[PX + 1]), __uint_as_float(row[PX + 2])};
       state = (row[PFLAGS] & F_TOMBSTONED) ? 1 : 0;
@@ -2178,9 +2194,9 @@ __global__ void __launch_bounds__(256) k_column_histogram(ParticleBuf P, float h
     if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&counts[bin], (unsigned long long)__popc(peers));
   }
 }
-__global__ void k_add_u32(uint32_t* a, uint32_t n, uint32_t add) {
+__global__ void k_add_orig(ParticleBuf P, uint32_t n, uint32_t add) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += add;
+  if (i < n) P.u(PORIG)[i] += add;
 }
 // rows that are still resident (not migrated away), compacted in arbitrary order
 __global__ void __launch_bounds__(256) k_resident_rows(ParticleBuf P, uint32_t n, uint32_t* __restrict__ rows, uint32_t* __restrict__ count) {
@@ -2193,12 +2209,16 @@ __global__ void __launch_bounds__(256) k_resident_rows(ParticleBuf P, uint32_t n
   if (keep) rows[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = i;
 }
 template <int K>
-__global__ void k_rows_to_wire(const float* __restrict__ src, size_t cap, const uint32_t* __restrict__ rows, float* __restrict__ dst, uint32_t n) {
+__global__ void k_rows_to_wire(ParticleBuf P, int field, const uint32_t* __restrict__ rows, uint32_t* __restrict__ dst, uint32_t n) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const uint32_t i = rows[q];
 #pragma unroll
-  for (int k = 0; k < K; ++k) dst[(size_t)q * K + k] = src[(size_t)k * cap + i];
+  for (int k = 0; k < K; ++k) dst[(size_t)q * K + k] = P.u(field + k)[i];
+}
+__global__ void k_array_rows_to_wire(const float* __restrict__ src, const uint32_t* __restrict__ rows, float* __restrict__ dst, uint32_t n) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) dst[q] = src[rows[q]];
 }
 
 // ------------------------------------------------------------------------------------------------
