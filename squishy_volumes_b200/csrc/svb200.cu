@@ -425,16 +425,16 @@ uint32_t work_split_last(int phase) {
     if (!e) return 0u;
     return e[0] == 'a' ? 0xffffffffu : (uint32_t)std::atoi(e);
   }();
-  return v ? v : 148u * (phase == 0 ? P2G_CTAS_PER_SM : 5);   // default: as many tiles as CTAs are resident = the launch's final wave
+  return v ? v : 148u * (phase == 0 ? P2G_CTAS_PER_SM : G2P_CTAS_PER_SM);   // default: as many tiles as CTAs are resident = the launch's final wave
 }
 WorkList work_all(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_class, &S->work_counter[phase], nullptr, tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5), work_split_last(phase)};
+  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_class, &S->work_counter[phase], nullptr, tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : G2P_CTAS_PER_SM), work_split_last(phase)};
 }
 // boundary tiles first, then the interior ones; `phase` 0 = P2G, 1 = G2P (work cursor and boundary-done counter of the scalars)
 WorkList work_ordered(SvbHandle* h, int phase, int tail) {
   StepScalars* S = cur_scalars(h);
-  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_class, &S->work_counter[phase], &S->boundary_done[phase], tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : 5), work_split_last(phase)};
+  return WorkList{h->work_list.as<uint32_t>(), (uint32_t)h->tile_cap, S->n_class, &S->work_counter[phase], &S->boundary_done[phase], tail, work_parts(h, phase == 0 ? P2G_CTAS_PER_SM : G2P_CTAS_PER_SM), work_split_last(phase)};
 }
 
 int enqueue_p2g(SvbHandle* h, const StepInputs& in, const WorkList& W, uint32_t grid_cap = 148 * P2G_CTAS_PER_SM) {
@@ -898,7 +898,7 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   static const bool migrate_beside = [] { const char* e = std::getenv("SVB_MIGRATE_BESIDE_G2P"); return !(e && e[0] == '0'); }();
   const bool send_beside_g2p = concurrent && !in.adaptive && migrate_beside;
   if (send_beside_g2p) {   // second stream: the migration sender, gated on the device by G2P's boundary tiles
-    k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0], work_parts(h, 5));
+    k_migrate_send_list<<<32, 256, 0, sb>>>(h->P(src_buf ^ 1), h->energy.as<float>(), S, cut, peers, (uint32_t)h->mb_mig_cap, seq, h->p2p_local + 10, 0, &S->boundary_done[1], &S->n_work[0], work_parts(h, G2P_CTAS_PER_SM));
     LAUNCH_CHECK();
   }
   if (!in.adaptive) {

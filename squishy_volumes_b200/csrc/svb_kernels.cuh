@@ -282,8 +282,9 @@ __global__ void __launch_bounds__(256) k_collide_query(ParticleBuf P, StepScalar
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   int kind = 0;   // 1: a short triangle run (front of the list, one thread each), 2: a long one (back of the list, four lanes each)
   if (i < n) {
-    const uint32_t flags = P.u(PFLAGS)[i];
-    const float x0 = P.f(PX)[i], x1 = P.f(PX + 1)[i], x2 = P.f(PX + 2)[i];
+    const float4 pq0 = P.q(0)[i];   // position, flags
+    const uint32_t flags = __float_as_uint(pq0.w);
+    const float x0 = pq0.x, x1 = pq0.y, x2 = pq0.z;
     if (!(flags & (F_TOMBSTONED | F_GONE))) {
       int first, count;
       bvh_query(M, (int)floorf(x0 / K.leaf_size), (int)floorf(x1 / K.leaf_size), (int)floorf(x2 / K.leaf_size), first, count);
@@ -336,7 +337,8 @@ __global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepS
     V3 p = V3{0.f, 0.f, 0.f};
     int first = 0, count = 0;
     if (have) {
-      p = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+      const float4 pq0 = P.q(0)[i];
+      p = V3{pq0.x, pq0.y, pq0.z};
       bvh_query(M, (int)floorf(p.x / K.leaf_size), (int)floorf(p.y / K.leaf_size), (int)floorf(p.z / K.leaf_size), first, count);
     }
     unsigned long long best[NC];
@@ -367,10 +369,13 @@ __global__ void __launch_bounds__(128) k_collide_cand(ParticleBuf P, const StepS
       closest[c] = b != ~0ull ? M.tri_indices[first + (uint32_t)b] : 0xffffffffu;
     }
     if (have && sub == 0) {
-      V3 vel = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
-      const uint32_t bits = collide_respond<NC>(M, K, dt, p, vel, P.u(PBITS)[i], closest);
-      P.u(PBITS)[i] = bits;
-      P.f(PV)[i] = vel.x; P.f(PV + 1)[i] = vel.y; P.f(PV + 2)[i] = vel.z;
+      float4 pq5 = P.q(5)[i];   // collider bits, original index, v.x, v.y
+      float* vz = &P.f(PV + 2)[i];
+      V3 vel = V3{pq5.z, pq5.w, *vz};
+      const uint32_t bits = collide_respond<NC>(M, K, dt, p, vel, __float_as_uint(pq5.x), closest);
+      pq5.x = __uint_as_float(bits); pq5.z = vel.x; pq5.w = vel.y;
+      P.q(5)[i] = pq5;
+      *vz = vel.z;
     }
   }
 }
@@ -648,8 +653,9 @@ __global__ void __launch_bounds__(256) k_bin(ParticleBuf P, StepScalars* S, SimC
   uint32_t bits = 0u;
   if (i < n) {
     // every load of the row is issued before the flags are looked at: one memory latency instead of two in the chain
-    const uint32_t flags = P.u(PFLAGS)[i];
-    x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
+    const float4 pq0 = P.q(0)[i];   // position, flags
+    const uint32_t flags = __float_as_uint(pq0.w);
+    x = V3{pq0.x, pq0.y, pq0.z};
     bits = HAS_MESH ? P.u(PBITS)[i] : 0u;
     const bool gone = (flags & F_GONE) != 0;   // migrated to a neighbour slab: the row is dropped by this re-bin
     state = gone ? 2 : ((flags & F_TOMBSTONED) ? 1 : 0);
@@ -1275,6 +1281,10 @@ __global__ void __launch_bounds__(256) k_meld(const StepScalars* __restrict__ S,
 // warp — were measured slower: 4-byte cp.async doubles the LSU instructions per particle and the
 // staging buffers cost occupancy; see profiles/README.md r1c-r1g.)
 constexpr int G2P_THREADS = 128;
+#ifndef SVB_G2P_CTAS_PER_SM
+#define SVB_G2P_CTAS_PER_SM 7   // 72 registers (60 bytes of spills) since the particle words come in quads; measured 5 -> 7: G2P 496 -> 477 us at 8 M, 171 -> 157 us on a 2 M dam break; 6 is slower, 8 the same as 7
+#endif
+constexpr int G2P_CTAS_PER_SM = SVB_G2P_CTAS_PER_SM;
 // Reads the particle through src_of from the pre-bin buffer `P`, writes every field of it to slot i of
 // `D` (this is where the physical re-bin happens).
 // slab ranks: a particle whose advanced position left the block columns [lo, hi) is noted in a per-side list of binned
@@ -1292,7 +1302,7 @@ struct BinNext {
   StepScalars* S; TileTable T; BinArrays B;
 };
 template <bool FUSE, bool REDUCE, bool MELDED, bool SLAB, bool BIN>
-__global__ void __launch_bounds__(G2P_THREADS, 5) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
+__global__ void __launch_bounds__(G2P_THREADS, G2P_CTAS_PER_SM) k_g2p(ParticleBuf P, ParticleBuf D, const uint32_t* __restrict__ src_of, float* __restrict__ energy,
                                                         const uint2* __restrict__ group_range, const int* __restrict__ nbr, StepScalars* S,
                                                         const float4* __restrict__ grid, SimConsts K, float dt, MigrateCut mc, BinNext bn,
                                                         const unsigned long long* __restrict__ tile_key, WorkList W) {
@@ -1713,7 +1723,7 @@ __global__ void k_dt_tail(DtState* D, StepScalars* S, DtPeers peers) {
 // position and F — the binning of the next substep (BIN, scenes without a collider mesh) and the per-particle limits of the next
 // substep's LimitTimeStepBeforeForce (limit_time_step.rs:35-182).  One thread per row of the binned buffer, tombstoned rows included.
 #ifndef SVB_ADVANCE_BLOCKS
-#define SVB_ADVANCE_BLOCKS 2   // (3 blocks / SM = 80 registers with 30 bytes of spills: measured the same, 0.288 vs 0.286 ms per adaptive substep)
+#define SVB_ADVANCE_BLOCKS 3   // 80 registers since the particle words come in quads (2 blocks / SM with the word layout)
 #endif
 template <bool BIN>
 __global__ void __launch_bounds__(256, SVB_ADVANCE_BLOCKS) k_advance(ParticleBuf P, float* __restrict__ energy, StepScalars* S, SimConsts K, uint32_t n, DtState* D, BinNext bn, MigrateCut mc) {
@@ -1727,28 +1737,31 @@ __global__ void __launch_bounds__(256, SVB_ADVANCE_BLOCKS) k_advance(ParticleBuf
   int ks = INT32_MAX, ki = INT32_MAX;
   uint32_t live = 0;
   if (i < n) {
-    uint32_t flags = P.u(PFLAGS)[i];
+    const float4 pq0 = P.q(0)[i];   // (every quad of the row is requested before the flags are looked at)
+    const float4 pq1 = P.q(1)[i], pq2 = P.q(2)[i], pq3 = P.q(3)[i], pq4 = P.q(4)[i], pq5 = P.q(5)[i], pq6 = P.q(6)[i], pq7 = P.q(7)[i];
+    const float2 pq8 = *reinterpret_cast<const float2*>(P.q(8) + i);
+    uint32_t flags = __float_as_uint(pq0.w);
     bin_state = 1;
     if (!(flags & F_TOMBSTONED)) {
-      x = V3{P.f(PX)[i], P.f(PX + 1)[i], P.f(PX + 2)[i]};
-      const V3 v = V3{P.f(PV)[i], P.f(PV + 1)[i], P.f(PV + 2)[i]};
+      x = V3{pq0.x, pq0.y, pq0.z};
+      const V3 v = V3{pq5.z, pq5.w, pq6.x};
       M3 C, F;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) { C.m[q] = P.f(PC + q)[i]; F.m[q] = P.f(PF + q)[i]; }
-      const float p0 = P.f(PP0)[i], p1 = P.f(PP1)[i];
+      F.m[0] = pq1.x; F.m[1] = pq1.y; F.m[2] = pq1.z; F.m[3] = pq1.w; F.m[4] = pq2.x; F.m[5] = pq2.y; F.m[6] = pq2.z; F.m[7] = pq2.w; F.m[8] = pq3.x;
+      C.m[0] = pq6.y; C.m[1] = pq6.z; C.m[2] = pq6.w; C.m[3] = pq7.x; C.m[4] = pq7.y; C.m[5] = pq7.z; C.m[6] = pq7.w; C.m[7] = pq8.x; C.m[8] = pq8.y;
+      const float p0 = pq3.w, p1 = pq4.x;
       x = x + v * dt;
       const M3 CF = mul(C, F);
 #pragma unroll
       for (int q = 0; q < 9; ++q) F.m[q] += CF.m[q] * dt;
       float e;
-      if (return_map_and_energy(flags, p0, p1, (flags & F_USE_SAND_ALPHA) ? P.f(PALPHA)[i] : 0.f, F, e)) energy[i] = e;
+      if (return_map_and_energy(flags, p0, p1, (flags & F_USE_SAND_ALPHA) ? pq4.y : 0.f, F, e)) energy[i] = e;
       else { flags |= F_FAILED; atomicOr(&S->sticky_new, 8u); }
       const bool within = x.x > K.domain_min[0] && x.x < K.domain_max[0] && x.y > K.domain_min[1] && x.y < K.domain_max[1] && x.z > K.domain_min[2] && x.z < K.domain_max[2];
       if (!within) flags |= F_TOMBSTONED;
-      P.f(PX)[i] = x.x; P.f(PX + 1)[i] = x.y; P.f(PX + 2)[i] = x.z;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) P.f(PF + q)[i] = F.m[q];
-      P.u(PFLAGS)[i] = flags;
+      P.q(0)[i] = make_float4(x.x, x.y, x.z, __uint_as_float(flags));
+      P.q(1)[i] = make_float4(F.m[0], F.m[1], F.m[2], F.m[3]);
+      P.q(2)[i] = make_float4(F.m[4], F.m[5], F.m[6], F.m[7]);
+      P.f(PF + 8)[i] = F.m[8];
       if (within) {
         bin_state = 0;
         if (mc.list) {   // slab ranks: note the particles whose advanced position left the rank's block columns (like the fused G2P)
@@ -1766,7 +1779,7 @@ __global__ void __launch_bounds__(256, SVB_ADVANCE_BLOCKS) k_advance(ParticleBuf
             }
           }
         }
-        const ParticleLimits l = particle_time_step_limits((flags & F_IS_FLUID) != 0, p0, p1, P.f(PMASS)[i], P.f(PVOL)[i], F, K.h);
+        const ParticleLimits l = particle_time_step_limits((flags & F_IS_FLUID) != 0, p0, p1, pq3.y, pq3.z, F, K.h);
         ks = total_key(l.by_sound);
         ki = total_key(l.by_isolated);
         live = 1;
@@ -1797,10 +1810,10 @@ __global__ void __launch_bounds__(256) k_limit_force(ParticleBuf P, DtState* D, 
   if (i < n) {
     const uint32_t flags = P.u(PFLAGS)[i];
     if (!(flags & (F_TOMBSTONED | F_GONE))) {
+      const float4 pq1 = P.q(1)[i], pq2 = P.q(2)[i], pq3 = P.q(3)[i];
       M3 F;
-#pragma unroll
-      for (int q = 0; q < 9; ++q) F.m[q] = P.f(PF + q)[i];
-      const ParticleLimits l = particle_time_step_limits((flags & F_IS_FLUID) != 0, P.f(PP0)[i], P.f(PP1)[i], P.f(PMASS)[i], P.f(PVOL)[i], F, h);
+      F.m[0] = pq1.x; F.m[1] = pq1.y; F.m[2] = pq1.z; F.m[3] = pq1.w; F.m[4] = pq2.x; F.m[5] = pq2.y; F.m[6] = pq2.z; F.m[7] = pq2.w; F.m[8] = pq3.x;
+      const ParticleLimits l = particle_time_step_limits((flags & F_IS_FLUID) != 0, pq3.w, P.f(PP1)[i], pq3.y, pq3.z, F, h);
       ks = total_key(l.by_sound);
       ki = total_key(l.by_isolated);
       live = 1;
