@@ -522,7 +522,7 @@ int enqueue_meld(SvbHandle* h) {
 // CollectVelocity (+ Advance + Cull when fused) over the tiles of `W`, from particle buffer `src_buf` into `dst_buf` (the caller
 // swaps `cur` once all launches of the substep are queued).  `bin_next`: the fused kernel also bins the advanced positions into the
 // other front set.
-int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next, const WorkList& W, int src_buf, const MigrateCut* cut = nullptr, uint32_t grid_cap = 148 * 12) {
+int enqueue_g2p(SvbHandle* h, bool has_mesh, bool fuse, float dt, bool bin_next, const WorkList& W, int src_buf, const MigrateCut* cut = nullptr, uint32_t grid_cap = 148 * 16) {
   cudaStream_t s = h->stream;
   StepScalars* S = cur_scalars(h);
   auto& F = h->fs[h->s_cur];

@@ -945,7 +945,10 @@ __device__ __forceinline__ void quad_weights(float shifted, float* w) {
 #ifndef SVB_P2G_CTAS_PER_SM
 #define SVB_P2G_CTAS_PER_SM 7   // 71 registers, 24 KB of shared memory per CTA; measured: 6 -> 81 us, 7 -> 79 us, 8 (spills) -> 88 us at 1 M
 #endif
-constexpr int P2G_WARPS = 4;
+#ifndef SVB_P2G_WARPS
+#define SVB_P2G_WARPS 4
+#endif
+constexpr int P2G_WARPS = SVB_P2G_WARPS;
 constexpr int P2G_CTAS_PER_SM = SVB_P2G_CTAS_PER_SM;
 constexpr int TILE_NODES = 216;
 constexpr int STAGE_STRIDE = 20;  // floats per staged particle (16 used + the cell id): 16-byte aligned rows, conflict-free float4 stores
@@ -982,6 +985,7 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
   return *reinterpret_cast<float2*>(&d);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void red_add_v4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -1280,9 +1284,12 @@ __global__ void __launch_bounds__(256) k_meld(const StepScalars* __restrict__ S,
 // (Two software-pipelined variants — TMA bulk tile copies + cp.async particle staging, per CTA and per
 // warp — were measured slower: 4-byte cp.async doubles the LSU instructions per particle and the
 // staging buffers cost occupancy; see profiles/README.md r1c-r1g.)
-constexpr int G2P_THREADS = 128;
+#ifndef SVB_G2P_THREADS
+#define SVB_G2P_THREADS 64   // two warps per CTA, 14 CTAs per SM: a CTA's serial sections (claim, tile load, barriers) stall two warps instead of four; measured 128 x 7 -> 64 x 14: G2P 471 -> 439 us at 8 M
+#endif
+constexpr int G2P_THREADS = SVB_G2P_THREADS;
 #ifndef SVB_G2P_CTAS_PER_SM
-#define SVB_G2P_CTAS_PER_SM 7   // 72 registers (60 bytes of spills) since the particle words come in quads; measured 5 -> 7: G2P 496 -> 477 us at 8 M, 171 -> 157 us on a 2 M dam break; 6 is slower, 8 the same as 7
+#define SVB_G2P_CTAS_PER_SM 14   // (x 64 threads; 7 x 128 before) 72 registers (60 bytes of spills) since the particle words come in quads; measured 5 -> 7: G2P 496 -> 477 us at 8 M, 171 -> 157 us on a 2 M dam break; 6 is slower, 8 the same as 7
 #endif
 constexpr int G2P_CTAS_PER_SM = SVB_G2P_CTAS_PER_SM;
 // Reads the particle through src_of from the pre-bin buffer `P`, writes every field of it to slot i of
@@ -1334,9 +1341,9 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_CTAS_PER_SM) k_g2p(ParticleBu
         const uint32_t c = s_cnt[q];
         if (c) { atomicAdd(&bn.B.cell_count[(size_t)s_cache[q >> 6] * 64 + (q & 63)], c); s_cnt[q] = 0u; }
       }
-      if (threadIdx.x >= 64 && threadIdx.x < 64 + 27) {
-        const uint32_t m = s_touch[threadIdx.x - 64];
-        if (m) { atomicOr(&bn.B.tile_touch[s_cache[threadIdx.x - 64]], m); s_touch[threadIdx.x - 64] = 0u; }
+      if (threadIdx.x < 27) {
+        const uint32_t m = s_touch[threadIdx.x];
+        if (m) { atomicOr(&bn.B.tile_touch[s_cache[threadIdx.x]], m); s_touch[threadIdx.x] = 0u; }
       }
     }
     if (threadIdx.x < 8) {
@@ -1372,12 +1379,33 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_CTAS_PER_SM) k_g2p(ParticleBu
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     // a warp's 32 slots start on a 128-byte line of the destination arrays: every store of a warp is one line, not two (G2P 80 -> 77 us at 1 M)
+#ifndef SVB_G2P_PF
+#define SVB_G2P_PF 1   // 1: the rows of the warp's NEXT iteration are requested into L2 while this one computes (row indices two iterations ahead)
+#endif
+#if SVB_G2P_PF
+    const uint32_t i_first = (start & ~31u) + threadIdx.x;
+    uint32_t s_cur = (i_first >= start && i_first < end) ? src_of[i_first] : 0u;
+    uint32_t s_nxt = i_first + blockDim.x < end ? src_of[i_first + blockDim.x] : 0u;
+#endif
     for (uint32_t base = (start & ~31u) + (threadIdx.x & ~31u); base < end; base += blockDim.x) {   // warp-uniform trip count (bin_warp is warp-collective)
       const uint32_t i = base + lane;
       int bin_state = 2;
       V3 bin_x = V3{0.f, 0.f, 0.f};
+#if SVB_G2P_PF
+      const uint32_t si_pf = s_cur;
+      s_cur = s_nxt;
+      s_nxt = i + 2 * blockDim.x < end ? src_of[i + 2 * blockDim.x] : 0u;
+      if (i + blockDim.x < end) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) prefetch_l2(P.q(q) + s_cur);
+      }
+#endif
       if (i >= start && i < end) {
+#if SVB_G2P_PF
+      const uint32_t si = si_pf;
+#else
       const uint32_t si = src_of[i];   // (fetching the next iteration's row index one iteration ahead: measured neutral, r1n)
+#endif
       // quads 0..5 of the particle (svb_device.cuh: Field): position, flags, F and the words this thread merely carries — six 16-byte
       // gathers instead of thirty 4-byte ones (v and C are replaced, quads 6..8 are not read)
       const float4 pq0 = P.q(0)[si], pq1 = P.q(1)[si], pq2 = P.q(2)[si], pq3 = P.q(3)[si], pq4 = P.q(4)[si];
