@@ -282,11 +282,11 @@ def main():
     scene.frame_input.consts.frames_per_second = 1  # one long frame: the bench never crosses a keyframe boundary
     dt = scene.time_step
     max_dt = 4.0 * dt if args.adaptive else dt
-    state_mb = scene.n / max(world_env, 1) * 136 / 1e6
+    state_mb = scene.n / max(world_env, 1) * 144 / 1e6   # 9 quads of 16 bytes per particle (svb_device.cuh)
     config = {"workload": f"{args.scene}: {scene.description}", "particles_total": scene.n, "particles_per_gpu": scene.n // max(world_env, 1),
               "time_step": dt, "adaptive_time_steps": bool(args.adaptive), "max_time_step": max_dt,
               "rebin": "every substep (counting sort on (tile, cell); the physical permutation rides on the G2P write)",
-              "l2": f"per-GPU particle state {state_mb:.0f} MB (136 B/particle) + grid vs the 126 MB L2: " + ("larger than L2, no explicit flush" if state_mb > 126 else "NOT larger than L2 - the HBM fractions of this run are partly L2 numbers"),
+              "l2": f"per-GPU particle state {state_mb:.0f} MB (144 B/particle: 34 words in 9 quads) + grid vs the 126 MB L2: " + ("larger than L2, no explicit flush" if state_mb > 126 else "NOT larger than L2 - the HBM fractions of this run are partly L2 numbers"),
               "decomposition": "single GPU" if world_env == 1 else f"{world_env} slabs along x ({'weak: the scene grows with N' if weak else 'strong: one scene split N ways'}); halo-column sums + particle migration every substep over peer memory (NVLink, CUDA IPC), NCCL fallback"}
     scaling = "weak" if (weak or world_env == 1) else "strong"
 

@@ -948,14 +948,14 @@ int substep_slab_p2p(SvbHandle* h, const StepInputs& in) {
   return 0;
 }
 
-// H2D of a wire-format particle state into the current SoA buffer (from_io_state, cpu/src/cpu_state.rs:26-69)
+// H2D of a wire-format particle state into the current particle buffer (from_io_state, cpu/src/cpu_state.rs:26-69)
 int load_particles(SvbHandle* h, const SvbParticles* p) {
   const uint32_t n = h->n;
   if (!n) return 0;
   if (!p->flags || !p->mass || !p->initial_volume || !p->mu_or_bulk_modulus || !p->lambda_or_exponent || !p->positions || !p->position_gradients || !p->velocities ||
       !p->velocity_gradients)
     return fail(h, SVB_BAD_ARGUMENT, "a required particle array is NULL");
-  // stage each wire array through the spare particle buffer and transpose it into the SoA
+  // stage each wire array through the spare particle buffer and transpose it into the quads
   ParticleBuf P = h->Pc();
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();
   const uint32_t blocks = blocks_for(n, 256);

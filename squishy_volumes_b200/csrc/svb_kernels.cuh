@@ -60,7 +60,7 @@ __device__ __forceinline__ int base_node_fast(float x, float h, float inv_h) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// wire <-> SoA
+// wire <-> particle quads
 // (all words as u32: a flag / bit word must not pass through a float register as a signalling NaN pattern would still be preserved
 // by LDG / STG, but typed loads keep this obvious)
 template <int K>
@@ -858,7 +858,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* a, const uint32_t
 //   j = slot_first[slot] + cell_offset[slot*64 + cell] + rank      (slot = the tile's table slot; tombstoned: n_live + rank)
 // Only the inverse map src_of[j] = i is materialised here (4 B per particle).  P2G gathers its inputs
 // through it and G2P writes its results — and the fields it merely carries — to slot j of the other
-// buffer, so the physical permutation of the 136-byte state costs no pass of its own: consecutive
+// buffer, so the physical permutation of the 144-byte state costs no pass of its own: consecutive
 // slots come from (nearly) consecutive rows of the previous order, the gathers stay coalesced.
 // The same launch also clears the grid tiles of this substep (blocks beyond the particle range).
 // With `prep.blocks` > 0 the last blocks also prepare the OTHER front set for the G2P of this substep, which bins the advanced
