@@ -981,8 +981,9 @@ int load_particles(SvbHandle* h, const SvbParticles* p) {
   if (p->elastic_energies) CK(cudaMemcpyAsync(h->energy.p, p->elastic_energies, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   k_iota_orig<<<blocks, 256, 0, h->stream>>>(P, n, 0);
   LAUNCH_CHECK();
-  h->initial_positions.assign((size_t)n * 3, 0.f);
-  if (p->initial_positions) std::memcpy(h->initial_positions.data(), p->initial_positions, (size_t)n * 12);
+  // (host work behind the queued copies: it overlaps the H2D transfers)
+  if (p->initial_positions) h->initial_positions.assign(p->initial_positions, p->initial_positions + (size_t)n * 3);
+  else h->initial_positions.assign((size_t)n * 3, 0.f);
   return 0;
 }
 
@@ -1422,8 +1423,8 @@ int32_t svb_download(SvbHandle* h, SvbParticles* out) {
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(out->elastic_energies, h->scratch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   }
+  if (out->initial_positions) std::memcpy(out->initial_positions, h->initial_positions.data(), (size_t)n * 12);   // while the D2H copies run
   CK(cudaStreamSynchronize(h->stream));
-  if (out->initial_positions) std::memcpy(out->initial_positions, h->initial_positions.data(), (size_t)n * 12);
   return 0;
 }
 
