@@ -10,7 +10,9 @@ reference formulas for the cases small enough to do so:
   say it is NOT on, so collide.rs:180-203 pushes it out with v -= to_p / dt;
 * the three-triangle fan `simple2` (:297-360), the torus with a particle lattice (:362-420), the 512 `many_positions`
   (test_util.rs:112) with the canonical position gradients (:632) and the captured positions + bits of test_util.rs:678:
-  oracle and CUDA path must agree (bits exactly)."""
+  oracle and CUDA path must agree (bits exactly);
+* the node sets of gpu/src/prepare_grid/test.rs (`test_single`, `test_simple`, `specific`): the active (node, collider bits) set is
+  exactly the union of the particles' 27-node stencils."""
 import os
 
 import numpy as np
@@ -123,7 +125,58 @@ def test_many_positions_conserve_mass_and_momentum_oracle():
     assert float(out.grid_nodes.masses.sum(dtype=np.float64)) == pytest.approx(float(sc.io_state.particles.mass.sum(dtype=np.float64)), rel=1e-5)
 
 
+def node_set_by_hand(positions, bits, h):
+    """get_node_set of the reference's tests (gpu/src/test_util.rs): every particle activates the 27 nodes base + {0,1,2}^3 of its
+    collider-bits layer, base = floor(x / h - 1/2) in f32 like cpu/src/kernels.rs:46-49."""
+    out = set()
+    hf = np.float32(h)
+    for x, b in zip(np.asarray(positions, np.float32).reshape(-1, 3), bits):
+        base = np.floor(x / hf - np.float32(0.5)).astype(np.int64)
+        for i in range(3):
+            for j in range(3):
+                for k in range(3):
+                    out.add((int(base[0]) + i, int(base[1]) + j, int(base[2]) + k, int(b)))
+    return out
+
+
+def prepare_grid_cases():
+    """gpu/src/prepare_grid/test.rs:106-152 (`test_single`, `test_simple`) and :179-189 (`specific`: the captured positions + bits)."""
+    yield "single", [[0.0, 0.0, 0.0]], [0], 1.0
+    corners = [[sx, sy, sz] for sx in (-0.5, 0.5) for sy in (-0.5, 0.5) for sz in (-0.5, 0.5)]
+    yield "simple", corners, [0] * 8, 1.1
+    # (the captured bits belong to the torus of collide/test.rs; this replay has no collider mesh, so the Collide phase that precedes
+    #  UpdateGridNodes in the substep clears them — collide.rs:55-58 — and the expected layer is 0; the bits themselves are replayed
+    #  WITH the torus in "captured positions" below)
+    yield "specific", REF["specific_positions"], [0] * len(REF["specific_positions"]), 0.5
+
+
+def check_prepare_grid(cls):
+    for name, pos, bits, h in prepare_grid_cases():
+        sc = make_scene(pos, h, bits=bits)
+        out = one_substep(cls, sc, store_grid=True)
+        g = out.grid_nodes
+        keep = g.contributor_counts > 0
+        got = {(int(r[0]), int(r[1]), int(r[2]), int(b)) for r, b in zip(g.node_ids[keep], g.collider_bits[keep])}
+        want = node_set_by_hand(pos, bits, h)
+        assert got == want, (name, len(got), len(want))
+        if name == "single":
+            assert want == {(i, j, k, 0) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)}     # floor(0 - 1/2) = -1
+        if name == "simple":
+            assert len(want) == 27                                                                      # +-0.5 / 1.1 - 0.5 = -0.95, -0.05: every base is -1
+
+
+def test_prepare_grid_node_sets_oracle():
+    import oracle.oracle as orc
+    check_prepare_grid(orc.OracleState)
+
+
 # ------------------------------------------------------------------------------------------------ CUDA path (GPU box)
+@pytest.mark.gpu
+def test_prepare_grid_node_sets_cuda():
+    from squishy_volumes_b200.state import B200State
+    check_prepare_grid(B200State)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("v", [(0.0, 0.0, 0.0), (1.0, -2.0, 3.0)])
 def test_single_undeformed_particle_known_answer_cuda(v):
