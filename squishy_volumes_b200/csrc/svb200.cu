@@ -747,7 +747,6 @@ int substep_slab(SvbHandle* h, const StepInputs& in) {
 // The host's (lagged) look at the front-half scalars of the oldest unchecked substep of a peer-memory slab rank.
 //   0: fine   2: that substep was a no-op (an earlier one stopped the run); every substep queued since is forgotten
 int process_front_p2p(SvbHandle* h) {
-  cudaStream_t s = h->stream;
   SvbHandle::FrontLag& L = h->lag[h->lag_done % 4];
   CK(cudaEventSynchronize(L.ev));
   const StepScalars& r = *L.host;
