@@ -958,25 +958,31 @@ int load_particles(SvbHandle* h, const SvbParticles* p) {
   ParticleBuf P = h->Pc();
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();
   const uint32_t blocks = blocks_for(n, 256);
-  size_t stage_off = 0;  // every wire array gets its own region of the spare buffer (33 n words <= 36 cap): no sync in between
-  auto vec = [&](const void* src, int field, int k) -> int {
-    if (!src) return 0;
-    float* st = stagef + stage_off;
-    stage_off += (size_t)h->cap * k;
-    CK(cudaMemcpyAsync(st, src, (size_t)n * k * 4, cudaMemcpyHostToDevice, h->stream));
-    if (k == 1) k_wire_to_soa<1><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(st), P, field, n);
-    else if (k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(st), P, field, n);
-    else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(st), P, field, n);
+  // every wire array gets its own region of the spare buffer (33 n words <= 36 cap): all copies are queued back to back (the copy
+  // engine never waits for a transpose), then the transposes
+  struct Wire { const void* src; int field, k; float* st; };
+  const Wire wires[] = {{p->flags, PFLAGS, 1, nullptr}, {p->mass, PMASS, 1, nullptr}, {p->initial_volume, PVOL, 1, nullptr}, {p->mu_or_bulk_modulus, PP0, 1, nullptr},
+                        {p->lambda_or_exponent, PP1, 1, nullptr}, {p->sand_alpha, PALPHA, 1, nullptr}, {p->viscosity_dynamic, PVD, 1, nullptr}, {p->viscosity_bulk, PVB, 1, nullptr},
+                        {p->collider_bits, PBITS, 1, nullptr}, {p->positions, PX, 3, nullptr}, {p->velocities, PV, 3, nullptr}, {p->velocity_gradients, PC, 9, nullptr},
+                        {p->position_gradients, PF, 9, nullptr}};
+  Wire queued[sizeof(wires) / sizeof(wires[0])];
+  int n_queued = 0;
+  size_t stage_off = 0;
+  for (const Wire& w : wires) {
+    if (!w.src) continue;
+    Wire q = w;
+    q.st = stagef + stage_off;
+    stage_off += (size_t)h->cap * w.k;
+    CK(cudaMemcpyAsync(q.st, w.src, (size_t)n * w.k * 4, cudaMemcpyHostToDevice, h->stream));
+    queued[n_queued++] = q;
+  }
+  for (int j = 0; j < n_queued; ++j) {
+    const Wire& q = queued[j];
+    if (q.k == 1) k_wire_to_soa<1><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(q.st), P, q.field, n);
+    else if (q.k == 3) k_wire_to_soa<3><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(q.st), P, q.field, n);
+    else k_wire_to_soa<9><<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const uint32_t*>(q.st), P, q.field, n);
     LAUNCH_CHECK();
-    return 0;
-  };
-  auto scalar = [&](const void* src, int field) -> int { return vec(src, field, 1); };
-  int rc = 0;
-  if ((rc = scalar(p->flags, PFLAGS)) || (rc = scalar(p->mass, PMASS)) || (rc = scalar(p->initial_volume, PVOL)) || (rc = scalar(p->mu_or_bulk_modulus, PP0)) ||
-      (rc = scalar(p->lambda_or_exponent, PP1)) || (rc = scalar(p->sand_alpha, PALPHA)) || (rc = scalar(p->viscosity_dynamic, PVD)) || (rc = scalar(p->viscosity_bulk, PVB)) ||
-      (rc = scalar(p->collider_bits, PBITS)) || (rc = vec(p->positions, PX, 3)) || (rc = vec(p->velocities, PV, 3)) || (rc = vec(p->velocity_gradients, PC, 9)) ||
-      (rc = vec(p->position_gradients, PF, 9)))
-    return rc;
+  }
   if (p->elastic_energies) CK(cudaMemcpyAsync(h->energy.p, p->elastic_energies, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   k_iota_orig<<<blocks, 256, 0, h->stream>>>(P, n, 0);
   LAUNCH_CHECK();
@@ -1396,32 +1402,35 @@ int32_t svb_download(SvbHandle* h, SvbParticles* out) {
   ParticleBuf P = h->Pc();
   float* stagef = h->pbuf[h->cur ^ 1].as<float>();  // the spare buffer is free between substeps
   const uint32_t blocks = blocks_for(n, 256);
-  size_t stage_off = 0;  // one region per field (33 n words in total): all gathers and copies queue back to back
-  auto field = [&](void* dst, int word, int k) -> int {
-    if (!dst) return 0;
-    float* st = stagef + stage_off;
-    stage_off += (size_t)h->cap * k;
-    if (k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(P, word, reinterpret_cast<uint32_t*>(st), n);
-    else if (k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(P, word, reinterpret_cast<uint32_t*>(st), n);
-    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(P, word, reinterpret_cast<uint32_t*>(st), n);
+  // one region of the spare buffer per field (33 n words in total): all gathers into original order are queued first, then the
+  // copies back to back (the copy engine never waits for a gather)
+  struct Wire { void* dst; int word, k; float* st; };
+  const Wire wires[] = {{out->flags, PFLAGS, 1, nullptr}, {out->mass, PMASS, 1, nullptr}, {out->initial_volume, PVOL, 1, nullptr}, {out->mu_or_bulk_modulus, PP0, 1, nullptr},
+                        {out->lambda_or_exponent, PP1, 1, nullptr}, {out->sand_alpha, PALPHA, 1, nullptr}, {out->viscosity_dynamic, PVD, 1, nullptr}, {out->viscosity_bulk, PVB, 1, nullptr},
+                        {out->collider_bits, PBITS, 1, nullptr}, {out->positions, PX, 3, nullptr}, {out->velocities, PV, 3, nullptr}, {out->velocity_gradients, PC, 9, nullptr},
+                        {out->position_gradients, PF, 9, nullptr}};
+  Wire queued[sizeof(wires) / sizeof(wires[0])];
+  int n_queued = 0;
+  size_t stage_off = 0;
+  for (const Wire& w : wires) {
+    if (!w.dst) continue;
+    Wire q = w;
+    q.st = stagef + stage_off;
+    stage_off += (size_t)h->cap * w.k;
+    if (q.k == 1) k_soa_to_wire<1><<<blocks, 256, 0, h->stream>>>(P, q.word, reinterpret_cast<uint32_t*>(q.st), n);
+    else if (q.k == 3) k_soa_to_wire<3><<<blocks, 256, 0, h->stream>>>(P, q.word, reinterpret_cast<uint32_t*>(q.st), n);
+    else k_soa_to_wire<9><<<blocks, 256, 0, h->stream>>>(P, q.word, reinterpret_cast<uint32_t*>(q.st), n);
     LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(dst, st, (size_t)n * k * 4, cudaMemcpyDeviceToHost, h->stream));
-    return 0;
-  };
-  int rc = 0;
-  if ((rc = field(out->flags, PFLAGS, 1)) || (rc = field(out->mass, PMASS, 1)) || (rc = field(out->initial_volume, PVOL, 1)) ||
-      (rc = field(out->mu_or_bulk_modulus, PP0, 1)) || (rc = field(out->lambda_or_exponent, PP1, 1)) || (rc = field(out->sand_alpha, PALPHA, 1)) ||
-      (rc = field(out->viscosity_dynamic, PVD, 1)) || (rc = field(out->viscosity_bulk, PVB, 1)) || (rc = field(out->collider_bits, PBITS, 1)) ||
-      (rc = field(out->positions, PX, 3)) || (rc = field(out->velocities, PV, 3)) || (rc = field(out->velocity_gradients, PC, 9)) ||
-      (rc = field(out->position_gradients, PF, 9)))
-    return rc;
+    queued[n_queued++] = q;
+  }
   // energies live in their own array: park them in the node-mask scratch
   if (out->elastic_energies) {
     CK(h->scratch.ensure((size_t)h->cap * 4));
     k_array_to_wire<<<blocks, 256, 0, h->stream>>>(h->energy.as<float>(), P, h->scratch.as<float>(), n);
     LAUNCH_CHECK();
-    CK(cudaMemcpyAsync(out->elastic_energies, h->scratch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   }
+  for (int j = 0; j < n_queued; ++j) CK(cudaMemcpyAsync(queued[j].dst, queued[j].st, (size_t)n * queued[j].k * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out->elastic_energies) CK(cudaMemcpyAsync(out->elastic_energies, h->scratch.p, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   if (out->initial_positions) std::memcpy(out->initial_positions, h->initial_positions.data(), (size_t)n * 12);   // while the D2H copies run
   CK(cudaStreamSynchronize(h->stream));
   return 0;
