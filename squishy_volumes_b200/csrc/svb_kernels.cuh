@@ -1379,19 +1379,14 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_CTAS_PER_SM) k_g2p(ParticleBu
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     // a warp's 32 slots start on a 128-byte line of the destination arrays: every store of a warp is one line, not two (G2P 80 -> 77 us at 1 M)
-#ifndef SVB_G2P_PF
-#define SVB_G2P_PF 1   // 1: the rows of the warp's NEXT iteration are requested into L2 while this one computes (row indices two iterations ahead)
-#endif
-#if SVB_G2P_PF
+    // the rows of the warp's NEXT iteration are requested into L2 while this one computes (row indices two iterations ahead)
     const uint32_t i_first = (start & ~31u) + threadIdx.x;
     uint32_t s_cur = (i_first >= start && i_first < end) ? src_of[i_first] : 0u;
     uint32_t s_nxt = i_first + blockDim.x < end ? src_of[i_first + blockDim.x] : 0u;
-#endif
     for (uint32_t base = (start & ~31u) + (threadIdx.x & ~31u); base < end; base += blockDim.x) {   // warp-uniform trip count (bin_warp is warp-collective)
       const uint32_t i = base + lane;
       int bin_state = 2;
       V3 bin_x = V3{0.f, 0.f, 0.f};
-#if SVB_G2P_PF
       const uint32_t si_pf = s_cur;
       s_cur = s_nxt;
       s_nxt = i + 2 * blockDim.x < end ? src_of[i + 2 * blockDim.x] : 0u;
@@ -1399,13 +1394,8 @@ __global__ void __launch_bounds__(G2P_THREADS, G2P_CTAS_PER_SM) k_g2p(ParticleBu
 #pragma unroll
         for (int q = 0; q < 6; ++q) prefetch_l2(P.q(q) + s_cur);
       }
-#endif
       if (i >= start && i < end) {
-#if SVB_G2P_PF
       const uint32_t si = si_pf;
-#else
-      const uint32_t si = src_of[i];   // (fetching the next iteration's row index one iteration ahead: measured neutral, r1n)
-#endif
       // quads 0..5 of the particle (svb_device.cuh: Field): position, flags, F and the words this thread merely carries — six 16-byte
       // gathers instead of thirty 4-byte ones (v and C are replaced, quads 6..8 are not read)
       const float4 pq0 = P.q(0)[si], pq1 = P.q(1)[si], pq2 = P.q(2)[si], pq3 = P.q(3)[si], pq4 = P.q(4)[si];
